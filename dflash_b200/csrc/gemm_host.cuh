@@ -1,0 +1,152 @@
+// Host side of the skinny GEMM: TMA tensor maps (driver entry point fetched through the runtime,
+// so the library does not link libcuda) and the PDL launch.
+#pragma once
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "gemm_skinny.cuh"
+
+namespace dfl {
+
+void set_error(const char* fmt, ...);  // api.cu
+
+inline PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  return fn;
+}
+
+// Row-major bf16 matrix [rows, cols] (cols contiguous, row pitch ld elements) tiled as
+// [box_rows x 64] boxes with the 128-byte swizzle the UMMA descriptors in ptx.cuh expect.
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, long long rows, long long cols,
+                          long long ld, int box_rows) {
+  PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
+  if (!fn) return -2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) {
+    set_error("tensor map: base/pitch must be 16-byte aligned");
+    return -1;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%lld ld=%lld box=%d)",
+              static_cast<int>(r), rows, cols, ld, box_rows);
+    return -3;
+  }
+  return 0;
+}
+
+struct GemmPlan {
+  CUtensorMap tmW;
+  CUtensorMap tmX;
+  GemmArgs args;
+  int mb;     // UMMA N (padded activation rows): 16, 32, 64, 128, 256
+  int mode;   // GemmMode
+  int grid;
+  int max_slots;  // partial slots the consumer must allocate
+};
+
+// Largest number of partial slots any tile can get when T units are cut into G ranges.
+inline int max_slots_for(int n_tiles, int k_blocks, int grid) {
+  const long long T = static_cast<long long>(n_tiles) * k_blocks;
+  int mx = 1;
+  for (int t = 0; t < n_tiles; ++t) {
+    int s = tile_num_slots(t, k_blocks, T, grid);
+    if (s > mx) mx = s;
+  }
+  return mx;
+}
+
+template <int MB, int MODE>
+inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pdl) {
+  using Cfg = GemmCfg<MB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<MB, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<MB, MODE>, p.tmW, p.tmX, p.args);
+}
+
+inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl) {
+  if (p.mode == kModeArgmax) {
+    switch (p.mb) {
+      case 16: return launch_gemm_t<16, kModeArgmax>(p, stream, pdl);
+      case 32: return launch_gemm_t<32, kModeArgmax>(p, stream, pdl);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  switch (p.mb) {
+    case 16: return launch_gemm_t<16, kModePartials>(p, stream, pdl);
+    case 32: return launch_gemm_t<32, kModePartials>(p, stream, pdl);
+    case 64: return launch_gemm_t<64, kModePartials>(p, stream, pdl);
+    case 128: return launch_gemm_t<128, kModePartials>(p, stream, pdl);
+    case 256: return launch_gemm_t<256, kModePartials>(p, stream, pdl);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Fill a plan. W: [w_rows_total, K] bf16 (pitch K); the GEMM covers weight rows [w_row0, w_row0+N).
+// X: [x_rows_total, K] bf16 (pitch K); activation rows [x_row0, x_row0+mb) feed the MMA.
+inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, int w_row0, int N, int K,
+                          const void* X, int x_rows_total, int x_row0, int mb, int m_valid, int mode,
+                          int grid) {
+  memset(p, 0, sizeof(*p));
+  if (K % kTileK != 0) { set_error("gemm: K=%d must be a multiple of %d", K, kTileK); return -1; }
+  if (!(mb == 16 || mb == 32 || mb == 64 || mb == 128 || mb == 256)) {
+    set_error("gemm: mb=%d unsupported", mb);
+    return -1;
+  }
+  if (mode == kModeArgmax && mb > 32) { set_error("gemm: argmax mode needs mb<=32"); return -1; }
+  if (x_row0 + mb > x_rows_total) { set_error("gemm: activation buffer too small"); return -1; }
+  int rc = make_tmap_bf16(&p->tmW, W, w_rows_total, K, K, kTileN);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&p->tmX, X, x_rows_total, K, K, mb);
+  if (rc) return rc;
+  p->mb = mb;
+  p->mode = mode;
+  p->args.n_tiles = (N + kTileN - 1) / kTileN;
+  p->args.k_blocks = K / kTileK;
+  p->args.N = N;
+  p->args.w_row0 = w_row0;
+  p->args.x_row0 = x_row0;
+  p->args.m_valid = m_valid;
+  const long long T = static_cast<long long>(p->args.n_tiles) * p->args.k_blocks;
+  if (mode == kModeArgmax) {
+    p->grid = grid < p->args.n_tiles ? grid : p->args.n_tiles;
+    p->max_slots = 1;
+  } else {
+    p->grid = static_cast<long long>(grid) < T ? grid : static_cast<int>(T);
+    p->max_slots = max_slots_for(p->args.n_tiles, p->args.k_blocks, p->grid);
+  }
+  return 0;
+}
+
+}  // namespace dfl

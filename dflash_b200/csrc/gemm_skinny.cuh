@@ -1,0 +1,311 @@
+// Weight-streaming "skinny" GEMM for the DFlash draft step (sm_100a, tcgen05 + TMEM + TMA).
+//
+//   Y[m, n] = sum_k X[m, k] * W[n, k]        X: [rows<=MB, K] bf16, W: [N, K] bf16 (nn.Linear layout)
+//
+// The draft step has 16..256 activation rows against 10^7..10^9 weight elements, so the kernel is an
+// HBM stream of W. It runs swap-AB: a 128-row slab of W is the UMMA "A" operand (M=128), the MB
+// activation rows are the UMMA "B" operand (N=MB), and the fp32 accumulator D[128 x MB] lives in
+// TMEM. One elected thread issues tcgen05.mma; one elected thread issues TMA; four warps drain TMEM.
+//
+// Work split ("stream-K"): the (n-tile, k-block) grid is flattened n-major and cut into gridDim.x
+// equal contiguous unit ranges, so every CTA streams the same number of bytes regardless of N/128.
+// A CTA that ends inside a tile writes an fp32 partial into slot (cta - first_cta_of_tile); the
+// consumer kernel sums the slots in slot order (deterministic, no atomics).
+//
+// Programmatic dependent launch: weights never depend on the previous kernel, so the producer
+// issues the first kStages W tiles BEFORE griddepcontrol.wait and only the activation tiles after
+// it. The HBM pipe therefore stays full across kernel boundaries.
+//
+// Replaces the reference's nn.Linear call sites on the hot path: model/dflash.py:70-76,101,177,
+// Qwen3MLP (transformers) via :143, and target.lm_head at :238-245.
+#pragma once
+#include "ptx.cuh"
+
+namespace dfl {
+
+constexpr int kTileN = 128;   // weight rows per tile (UMMA M)
+constexpr int kTileK = 64;    // bf16 elements per k-block (= one 128-byte swizzle row)
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;  // warps 0-3 epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc
+
+enum GemmMode : int {
+  kModePartials = 0,  // write fp32 partial sums to ws[slot][m][n]
+  kModeArgmax = 1,    // whole tiles per CTA; per-CTA (max, argmax) of the bf16-rounded logits
+};
+
+struct GemmArgs {
+  int n_tiles;    // ceil(N / 128)
+  int k_blocks;   // K / 64
+  int N;          // weight rows in range (output columns)
+  int w_row0;     // first weight row of the range inside the TMA tensor
+  int x_row0;     // first activation row inside the activation TMA tensor
+  int m_valid;    // activation rows that are written out (<= MB)
+  // kModePartials
+  float* ws;          // [slots][ws_rows][ws_ld]
+  int ws_rows;
+  long long ws_ld;
+  // kModeArgmax
+  float* cand_val;            // [gridDim.x][MB]
+  int* cand_idx;              // [gridDim.x][MB]
+  __nv_bfloat16* logits;      // optional [m_valid][logits_ld] (bf16-rounded), may be null
+  long long logits_ld;
+};
+
+// The CTA that owns flat unit x when T units are cut into G ranges [floor(g*T/G), floor((g+1)*T/G)).
+__host__ __device__ inline int cta_of_unit(long long x, long long T, long long G) {
+  return static_cast<int>(((x + 1) * G - 1) / T);
+}
+__host__ __device__ inline long long unit_begin(long long g, long long T, long long G) {
+  return g * T / G;
+}
+// Number of partial slots tile t has (>= 1), and the first CTA that touches it.
+__host__ __device__ inline int tile_first_cta(int t, int k_blocks, long long T, long long G) {
+  return cta_of_unit(static_cast<long long>(t) * k_blocks, T, G);
+}
+__host__ __device__ inline int tile_num_slots(int t, int k_blocks, long long T, long long G) {
+  return cta_of_unit(static_cast<long long>(t + 1) * k_blocks - 1, T, G) -
+         tile_first_cta(t, k_blocks, T, G) + 1;
+}
+
+template <int MB>
+struct GemmCfg {
+  static constexpr int kWBytes = kTileN * kTileK * 2;   // 16 KB
+  static constexpr int kXBytes = MB * kTileK * 2;
+  static constexpr int kStageBytes = kWBytes + kXBytes;
+  // keep a CTA under ~110 KB so the PDL successor's CTA can be co-resident on the SM
+  static constexpr int kStages = MB <= 16 ? 6 : MB <= 32 ? 5 : MB <= 64 ? 4 : MB <= 128 ? 3 : 4;
+  static constexpr int kTmemCols = (2 * MB < 32) ? 32 : 2 * MB;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int MB, int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                   const GemmArgs a) {
+  using Cfg = GemmCfg<MB>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sW = smem;
+  uint8_t* sX = smem + S * Cfg::kWBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const long long T = static_cast<long long>(a.n_tiles) * a.k_blocks;
+  const long long G = gridDim.x;
+  long long u0, u1;
+  if (MODE == kModeArgmax) {  // whole tiles only
+    u0 = (blockIdx.x * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
+    u1 = ((blockIdx.x + 1) * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
+  } else {
+    u0 = unit_begin(blockIdx.x, T, G);
+    u1 = unit_begin(blockIdx.x + 1, T, G);
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 5) {
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Let the next kernel in the stream start its own prologue / weight prefetch right away.
+  pdl_trigger();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t polW = l2_policy_evict_first();
+      const uint64_t polX = l2_policy_evict_last();
+      const long long n_units = u1 - u0;
+      const int npre = n_units < S ? static_cast<int>(n_units) : S;
+      // weight tiles first: they do not depend on the predecessor kernel
+      for (int i = 0; i < npre; ++i) {
+        const long long u = u0 + i;
+        const int tile = static_cast<int>(u / a.k_blocks);
+        const int kb = static_cast<int>(u % a.k_blocks);
+        mbar_expect_tx(&full[i], Cfg::kStageBytes);
+        tma_load_2d(sW + i * Cfg::kWBytes, &tmW, &full[i], kb * kTileK, a.w_row0 + tile * kTileN,
+                    polW);
+      }
+      pdl_wait();
+      for (int i = 0; i < npre; ++i) {
+        const int kb = static_cast<int>((u0 + i) % a.k_blocks);
+        tma_load_2d(sX + i * Cfg::kXBytes, &tmX, &full[i], kb * kTileK, a.x_row0, polX);
+      }
+      int stage = npre % S;
+      uint32_t phase = (npre == S) ? 1u : 0u;
+      for (long long u = u0 + npre; u < u1; ++u) {
+        const int tile = static_cast<int>(u / a.k_blocks);
+        const int kb = static_cast<int>(u % a.k_blocks);
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+        tma_load_2d(sW + stage * Cfg::kWBytes, &tmW, &full[stage], kb * kTileK,
+                    a.w_row0 + tile * kTileN, polW);
+        tma_load_2d(sX + stage * Cfg::kXBytes, &tmX, &full[stage], kb * kTileK, a.x_row0, polX);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileN, MB);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      long long u = u0;
+      while (u < u1) {
+        const long long tile = u / a.k_blocks;
+        const long long seg_end = (tile + 1) * a.k_blocks < u1 ? (tile + 1) * a.k_blocks : u1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MB);
+        uint32_t accumulate = 0;
+        for (; u < seg_end; ++u) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(sW + stage * Cfg::kWBytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(sX + stage * Cfg::kXBytes));
+#pragma unroll
+          for (int k = 0; k < kTileK / kUmmaK; ++k) {
+            // +32 B per K=16 step inside the 128-byte swizzle row (address field is in 16 B units)
+            umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                         idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(&empty[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0..3)
+    pdl_wait();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const int row_in_tile = warp * 32 + lane;
+
+    // kModeArgmax running best per activation row (this thread's weight rows only ever increase)
+    float best_v[MODE == kModeArgmax ? MB : 1];
+    int best_i[MODE == kModeArgmax ? MB : 1];
+    if (MODE == kModeArgmax) {
+#pragma unroll
+      for (int j = 0; j < MB; ++j) { best_v[j] = -INFINITY; best_i[j] = 0x7fffffff; }
+    }
+
+    long long u = u0;
+    while (u < u1) {
+      const int tile = static_cast<int>(u / a.k_blocks);
+      const long long seg_end =
+          static_cast<long long>(tile + 1) * a.k_blocks < u1 ? static_cast<long long>(tile + 1) * a.k_blocks : u1;
+      const int n = tile * kTileN + row_in_tile;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      float* dst = nullptr;
+      if (MODE == kModePartials) {
+        const int slot = static_cast<int>(blockIdx.x) - tile_first_cta(tile, a.k_blocks, T, G);
+        dst = a.ws + (static_cast<long long>(slot) * a.ws_rows) * a.ws_ld + n;
+      }
+#pragma unroll
+      for (int c = 0; c < MB / 16; ++c) {
+        float v[16];
+        tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + c * 16), v);
+        tmem_ld_wait();
+        if (c == MB / 16 - 1) {
+          // all of this accumulator is in registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty[acc]);
+        }
+        if (MODE == kModePartials) {
+          if (n < a.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int m = c * 16 + j;
+              if (m < a.m_valid) dst[static_cast<long long>(m) * a.ws_ld] = v[j];
+            }
+          }
+        } else {
+          if (n < a.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int m = c * 16 + j;
+              const float r = bf16_round(v[j]);
+              if (r > best_v[m]) { best_v[m] = r; best_i[m] = n; }
+              if (a.logits != nullptr && m < a.m_valid)
+                a.logits[static_cast<long long>(m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      u = seg_end;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+
+    if (MODE == kModeArgmax) {
+      // reduce over the 128 epilogue threads: max value, ties -> lowest index
+      float* red_v = reinterpret_cast<float*>(sW);  // pipeline smem is idle by now (all MMAs retired)
+      int* red_i = reinterpret_cast<int*>(sW + 4 * MB * sizeof(float));
+#pragma unroll
+      for (int j = 0; j < MB; ++j) {
+        float bv = best_v[j];
+        int bi = best_i[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { red_v[warp * MB + j] = bv; red_i[warp * MB + j] = bi; }
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (threadIdx.x < MB) {
+        const int j = threadIdx.x;
+        float bv = red_v[j];
+        int bi = red_i[j];
+        for (int w = 1; w < 4; ++w) {
+          const float ov = red_v[w * MB + j];
+          const int oi = red_i[w * MB + j];
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        a.cand_val[static_cast<long long>(blockIdx.x) * MB + j] = bv;
+        a.cand_idx[static_cast<long long>(blockIdx.x) * MB + j] = bi;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+}  // namespace dfl

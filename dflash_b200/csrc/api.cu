@@ -43,6 +43,135 @@ int dflash_device_check(void) {
   return prop.multiProcessorCount;
 }
 
+struct dflash_engine {
+  Engine* impl;
+};
+
+static int device_sm_count(int* sms) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (major != 10) {
+    set_error("dflash_b200 needs an sm_100a device (compute capability major %d found)", major);
+    return DFLASH_ERR_ARCH;
+  }
+  e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  return DFLASH_OK;
+}
+
+size_t dflash_workspace_bytes(const dflash_config_t* cfg) {
+  if (!cfg) { set_error("null config"); return 0; }
+  if (check_config(*cfg)) return 0;
+  int sms = 148;
+  if (cfg->gemm_grid <= 0) {
+    if (device_sm_count(&sms)) return 0;
+  }
+  Region reg[DFLASH_BUF_COUNT];
+  return layout_workspace(*cfg, reg, sms, nullptr);
+}
+
+int dflash_engine_create(const dflash_config_t* cfg, const dflash_weights_t* weights, void* workspace,
+                         size_t workspace_bytes, dflash_engine_t** out) {
+  if (!cfg || !weights || !out || !weights->layers_host) {
+    set_error("engine_create: null argument");
+    return DFLASH_ERR_ARG;
+  }
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  Engine* impl = nullptr;
+  rc = engine_create(*cfg, *weights, workspace, workspace_bytes, sms, &impl);
+  if (rc) return rc;
+  *out = new dflash_engine{impl};
+  return DFLASH_OK;
+}
+
+void dflash_engine_destroy(dflash_engine_t* e) {
+  if (!e) return;
+  delete e->impl;
+  delete e;
+}
+
+int dflash_engine_buffer(const dflash_engine_t* e, int id, void** ptr_out, size_t* bytes_out) {
+  if (!e || id < 0 || id >= DFLASH_BUF_COUNT) { set_error("engine_buffer: bad argument"); return DFLASH_ERR_ARG; }
+  if (ptr_out) *ptr_out = e->impl->base + e->impl->reg[id].off;
+  if (bytes_out) *bytes_out = e->impl->reg[id].bytes;
+  return DFLASH_OK;
+}
+
+int dflash_prefill_context(dflash_engine_t* e, int r, const void* const* hidden, int P, void* stream) {
+  if (!e || !hidden) { set_error("prefill_context: null argument"); return DFLASH_ERR_ARG; }
+  return enqueue_prefill(e->impl, r, hidden, P, static_cast<cudaStream_t>(stream));
+}
+
+int dflash_draft_step(dflash_engine_t* e, const void* noise_embedding, int run_lm_head, void* stream) {
+  if (!e) { set_error("draft_step: null engine"); return DFLASH_ERR_ARG; }
+  return enqueue_draft_step(e->impl, noise_embedding, run_lm_head != 0, static_cast<cudaStream_t>(stream));
+}
+
+int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long logits_ld,
+                       const long long* posterior_in, const void* const* hidden, float temperature,
+                       const float* noise, unsigned long long seed, const long long* stop_ids, int n_stop,
+                       const int* forced_k, int forced_ld, int clamp_tail, void* stream) {
+  if (!e || !hidden || (!target_logits && !posterior_in)) {
+    set_error("verify_step: null argument");
+    return DFLASH_ERR_ARG;
+  }
+  VerifyInputs v;
+  memset(&v, 0, sizeof(v));
+  v.target_logits = target_logits;
+  v.logits_ld = logits_ld;
+  v.posterior_in = posterior_in;
+  for (int s = 0; s < e->impl->nsel; ++s) {
+    if (!hidden[s]) { set_error("verify_step: hidden[%d] is null", s); return DFLASH_ERR_ARG; }
+    v.hidden[s] = hidden[s];
+  }
+  v.temperature = temperature;
+  v.noise = noise;
+  v.seed = seed;
+  v.stop_ids = stop_ids;
+  v.n_stop = stop_ids ? n_stop : 0;
+  v.forced_k = forced_k;
+  v.forced_ld = forced_ld;
+  v.clamp_tail = clamp_tail;
+  return enqueue_verify_step(e->impl, v, static_cast<cudaStream_t>(stream));
+}
+
+int dflash_sample(const void* logits, long long logits_ld, int rows, int vocab, float temperature,
+                  const float* noise, unsigned long long seed, float* scratch_val, int* scratch_idx,
+                  int nsplit, long long* tokens_out, void* stream) {
+  if (!logits || !scratch_val || !scratch_idx || !tokens_out || rows < 1 || vocab < 1 || nsplit < 1) {
+    set_error("sample: bad argument");
+    return DFLASH_ERR_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PosteriorArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.logits = static_cast<const __nv_bfloat16*>(logits);
+  pa.ld = logits_ld;
+  pa.rows = rows;
+  pa.V = vocab;
+  pa.nsplit = nsplit;
+  pa.inv_temp = temperature < 1e-5f ? 0.f : 1.0f / temperature;
+  pa.noise = noise;
+  pa.seed = seed;
+  pa.rng_step = nullptr;
+  pa.cand_val = scratch_val;
+  pa.cand_idx = scratch_idx;
+  posterior_kernel<<<dim3(nsplit, rows), 256, 0, st>>>(pa);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "posterior launch");
+  // second stage: candidates are laid out [rows][nsplit] -> reuse the lm_head reducer with mb = 1 stride trick
+  sample_reduce_kernel<<<rows, 32, 0, st>>>(scratch_val, scratch_idx, nsplit, tokens_out);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "sample reduce launch");
+  return DFLASH_OK;
+}
+
 int dflash_gemm_max_slots(int N, int K, int grid) {
   if (N <= 0 || K <= 0 || K % kTileK != 0 || grid <= 0) return DFLASH_ERR_ARG;
   const int n_tiles = (N + kTileN - 1) / kTileN;

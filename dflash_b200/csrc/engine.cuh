@@ -1,7 +1,514 @@
-// Draft/verify engine: buffer layout, per-step kernel schedule.
+// Draft/verify engine: workspace layout, GEMM plans (TMA maps built once), per-step kernel schedule.
+// The engine object is host memory only; every device byte belongs to the caller's workspace.
 #pragma once
+#include <math.h>
+
+#include <vector>
+
+#include "../../include/dflash_b200.h"
+#include "attention.cuh"
 #include "fused_ops.cuh"
+#include "verify.cuh"
 
 namespace dfl {
 int cuda_fail(cudaError_t e, const char* what);  // api.cu
+
+struct Region {
+  size_t off = 0, bytes = 0;
+};
+
+struct Engine {
+  dflash_config_t cfg;
+  dflash_weights_t w;
+  std::vector<dflash_layer_weights_t> layers;
+  uint8_t* base = nullptr;
+  size_t total = 0;
+  Region reg[DFLASH_BUF_COUNT];
+  int R, SL, RS, H, I, L, Hq, Hkv, V, nsel, bs, grid, nsplit_attn, nsplit_post;
+  bool pdl;
+  int max_slots;
+  // plans
+  GemmPlan fc;                  // ctx_feat -> partials
+  std::vector<GemmPlan> qkv;    // a_in (ctx + block rows)
+  std::vector<GemmPlan> kv;     // a_in ctx rows only, K/V weight rows only (prompt prefill)
+  std::vector<GemmPlan> o, gu, d;
+  GemmPlan lm;
+
+  template <class T>
+  T* buf(int id) const { return reinterpret_cast<T*>(base + reg[id].off); }
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline int round_mb(int rows) {
+  for (int mb : {16, 32, 64, 128, 256})
+    if (rows <= mb) return mb;
+  return -1;
+}
+
+// Fills reg[] (offsets/sizes) for cfg; returns total bytes or 0 on a bad config.
+inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_count, int* max_slots_out) {
+  const int SL = c.block_size <= 16 ? 16 : 32;
+  const int R = c.max_requests;
+  const int RS = R * SL;
+  const int H = c.hidden, I = c.intermediate, Hq = c.n_q_heads, Hkv = c.n_kv_heads;
+  const int grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
+  const int nsa = c.attn_splits > 0 ? c.attn_splits : 16;
+  const int nsp = c.post_splits > 0 ? c.post_splits : 8;
+  const int qkv_cols = (Hq + 2 * Hkv) * 128;
+  // widest fp32 partial plane over all GEMMs of the step
+  long long ws_elems = 0;
+  int max_slots = 1;
+  struct G { int rows, N, K; } gs[] = {{RS, H, c.n_sel * H}, {2 * RS, qkv_cols, H}, {RS, H, Hq * 128},
+                                       {RS, 2 * I, H},       {RS, H, I}};
+  for (auto& g : gs) {
+    const int nt = (g.N + kTileN - 1) / kTileN, kb = g.K / kTileK;
+    const long long T = static_cast<long long>(nt) * kb;
+    const int gg = T < grid ? static_cast<int>(T) : grid;
+    const int s = max_slots_for(nt, kb, gg);
+    const long long e = static_cast<long long>(s) * round_mb(g.rows) * g.N;
+    if (e > ws_elems) ws_elems = e;
+    if (s > max_slots) max_slots = s;
+  }
+  if (max_slots_out) *max_slots_out = max_slots;
+  size_t sz[DFLASH_BUF_COUNT] = {0};
+  sz[DFLASH_BUF_X] = static_cast<size_t>(RS) * H * 2;
+  sz[DFLASH_BUF_A_IN] = static_cast<size_t>(2 * RS) * H * 2;
+  sz[DFLASH_BUF_CTX_FEAT] = static_cast<size_t>(RS) * c.n_sel * H * 2;
+  sz[DFLASH_BUF_Q] = static_cast<size_t>(RS) * Hq * 128 * 2;
+  sz[DFLASH_BUF_ATTN_OUT] = static_cast<size_t>(RS) * Hq * 128 * 2;
+  sz[DFLASH_BUF_A2] = static_cast<size_t>(RS) * H * 2;
+  sz[DFLASH_BUF_HMID] = static_cast<size_t>(RS) * I * 2;
+  sz[DFLASH_BUF_HN] = static_cast<size_t>(RS) * H * 2;
+  sz[DFLASH_BUF_KV] = static_cast<size_t>(c.n_layers) * 2 * R * Hkv * c.max_seq * 128 * 2;
+  sz[DFLASH_BUF_WS] = static_cast<size_t>(ws_elems) * 4;
+  sz[DFLASH_BUF_ATTN_PO] = static_cast<size_t>(nsa) * RS * Hq * 128 * 4;
+  sz[DFLASH_BUF_ATTN_ML] = static_cast<size_t>(nsa) * RS * Hq * 2 * 4;
+  sz[DFLASH_BUF_CAND_VAL] = static_cast<size_t>(grid) * RS * 4;
+  sz[DFLASH_BUF_CAND_IDX] = static_cast<size_t>(grid) * RS * 4;
+  sz[DFLASH_BUF_POST_VAL] = static_cast<size_t>(R) * c.block_size * nsp * 4;
+  sz[DFLASH_BUF_POST_IDX] = static_cast<size_t>(R) * c.block_size * nsp * 4;
+  sz[DFLASH_BUF_DRAFT_TOKENS] = static_cast<size_t>(RS) * 8;
+  sz[DFLASH_BUF_BLOCK_IDS] = static_cast<size_t>(R) * c.block_size * 8;
+  sz[DFLASH_BUF_POSTERIOR] = static_cast<size_t>(R) * c.block_size * 8;
+  sz[DFLASH_BUF_OUTPUT_IDS] = static_cast<size_t>(R) * c.out_len * 8;
+  sz[DFLASH_BUF_START] = sz[DFLASH_BUF_CTX_LEN] = sz[DFLASH_BUF_DONE] = sz[DFLASH_BUF_N_CYCLES] =
+      sz[DFLASH_BUF_BLK_LEN] = sz[DFLASH_BUF_MAX_LEN] = static_cast<size_t>(R) * 4;
+  sz[DFLASH_BUF_ACC_HIST] = static_cast<size_t>(R) * c.hist_len * 4;
+  sz[DFLASH_BUF_RNG_STEP] = 8;
+  sz[DFLASH_BUF_DRAFT_LOGITS] = c.keep_draft_logits ? static_cast<size_t>(RS) * c.vocab * 2 : 0;
+  size_t off = 0;
+  for (int i = 0; i < DFLASH_BUF_COUNT; ++i) {
+    reg[i].off = off;
+    reg[i].bytes = sz[i];
+    off += align_up(sz[i], 1024);
+  }
+  return off;
+}
+
+inline int check_config(const dflash_config_t& c) {
+  if (c.head_dim != 128) { set_error("head_dim %d unsupported (128 only)", c.head_dim); return DFLASH_ERR_ARG; }
+  if (c.hidden % 64 || c.intermediate % 64 || c.hidden > 8192) {
+    set_error("hidden/intermediate must be multiples of 64 and hidden <= 8192");
+    return DFLASH_ERR_ARG;
+  }
+  if (c.block_size < 2 || c.block_size > 32) { set_error("block_size must be in [2,32]"); return DFLASH_ERR_ARG; }
+  if (c.n_q_heads % c.n_kv_heads || c.n_q_heads / c.n_kv_heads > 8) {
+    set_error("GQA group must divide and be <= 8");
+    return DFLASH_ERR_ARG;
+  }
+  const int SL = c.block_size <= 16 ? 16 : 32;
+  if (c.max_requests < 1 || 2 * c.max_requests * SL > 256) {
+    set_error("max_requests %d unsupported: 2*R*%d activation rows must fit one 256-wide UMMA", c.max_requests, SL);
+    return DFLASH_ERR_ARG;
+  }
+  if ((c.max_requests & (c.max_requests - 1)) != 0 || c.max_requests * SL > 32) {
+    set_error("max_requests %d: fused lm_head argmax currently covers <= 32 block rows", c.max_requests);
+    return DFLASH_ERR_ARG;
+  }
+  if (c.n_sel < 1 || c.n_sel > 8) { set_error("n_sel must be in [1,8]"); return DFLASH_ERR_ARG; }
+  if (c.max_seq < 2 * c.block_size || c.out_len < 1 || c.hist_len < 1) {
+    set_error("max_seq/out_len/hist_len too small");
+    return DFLASH_ERR_ARG;
+  }
+  return DFLASH_OK;
+}
+
+#define DFL_CUDA(expr, what)                              \
+  do {                                                    \
+    cudaError_t _e = (expr);                              \
+    if (_e != cudaSuccess) return cuda_fail(_e, what);    \
+  } while (0)
+
+template <class Kern, class Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              const Args& args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, void* workspace,
+                         size_t workspace_bytes, int sm_count, Engine** out) {
+  int rc = check_config(c);
+  if (rc) return rc;
+  Engine* e = new Engine();
+  e->cfg = c;
+  e->w = w;
+  e->layers.assign(w.layers_host, w.layers_host + c.n_layers);
+  e->w.layers_host = nullptr;
+  e->R = c.max_requests;
+  e->SL = c.block_size <= 16 ? 16 : 32;
+  e->RS = e->R * e->SL;
+  e->H = c.hidden; e->I = c.intermediate; e->L = c.n_layers; e->Hq = c.n_q_heads; e->Hkv = c.n_kv_heads;
+  e->V = c.vocab; e->nsel = c.n_sel; e->bs = c.block_size;
+  e->grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
+  e->nsplit_attn = c.attn_splits > 0 ? c.attn_splits : 16;
+  e->nsplit_post = c.post_splits > 0 ? c.post_splits : 8;
+  e->pdl = c.use_pdl != 0;
+  e->total = layout_workspace(c, e->reg, sm_count, &e->max_slots);
+  if (workspace == nullptr || workspace_bytes < e->total) {
+    set_error("workspace too small: need %zu bytes, got %zu", e->total, workspace_bytes);
+    delete e;
+    return DFLASH_ERR_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) {
+    set_error("workspace must be 1024-byte aligned");
+    delete e;
+    return DFLASH_ERR_ARG;
+  }
+  e->base = static_cast<uint8_t*>(workspace);
+
+  const int RS = e->RS, H = e->H, I = e->I;
+  const int qkv_cols = (e->Hq + 2 * e->Hkv) * 128;
+  const int mb_blk = round_mb(RS), mb_all = round_mb(2 * RS);
+  float* ws = e->buf<float>(DFLASH_BUF_WS);
+  auto finish = [&](GemmPlan& p, int ws_rows) {
+    p.args.ws = ws;
+    p.args.ws_rows = ws_rows;
+    p.args.ws_ld = p.args.N;
+  };
+#define DFL_PLAN(call)        \
+  do {                        \
+    int _rc = (call);         \
+    if (_rc) { delete e; return DFLASH_ERR_ARG; } \
+  } while (0)
+  // activation TMA tensors are declared with mb rows so the box never leaves the allocation:
+  // buffers of RS (or 2*RS) rows are exactly mb rows when RS is a power of two >= 16.
+  DFL_PLAN(make_gemm_plan(&e->fc, w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_CTX_FEAT), RS, 0, mb_blk, RS,
+                          kModePartials, e->grid));
+  finish(e->fc, mb_blk);
+  e->qkv.resize(e->L); e->kv.resize(e->L); e->o.resize(e->L); e->gu.resize(e->L); e->d.resize(e->L);
+  for (int l = 0; l < e->L; ++l) {
+    const dflash_layer_weights_t& lw = e->layers[l];
+    DFL_PLAN(make_gemm_plan(&e->qkv[l], lw.wqkv, qkv_cols, 0, qkv_cols, H, e->buf<void>(DFLASH_BUF_A_IN), 2 * RS, 0,
+                            mb_all, 2 * RS, kModePartials, e->grid));
+    finish(e->qkv[l], mb_all);
+    DFL_PLAN(make_gemm_plan(&e->kv[l], lw.wqkv, qkv_cols, e->Hq * 128, 2 * e->Hkv * 128, H,
+                            e->buf<void>(DFLASH_BUF_A_IN), 2 * RS, 0, mb_blk, RS, kModePartials, e->grid));
+    finish(e->kv[l], mb_blk);
+    DFL_PLAN(make_gemm_plan(&e->o[l], lw.wo, H, 0, H, e->Hq * 128, e->buf<void>(DFLASH_BUF_ATTN_OUT), RS, 0, mb_blk, RS,
+                            kModePartials, e->grid));
+    finish(e->o[l], mb_blk);
+    DFL_PLAN(make_gemm_plan(&e->gu[l], lw.wgu, 2 * I, 0, 2 * I, H, e->buf<void>(DFLASH_BUF_A2), RS, 0, mb_blk, RS,
+                            kModePartials, e->grid));
+    finish(e->gu[l], mb_blk);
+    DFL_PLAN(make_gemm_plan(&e->d[l], lw.wd, H, 0, H, I, e->buf<void>(DFLASH_BUF_HMID), RS, 0, mb_blk, RS,
+                            kModePartials, e->grid));
+    finish(e->d[l], mb_blk);
+  }
+  DFL_PLAN(make_gemm_plan(&e->lm, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
+                          kModeArgmax, e->grid));
+  e->lm.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
+  e->lm.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
+  e->lm.args.logits = c.keep_draft_logits ? e->buf<__nv_bfloat16>(DFLASH_BUF_DRAFT_LOGITS) : nullptr;
+  e->lm.args.logits_ld = e->V;
+#undef DFL_PLAN
+  cudaError_t ce = cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
+  *out = e;
+  return DFLASH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+inline RowsArgs rows_args_base(const Engine* e) {
+  RowsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.H = e->H;
+  a.SL = e->SL;
+  a.bs = e->bs;
+  a.eps = e->cfg.rms_eps;
+  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  a.valid_mode = kRowsAll;
+  return a;
+}
+
+// fc GEMM + hidden_norm over the pending context rows -> a_in rows [0, RS)   (dflash.py:177)
+inline int enqueue_ctx_inject(Engine* e, cudaStream_t st) {
+  DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
+  RowsArgs a = rows_args_base(e);
+  a.ws = e->fc.args.ws;
+  a.sm = slot_map_of(e->fc);
+  a.valid_mode = kRowsCtx;
+  a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
+  a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
+  DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), 0, st, e->pdl, a), "fc finalize");
+  return DFLASH_OK;
+}
+
+inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_only) {
+  QkvPostArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ws = p.args.ws;
+  a.sm = slot_map_of(p);
+  a.R = e->R; a.SL = e->SL; a.bs = e->bs; a.Hq = e->Hq; a.Hkv = e->Hkv;
+  a.q_cols = kv_only ? 0 : e->Hq * 128;
+  a.row0 = 0;
+  a.rows = kv_only ? e->RS : 2 * e->RS;
+  a.start = e->buf<int>(DFLASH_BUF_START);
+  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  a.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  a.q_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].q_norm);
+  a.k_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].k_norm);
+  a.inv_freq = e->w.inv_freq;
+  a.rope_scale = e->cfg.rope_scale;
+  a.eps = e->cfg.rms_eps;
+  a.q_out = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
+  const size_t per = static_cast<size_t>(e->R) * e->Hkv * e->cfg.max_seq * 128;
+  a.k_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 0) * per;
+  a.v_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 1) * per;
+  a.S_max = e->cfg.max_seq;
+  return a;
+}
+
+// Context-only pass (prompt prefill chunks): ctx inject, then per layer K/V projection of the
+// context rows into the cache. No queries, no block rows.
+inline int enqueue_ctx_only(Engine* e, cudaStream_t st) {
+  int rc = enqueue_ctx_inject(e, st);
+  if (rc) return rc;
+  for (int l = 0; l < e->L; ++l) {
+    DFL_CUDA(launch_gemm(e->kv[l], st, e->pdl), "kv gemm");
+    QkvPostArgs qa = qkv_post_args(e, l, e->kv[l], true);
+    const int items = qa.rows * (2 * e->Hkv);
+    DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "kv post");
+  }
+  return DFLASH_OK;
+}
+
+// One draft step: block embedding -> ctx inject -> L layers -> final norm -> lm_head + argmax.
+// Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247).
+inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st) {
+  const int RS = e->RS;
+  __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
+  __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
+  {
+    RowsArgs a = rows_args_base(e);
+    if (noise_embedding != nullptr) {
+      a.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
+      a.ids = nullptr;
+    } else {
+      a.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
+      a.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+    }
+    a.ids_ld = e->bs;
+    a.pad_token = e->cfg.mask_token_id;
+    a.resid = x;
+    a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
+    a.out = a_in + static_cast<size_t>(RS) * e->H;
+    DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), 0, st, e->pdl, a), "embed+ln1");
+  }
+  int rc = enqueue_ctx_inject(e, st);
+  if (rc) return rc;
+  AttnArgs aa;
+  memset(&aa, 0, sizeof(aa));
+  aa.R = e->R; aa.SL = e->SL; aa.bs = e->bs; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.S_max = e->cfg.max_seq;
+  aa.nsplit = e->nsplit_attn;
+  aa.start = e->buf<int>(DFLASH_BUF_START);
+  aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  aa.q = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
+  aa.part_o = e->buf<float>(DFLASH_BUF_ATTN_PO);
+  aa.part_ml = e->buf<float>(DFLASH_BUF_ATTN_ML);
+  aa.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
+  aa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_ATTN_OUT);
+  const int group = e->Hq / e->Hkv;
+  for (int l = 0; l < e->L; ++l) {
+    DFL_CUDA(launch_gemm(e->qkv[l], st, e->pdl), "qkv gemm");
+    QkvPostArgs qa = qkv_post_args(e, l, e->qkv[l], false);
+    const int items = qa.rows * (e->Hq + 2 * e->Hkv);
+    DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
+    aa.k_cache = qa.k_cache;
+    aa.v_cache = qa.v_cache;
+    DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
+                        kAttnSmem, st, e->pdl, aa),
+             "attention");
+    DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + 7) / 8), dim3(256), 0, st, e->pdl, aa),
+             "attention combine");
+    DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
+    {
+      RowsArgs a = rows_args_base(e);
+      a.ws = e->o[l].args.ws;
+      a.sm = slot_map_of(e->o[l]);
+      a.resid = x;
+      a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
+      a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
+      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), 0, st, e->pdl, a), "o finalize");
+    }
+    DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
+    {
+      SwigluArgs sa;
+      sa.ws = e->gu[l].args.ws;
+      sa.sm = slot_map_of(e->gu[l]);
+      sa.rows = RS;
+      sa.I = e->I;
+      sa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
+      DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I + 255) / 256, RS), dim3(256), 0, st, e->pdl, sa), "swiglu");
+    }
+    DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
+    {
+      RowsArgs a = rows_args_base(e);
+      a.ws = e->d[l].args.ws;
+      a.sm = slot_map_of(e->d[l]);
+      a.resid = x;
+      if (l + 1 < e->L) {
+        a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l + 1].ln1);
+        a.out = a_in + static_cast<size_t>(RS) * e->H;
+      } else {
+        a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
+        a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
+      }
+      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), 0, st, e->pdl, a), "down finalize");
+    }
+  }
+  if (!run_lm_head) return DFLASH_OK;
+  DFL_CUDA(launch_gemm(e->lm, st, e->pdl), "lm_head gemm");
+  DraftTokArgs ta;
+  ta.cand_val = e->lm.args.cand_val;
+  ta.cand_idx = e->lm.args.cand_idx;
+  ta.n_cta = e->lm.grid;
+  ta.mb = e->lm.mb;
+  ta.R = e->R; ta.SL = e->SL; ta.bs = e->bs;
+  ta.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+  ta.draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
+  DFL_CUDA(launch_pdl(draft_tokens_kernel, dim3(RS), dim3(32), 0, st, e->pdl, ta), "draft tokens");
+  return DFLASH_OK;
+}
+
+struct VerifyInputs {
+  const void* target_logits;  // [R*bs][V] bf16 (row pitch logits_ld), or null with posterior_in
+  long long logits_ld;
+  const long long* posterior_in;
+  const void* hidden[8];      // n_sel x [R*bs][H] bf16
+  float temperature;
+  const float* noise;
+  unsigned long long seed;
+  const long long* stop_ids;
+  int n_stop;
+  const int* forced_k;
+  int forced_ld;
+  int clamp_tail;
+};
+
+// Posterior sampling -> acceptance/commit/state -> next-cycle context gather  (dflash.py:257-268)
+inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st) {
+  const int rows = e->R * e->bs;
+  if (v.posterior_in == nullptr) {
+    PosteriorArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.logits = static_cast<const __nv_bfloat16*>(v.target_logits);
+    pa.ld = v.logits_ld;
+    pa.rows = rows;
+    pa.V = e->V;
+    pa.nsplit = e->nsplit_post;
+    pa.inv_temp = v.temperature < 1e-5f ? 0.f : 1.0f / v.temperature;
+    pa.noise = v.noise;
+    pa.seed = v.seed;
+    pa.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
+    pa.cand_val = e->buf<float>(DFLASH_BUF_POST_VAL);
+    pa.cand_idx = e->buf<int>(DFLASH_BUF_POST_IDX);
+    DFL_CUDA(launch_pdl(posterior_kernel, dim3(e->nsplit_post, rows), dim3(256), 0, st, e->pdl, pa), "posterior");
+  }
+  AcceptArgs aa;
+  memset(&aa, 0, sizeof(aa));
+  aa.R = e->R; aa.bs = e->bs; aa.nsplit = e->nsplit_post;
+  aa.cand_val = e->buf<float>(DFLASH_BUF_POST_VAL);
+  aa.cand_idx = e->buf<int>(DFLASH_BUF_POST_IDX);
+  aa.posterior_in = v.posterior_in;
+  aa.posterior = e->buf<long long>(DFLASH_BUF_POSTERIOR);
+  aa.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+  aa.ids_ld = e->bs;
+  aa.output_ids = e->buf<long long>(DFLASH_BUF_OUTPUT_IDS);
+  aa.out_ld = e->cfg.out_len;
+  aa.start = e->buf<int>(DFLASH_BUF_START);
+  aa.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  aa.done = e->buf<int>(DFLASH_BUF_DONE);
+  aa.n_cycles = e->buf<int>(DFLASH_BUF_N_CYCLES);
+  aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  aa.acc_hist = e->buf<int>(DFLASH_BUF_ACC_HIST);
+  aa.hist_ld = e->cfg.hist_len;
+  aa.max_len = e->buf<int>(DFLASH_BUF_MAX_LEN);
+  aa.stop_ids = v.stop_ids;
+  aa.n_stop = v.n_stop;
+  aa.mask_token = e->cfg.mask_token_id;
+  aa.forced_k = v.forced_k;
+  aa.forced_ld = v.forced_ld > 0 ? v.forced_ld : 1;
+  aa.clamp_tail = v.clamp_tail;
+  aa.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
+  DFL_CUDA(launch_pdl(accept_kernel, dim3(e->R), dim3(32), 0, st, e->pdl, aa), "accept");
+  GatherArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  for (int s = 0; s < e->nsel; ++s) ga.src[s] = static_cast<const __nv_bfloat16*>(v.hidden[s]);
+  ga.n_sel = e->nsel; ga.H = e->H; ga.SL = e->SL;
+  ga.r0 = 0; ga.nreq = e->R;
+  ga.src_rows = e->bs;
+  ga.src_row0 = 0;
+  ga.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  ga.ctx_feat = e->buf<__nv_bfloat16>(DFLASH_BUF_CTX_FEAT);
+  DFL_CUDA(launch_pdl(ctx_gather_kernel, dim3(e->RS, e->nsel), dim3(256), 0, st, e->pdl, ga), "ctx gather");
+  return DFLASH_OK;
+}
+
+// Prompt prefill of request r: P rows of the selected target hidden states go through the
+// context-only pass in chunks of SL rows (cycle 0 of dflash.py:229,238-246 with c = P).
+inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int P, cudaStream_t st) {
+  if (r < 0 || r >= e->R || P < 1 || P + 2 * e->bs > e->cfg.max_seq) {
+    set_error("prefill: bad request %d or prompt length %d (max_seq %d)", r, P, e->cfg.max_seq);
+    return DFLASH_ERR_ARG;
+  }
+  for (int c0 = 0; c0 < P; c0 += e->SL) {
+    const int c = P - c0 < e->SL ? P - c0 : e->SL;
+    SetStateArgs sa;
+    sa.r = r; sa.start = c0 + c; sa.ctx_len = c;
+    sa.start_p = e->buf<int>(DFLASH_BUF_START);
+    sa.ctx_len_p = e->buf<int>(DFLASH_BUF_CTX_LEN);
+    DFL_CUDA(launch_pdl(set_state_kernel, dim3(1), dim3(1), 0, st, false, sa), "set state");
+    GatherArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    for (int s = 0; s < e->nsel; ++s) ga.src[s] = static_cast<const __nv_bfloat16*>(hidden[s]);
+    ga.n_sel = e->nsel; ga.H = e->H; ga.SL = e->SL;
+    ga.r0 = r; ga.nreq = 1;
+    ga.src_rows = P;
+    ga.src_row0 = c0;
+    ga.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+    ga.ctx_feat = e->buf<__nv_bfloat16>(DFLASH_BUF_CTX_FEAT);
+    DFL_CUDA(launch_pdl(ctx_gather_kernel, dim3(e->SL, e->nsel), dim3(256), 0, st, false, ga), "prefill gather");
+    int rc = enqueue_ctx_only(e, st);
+    if (rc) return rc;
+  }
+  SetStateArgs sa;
+  sa.r = r; sa.start = P; sa.ctx_len = 0;
+  sa.start_p = e->buf<int>(DFLASH_BUF_START);
+  sa.ctx_len_p = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  DFL_CUDA(launch_pdl(set_state_kernel, dim3(1), dim3(1), 0, st, false, sa), "set state");
+  return DFLASH_OK;
+}
+
 }  // namespace dfl

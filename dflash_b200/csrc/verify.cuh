@@ -1,0 +1,269 @@
+// Verify step: posterior sampling over the target logits, longest-matching-prefix acceptance,
+// token commit (+ bonus token), cache-length rollback, stop check, next-block setup and the gather
+// of the next cycle's context features  (model/dflash.py:257-268, model/utils.py:16-34).
+//
+// All state lives on the device (start / ctx_len / done per request) so the whole draft+verify
+// step replays from a CUDA graph with no host round trip. With static caches the reference's two
+// crops (dflash.py:246,262) are length writes: rows past `start` are dead and get overwritten.
+#pragma once
+#include "ptx.cuh"
+
+namespace dfl {
+
+// ------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                           uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1]
+  return (static_cast<float>(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+struct PosteriorArgs {
+  const __nv_bfloat16* logits;  // [rows][ld]
+  long long ld;
+  int rows, V, nsplit;
+  float inv_temp;           // 0 -> greedy argmax (temperature < 1e-5, utils.py:28)
+  const float* noise;       // optional Exp(1) draws [rows][V] (torch.multinomial's q); null -> Philox
+  unsigned long long seed;
+  const unsigned long long* rng_step;  // device counter, bumped by accept_kernel every cycle
+  float* cand_val;          // [rows][nsplit]
+  int* cand_idx;
+};
+
+// key_i = logit_i (greedy) or logit_i / T - log(e_i), e_i ~ Exp(1): argmax_i key_i is a draw from
+// softmax(logits / T) -- the same exponential race torch.multinomial runs (argmax(p / q)).
+__global__ void __launch_bounds__(256) posterior_kernel(const PosteriorArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.y, split = blockIdx.x;
+  int seg = (a.V + a.nsplit - 1) / a.nsplit;
+  seg = (seg + 7) & ~7;
+  const int c0 = split * seg;
+  const int c1 = min(a.V, c0 + seg);
+  const __nv_bfloat16* lp = a.logits + static_cast<long long>(row) * a.ld;
+  const bool greedy = a.inv_temp == 0.f;
+  const unsigned long long step = (a.rng_step != nullptr) ? *a.rng_step : 0ull;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(lp) & 15) == 0);
+  auto consider = [&](float logit, int col, uint32_t rnd) {
+    float key = logit;
+    if (!greedy) {
+      float e;
+      if (a.noise != nullptr) e = a.noise[static_cast<long long>(row) * a.V + col];
+      else e = -__logf(u32_to_unit(rnd));
+      key = logit * a.inv_temp - logf(fmaxf(e, 1e-30f));
+    }
+    if (key > bv) { bv = key; bi = col; }
+  };
+  if (vec_ok) {
+    for (int c = c0 + threadIdx.x * 8; c < c1; c += 256 * 8) {
+      uint32_t rnd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (!greedy && a.noise == nullptr) {
+        philox4x32(static_cast<uint32_t>(c), static_cast<uint32_t>(row), static_cast<uint32_t>(step),
+                   static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(a.seed),
+                   static_cast<uint32_t>(a.seed >> 32), rnd);
+        philox4x32(static_cast<uint32_t>(c + 4), static_cast<uint32_t>(row), static_cast<uint32_t>(step),
+                   static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(a.seed),
+                   static_cast<uint32_t>(a.seed >> 32), rnd + 4);
+      }
+      if (c + 8 <= c1) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(lp + c);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          consider(f.x, c + 2 * j, rnd[2 * j]);
+          consider(f.y, c + 2 * j + 1, rnd[2 * j + 1]);
+        }
+      } else {
+        for (int j = 0; c + j < c1; ++j) consider(__bfloat162float(lp[c + j]), c + j, rnd[j]);
+      }
+    }
+  } else {
+    for (int c = c0 + threadIdx.x; c < c1; c += 256) {
+      uint32_t rnd[4] = {0, 0, 0, 0};
+      if (!greedy && a.noise == nullptr)
+        philox4x32(static_cast<uint32_t>(c), static_cast<uint32_t>(row), static_cast<uint32_t>(step),
+                   static_cast<uint32_t>(step >> 32) | 0x80000000u, static_cast<uint32_t>(a.seed),
+                   static_cast<uint32_t>(a.seed >> 32), rnd);
+      consider(__bfloat162float(lp[c]), c, rnd[0]);
+    }
+  }
+  // block argmax, ties -> lowest column (torch.argmax on CPU; CUDA ties are unspecified)
+  __shared__ float sv[8];
+  __shared__ int si[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+    a.cand_val[row * a.nsplit + split] = bv;
+    a.cand_idx[row * a.nsplit + split] = bi;
+  }
+}
+
+// tokens[row] = best candidate over the splits of posterior_kernel (standalone sampler)
+__global__ void __launch_bounds__(32) sample_reduce_kernel(const float* __restrict__ cand_val,
+                                                           const int* __restrict__ cand_idx, int nsplit,
+                                                           long long* __restrict__ tokens) {
+  const int row = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  float bv = cand_val[row * nsplit];
+  int bi = cand_idx[row * nsplit];
+  for (int s = 1; s < nsplit; ++s) {
+    const float v = cand_val[row * nsplit + s];
+    const int ix = cand_idx[row * nsplit + s];
+    if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+  }
+  tokens[row] = bi;
+}
+
+struct AcceptArgs {
+  int R, bs, nsplit;
+  const float* cand_val;  // [R*bs][nsplit] from posterior_kernel; ignored if posterior_in != null
+  const int* cand_idx;
+  const long long* posterior_in;  // optional [R][bs]: already-sampled posterior tokens
+  long long* posterior;           // [R][bs] out
+  long long* block_ids;           // [R][ids_ld]; in: block tokens (slot 0 committed, 1.. drafted)
+  int ids_ld;
+  long long* output_ids;          // [R][out_ld], pre-filled with mask_token
+  long long out_ld;
+  int* start;
+  int* ctx_len;
+  int* done;
+  int* n_cycles;
+  int* blk_len;                   // [R] effective block length of the NEXT cycle (tail clamp)
+  int* acc_hist;                  // [R][hist_ld] tau per cycle (acceptance_length + 1)
+  int hist_ld;
+  const int* max_len;             // [R] prompt length + max_new_tokens
+  const long long* stop_ids;
+  int n_stop;
+  long long mask_token;
+  const int* forced_k;            // optional [R][forced_ld] test/bench hook: posterior[:k] = block[1:k+1]
+  int forced_ld;
+  int clamp_tail;                 // benchmark.py:104-105 effective block size at the tail
+  unsigned long long* rng_step;
+};
+
+// One warp per request.
+__global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.x, lane = threadIdx.x;
+  if (r == 0 && lane == 0 && a.rng_step != nullptr) *a.rng_step += 1ull;
+  if (a.done[r]) return;
+  const int bs = a.bs;
+  long long* blk = a.block_ids + static_cast<long long>(r) * a.ids_ld;
+  __shared__ long long post[64];
+  __shared__ long long btok[64];
+  for (int i = lane; i < bs; i += 32) {
+    long long p;
+    if (a.posterior_in != nullptr) {
+      p = a.posterior_in[r * bs + i];
+    } else {
+      const int row = r * bs + i;
+      float bv = a.cand_val[row * a.nsplit];
+      int bi = a.cand_idx[row * a.nsplit];
+      for (int s = 1; s < a.nsplit; ++s) {
+        const float v = a.cand_val[row * a.nsplit + s];
+        const int ix = a.cand_idx[row * a.nsplit + s];
+        if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+      }
+      p = bi;
+    }
+    post[i] = p;
+    btok[i] = blk[i];
+  }
+  __syncwarp();
+  const int st = a.start[r];
+  const int cyc = a.n_cycles[r];
+  if (a.forced_k != nullptr) {
+    const int k = a.forced_k[r * a.forced_ld + (cyc % a.forced_ld)];
+    for (int i = lane; i < bs - 1; i += 32)
+      if (i < k) post[i] = btok[i + 1];
+    __syncwarp();
+  }
+  for (int i = lane; i < bs; i += 32) a.posterior[r * bs + i] = post[i];
+  if (lane != 0) return;
+  const int eff = a.blk_len[r];  // == bs unless the tail clamp shortened this block
+  int acc = 0;  // (blk[1:] == post[:-1]).cumprod().sum()
+  while (acc < eff - 1 && btok[acc + 1] == post[acc]) ++acc;
+  long long* out = a.output_ids + static_cast<long long>(r) * a.out_ld;
+  bool stop = false;
+  for (int i = 0; i <= acc; ++i) {
+    out[st + i] = btok[i];
+    for (int s = 0; s < a.n_stop; ++s) stop |= (btok[i] == a.stop_ids[s]);
+  }
+  const long long bonus = post[acc];
+  out[st + acc + 1] = bonus;
+  for (int s = 0; s < a.n_stop; ++s) stop |= (bonus == a.stop_ids[s]);
+  const int nst = st + acc + 1;
+  a.start[r] = nst;
+  a.ctx_len[r] = acc + 1;
+  if (cyc < a.hist_ld) a.acc_hist[r * a.hist_ld + cyc] = acc + 1;
+  a.n_cycles[r] = cyc + 1;
+  if (stop || nst >= a.max_len[r]) a.done[r] = 1;
+  if (a.clamp_tail) {
+    const int remaining = a.max_len[r] - nst;
+    a.blk_len[r] = remaining < bs ? (remaining < 1 ? 1 : remaining) : bs;
+  }
+  blk[0] = bonus;
+  for (int i = 1; i < bs; ++i) blk[i] = a.mask_token;
+}
+
+// Next-cycle context features: the first ctx_len[r] rows of each selected target hidden state,
+// concatenated on the feature dim (extract_context_feature + [:, :tau] slice, dflash.py:263).
+struct GatherArgs {
+  const __nv_bfloat16* src[8];  // per selected layer: [nreq * src_rows][H]
+  int n_sel, H, SL;
+  int r0, nreq;      // requests [r0, r0 + nreq) are covered by src
+  int src_rows;      // rows per request in src
+  int src_row0;      // first source row (prefill chunk offset)
+  const int* ctx_len;
+  __nv_bfloat16* ctx_feat;  // [R*SL][n_sel*H]
+};
+
+__global__ void __launch_bounds__(256) ctx_gather_kernel(const GatherArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int rr = blockIdx.x / a.SL, j = blockIdx.x % a.SL;
+  const int r = a.r0 + rr;
+  if (j >= a.ctx_len[r]) return;
+  const int sel = blockIdx.y;
+  const uint4* s = reinterpret_cast<const uint4*>(
+      a.src[sel] + (static_cast<long long>(rr) * a.src_rows + a.src_row0 + j) * a.H);
+  uint4* d = reinterpret_cast<uint4*>(a.ctx_feat + (static_cast<long long>(r) * a.SL + j) * a.n_sel * a.H +
+                                      static_cast<long long>(sel) * a.H);
+  for (int i = threadIdx.x; i < a.H / 8; i += 256) d[i] = s[i];
+}
+
+struct SetStateArgs {
+  int r;
+  int start, ctx_len;
+  int* start_p;
+  int* ctx_len_p;
+};
+__global__ void set_state_kernel(const SetStateArgs a) {
+  pdl_wait();
+  a.start_p[a.r] = a.start;
+  a.ctx_len_p[a.r] = a.ctx_len;
+}
+
+}  // namespace dfl

@@ -1,0 +1,286 @@
+"""Host side of the draft/verify engine: packs the draft's weights once, owns the device workspace
+(one torch allocation carved by the C library), and enqueues the step kernels through the C ABI.
+
+PyTorch is plumbing here (device memory, streams, CUDA-graph capture); all arithmetic of the hot path
+runs in libdflash_b200.so. There is no fallback: a missing library or a non-sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import (POINTER, Structure, byref, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p)
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+class CConfig(Structure):
+    _fields_ = [
+        ("hidden", c_int), ("intermediate", c_int), ("n_layers", c_int), ("n_q_heads", c_int),
+        ("n_kv_heads", c_int), ("head_dim", c_int), ("vocab", c_int), ("n_sel", c_int), ("block_size", c_int),
+        ("max_requests", c_int), ("max_seq", c_int), ("out_len", c_int), ("hist_len", c_int),
+        ("rms_eps", c_float), ("rope_scale", c_float), ("mask_token_id", c_longlong), ("attn_splits", c_int),
+        ("post_splits", c_int), ("gemm_grid", c_int), ("use_pdl", c_int), ("keep_draft_logits", c_int),
+    ]
+
+
+class CLayerWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm")]
+
+
+class CWeights(Structure):
+    _fields_ = [("embed", c_void_p), ("lm_head", c_void_p), ("fc", c_void_p), ("hidden_norm", c_void_p),
+                ("final_norm", c_void_p), ("inv_freq", c_void_p), ("layers_host", POINTER(CLayerWeights))]
+
+
+# enum dflash_buffer_id (include/dflash_b200.h) -> (name, torch dtype)
+BUFFERS = [
+    ("x", torch.bfloat16), ("a_in", torch.bfloat16), ("ctx_feat", torch.bfloat16), ("q", torch.bfloat16),
+    ("attn_out", torch.bfloat16), ("a2", torch.bfloat16), ("hmid", torch.bfloat16), ("hn", torch.bfloat16),
+    ("kv", torch.bfloat16), ("ws", torch.float32), ("attn_po", torch.float32), ("attn_ml", torch.float32),
+    ("cand_val", torch.float32), ("cand_idx", torch.int32), ("post_val", torch.float32), ("post_idx", torch.int32),
+    ("draft_tokens", torch.int64), ("block_ids", torch.int64), ("posterior", torch.int64),
+    ("output_ids", torch.int64), ("start", torch.int32), ("ctx_len", torch.int32), ("done", torch.int32),
+    ("n_cycles", torch.int32), ("blk_len", torch.int32), ("max_len", torch.int32), ("acc_hist", torch.int32),
+    ("rng_step", torch.int64), ("draft_logits", torch.bfloat16),
+]
+
+
+def _declare(lib):
+    if getattr(lib, "_dflash_engine_declared", False):
+        return
+    lib.dflash_workspace_bytes.restype = c_size_t
+    lib.dflash_workspace_bytes.argtypes = [POINTER(CConfig)]
+    lib.dflash_engine_create.restype = c_int
+    lib.dflash_engine_create.argtypes = [POINTER(CConfig), POINTER(CWeights), c_void_p, c_size_t, POINTER(c_void_p)]
+    lib.dflash_engine_destroy.restype = None
+    lib.dflash_engine_destroy.argtypes = [c_void_p]
+    lib.dflash_engine_buffer.restype = c_int
+    lib.dflash_engine_buffer.argtypes = [c_void_p, c_int, POINTER(c_void_p), POINTER(c_size_t)]
+    lib.dflash_prefill_context.restype = c_int
+    lib.dflash_prefill_context.argtypes = [c_void_p, c_int, POINTER(c_void_p), c_int, c_void_p]
+    lib.dflash_draft_step.restype = c_int
+    lib.dflash_draft_step.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    lib.dflash_verify_step.restype = c_int
+    lib.dflash_verify_step.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, POINTER(c_void_p), c_float,
+                                       c_void_p, c_ulonglong, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
+    lib.dflash_sample.restype = c_int
+    lib.dflash_sample.argtypes = [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_ulonglong, c_void_p,
+                                  c_void_p, c_int, c_void_p, c_void_p]
+    lib._dflash_engine_declared = True
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class PackedDraftWeights:
+    """bf16 device copies of the draft's matrices in the fused layouts the kernels stream
+    (q/k/v stacked, gate/up stacked). When `alias` is set the module's own parameters are re-pointed at
+    views of the packed buffers, so the state-dict keys survive and nothing is stored twice."""
+
+    def __init__(self, draft, device, alias: bool = True):
+        bf = torch.bfloat16
+        self.layers = []
+        for layer in draft.layers:
+            at, mlp = layer.self_attn, layer.mlp
+            if getattr(at.q_proj, "bias", None) is not None:
+                raise _lib.DFlashNativeError("attention_bias=True drafts are not supported by the CUDA path")
+            wqkv = torch.cat([at.q_proj.weight, at.k_proj.weight, at.v_proj.weight], 0).to(device=device, dtype=bf).contiguous()
+            wgu = torch.cat([mlp.gate_proj.weight, mlp.up_proj.weight], 0).to(device=device, dtype=bf).contiguous()
+            ent = dict(
+                wqkv=wqkv, wgu=wgu,
+                wo=at.o_proj.weight.detach().to(device=device, dtype=bf).contiguous(),
+                wd=mlp.down_proj.weight.detach().to(device=device, dtype=bf).contiguous(),
+                ln1=layer.input_layernorm.weight.detach().to(device=device, dtype=bf).contiguous(),
+                ln2=layer.post_attention_layernorm.weight.detach().to(device=device, dtype=bf).contiguous(),
+                q_norm=at.q_norm.weight.detach().to(device=device, dtype=bf).contiguous(),
+                k_norm=at.k_norm.weight.detach().to(device=device, dtype=bf).contiguous(),
+            )
+            if alias and at.q_proj.weight.dtype == bf and at.q_proj.weight.device == wqkv.device:
+                nq, nk = at.q_proj.weight.shape[0], at.k_proj.weight.shape[0]
+                at.q_proj.weight.data = wqkv[:nq]
+                at.k_proj.weight.data = wqkv[nq:nq + nk]
+                at.v_proj.weight.data = wqkv[nq + nk:]
+                ni = mlp.gate_proj.weight.shape[0]
+                mlp.gate_proj.weight.data = wgu[:ni]
+                mlp.up_proj.weight.data = wgu[ni:]
+            self.layers.append(ent)
+        self.fc = draft.fc.weight.detach().to(device=device, dtype=bf).contiguous()
+        self.hidden_norm = draft.hidden_norm.weight.detach().to(device=device, dtype=bf).contiguous()
+        self.final_norm = draft.norm.weight.detach().to(device=device, dtype=bf).contiguous()
+        self.inv_freq = draft.rotary_emb.inv_freq.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.rope_scale = float(getattr(draft.rotary_emb, "attention_scaling", 1.0))
+
+
+class DraftEngine:
+    """One GPU's draft+verify engine for `max_requests` request streams (ABI v1: 1 or 2)."""
+
+    def __init__(self, draft, embed_weight: torch.Tensor, lm_head_weight: torch.Tensor, *, max_seq: int,
+                 out_len: int, max_requests: int = 1, block_size: Optional[int] = None, use_pdl: bool = True,
+                 keep_draft_logits: bool = False, gemm_grid: int = 0, attn_splits: int = 0, hist_len: int = 4096,
+                 device=None):
+        self.lib = _lib.load()
+        _declare(self.lib)
+        if not torch.cuda.is_available():
+            raise _lib.DFlashNativeError("dflash_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device if device is not None else embed_weight.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dflash_device_check(), "dflash_device_check")
+        cfg = draft.config
+        self.block_size = int(block_size or draft.block_size)
+        self.R = int(max_requests)
+        self.n_sel = len(draft.target_layer_ids)
+        self.hidden = cfg.hidden_size
+        self.vocab = int(lm_head_weight.shape[0])
+        self.mask_token_id = int(draft.mask_token_id)
+        bf = torch.bfloat16
+        if embed_weight.dtype != bf or lm_head_weight.dtype != bf:
+            raise _lib.DFlashNativeError("the CUDA path computes in bf16: load the target with dtype=torch.bfloat16")
+        self.embed = embed_weight.detach().contiguous()
+        self.lm_head = lm_head_weight.detach().contiguous()
+        self.weights = PackedDraftWeights(draft, self.device)
+        head_dim = getattr(cfg, "head_dim", cfg.hidden_size // cfg.num_attention_heads)
+        self.ccfg = CConfig(
+            hidden=cfg.hidden_size, intermediate=cfg.intermediate_size, n_layers=cfg.num_hidden_layers,
+            n_q_heads=cfg.num_attention_heads, n_kv_heads=cfg.num_key_value_heads, head_dim=head_dim,
+            vocab=self.vocab, n_sel=self.n_sel, block_size=self.block_size, max_requests=self.R,
+            max_seq=int(max_seq), out_len=int(out_len), hist_len=int(hist_len), rms_eps=float(cfg.rms_norm_eps),
+            rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id, attn_splits=attn_splits,
+            post_splits=0, gemm_grid=gemm_grid, use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits))
+        self.max_seq, self.out_len = int(max_seq), int(out_len)
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.dflash_workspace_bytes(byref(self.ccfg))
+            if nbytes == 0:
+                _lib.check(-1, "dflash_workspace_bytes")
+            self.workspace = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 1024
+            self._ws_view = self.workspace[off:off + nbytes]
+            arr = (CLayerWeights * len(self.weights.layers))()
+            for i, ent in enumerate(self.weights.layers):
+                for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm"):
+                    setattr(arr[i], k, ent[k].data_ptr())
+            self._layer_arr = arr
+            cw = CWeights(embed=self.embed.data_ptr(), lm_head=self.lm_head.data_ptr(), fc=self.weights.fc.data_ptr(),
+                          hidden_norm=self.weights.hidden_norm.data_ptr(), final_norm=self.weights.final_norm.data_ptr(),
+                          inv_freq=self.weights.inv_freq.data_ptr(), layers_host=arr)
+            h = c_void_p()
+            _lib.check(self.lib.dflash_engine_create(byref(self.ccfg), byref(cw), c_void_p(self._ws_view.data_ptr()),
+                                                     nbytes, byref(h)), "dflash_engine_create")
+        self.handle = h
+        self.buf = {}
+        base = self._ws_view.data_ptr()
+        for i, (name, dt) in enumerate(BUFFERS):
+            p, n = c_void_p(), c_size_t()
+            _lib.check(self.lib.dflash_engine_buffer(self.handle, i, byref(p), byref(n)), "dflash_engine_buffer")
+            o = (p.value or base) - base
+            self.buf[name] = self._ws_view[o:o + n.value].view(dt)
+        R, bs = self.R, self.block_size
+        self.block_ids = self.buf["block_ids"].view(R, bs)
+        self.posterior = self.buf["posterior"].view(R, bs)
+        self.output_ids = self.buf["output_ids"].view(R, self.out_len)
+        self.acc_hist = self.buf["acc_hist"].view(R, hist_len)
+        self.SL = 16 if bs <= 16 else 32
+        self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
+        self.kernels_per_draft_step = 3 + 10 * cfg.num_hidden_layers + 2
+        self.kernels_per_verify_step = 3
+        self._graph = None
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.dflash_engine_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def reset_request(self, r: int, prompt: torch.Tensor, first_token: int, max_new_tokens: int):
+        """Host-side (not hot path) initialisation of request r, mirroring dflash.py:206-229."""
+        P = int(prompt.numel())
+        if P + max_new_tokens + self.block_size > self.out_len:
+            raise ValueError("out_len too small for prompt + max_new_tokens + block_size")
+        if P + max_new_tokens + 2 * self.block_size > self.max_seq:
+            raise ValueError("max_seq too small for prompt + max_new_tokens + 2*block_size")
+        out = self.output_ids[r]
+        out.fill_(self.mask_token_id)
+        out[:P] = prompt.to(out.device).view(-1)
+        out[P] = first_token
+        blk = self.block_ids[r]
+        blk.fill_(self.mask_token_id)
+        blk[0] = first_token
+        self.buf["start"][r] = P
+        self.buf["ctx_len"][r] = 0
+        self.buf["done"][r] = 0
+        self.buf["n_cycles"][r] = 0
+        self.buf["blk_len"][r] = self.block_size
+        self.buf["max_len"][r] = P + max_new_tokens
+
+    def prefill_context(self, r: int, hidden: Sequence[torch.Tensor]):
+        """hidden[s]: [P, H] bf16 rows of the selected target layers for the prompt."""
+        assert len(hidden) == self.n_sel
+        hs = [h.contiguous() for h in hidden]
+        P = hs[0].shape[0]
+        arr = (c_void_p * self.n_sel)(*[h.data_ptr() for h in hs])
+        _lib.check(self.lib.dflash_prefill_context(self.handle, r, arr, P, _stream()), "dflash_prefill_context")
+        self._keep = hs
+
+    def draft_step(self, noise_embedding: Optional[torch.Tensor] = None, lm_head: bool = True):
+        _lib.check(self.lib.dflash_draft_step(self.handle, _p(noise_embedding), int(lm_head), _stream()),
+                   "dflash_draft_step")
+
+    def verify_step(self, target_logits: Optional[torch.Tensor], hidden: Sequence[torch.Tensor], *,
+                    temperature: float = 0.0, posterior_in: Optional[torch.Tensor] = None,
+                    noise: Optional[torch.Tensor] = None, seed: int = 0, stop_ids: Optional[torch.Tensor] = None,
+                    forced_k: Optional[torch.Tensor] = None, clamp_tail: bool = False):
+        """target_logits: [R*bs, V] bf16 (last dim contiguous); hidden[s]: [R*bs, H] bf16 contiguous."""
+        arr = (c_void_p * self.n_sel)(*[h.data_ptr() for h in hidden])
+        ld = 0 if target_logits is None else target_logits.stride(-2)
+        n_stop = 0 if stop_ids is None else int(stop_ids.numel())
+        fld = 0 if forced_k is None else int(forced_k.shape[-1])
+        _lib.check(self.lib.dflash_verify_step(self.handle, _p(target_logits), ld, _p(posterior_in), arr,
+                                               float(temperature), _p(noise), int(seed) & (2**64 - 1), _p(stop_ids),
+                                               n_stop, _p(forced_k), fld, int(clamp_tail), _stream()),
+                   "dflash_verify_step")
+
+    def sample(self, logits: torch.Tensor, temperature: float, seed: int = 0, noise: Optional[torch.Tensor] = None):
+        """sample() of model/utils.py:27-34 on [rows, V] bf16 logits -> int64 [rows]."""
+        rows, V = logits.shape
+        nsplit = 8
+        sv = torch.empty(rows * nsplit, dtype=torch.float32, device=logits.device)
+        si = torch.empty(rows * nsplit, dtype=torch.int32, device=logits.device)
+        out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+        _lib.check(self.lib.dflash_sample(_p(logits), logits.stride(0), rows, V, float(temperature), _p(noise),
+                                          int(seed) & (2**64 - 1), _p(sv), _p(si), nsplit, _p(out), _stream()),
+                   "dflash_sample")
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def capture_draft_graph(self):
+        """Capture one draft step (static pointers, device-resident state) into a CUDA graph."""
+        torch.cuda.synchronize(self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.draft_step()  # warm up (module load, func attributes) outside capture
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            self.draft_step()
+        self._graph = g
+        return g
+
+    def draft_step_graphed(self):
+        if self._graph is None:
+            self.capture_draft_graph()
+        self._graph.replay()

@@ -1,0 +1,60 @@
+"""Hot-path helpers with the reference's names and signatures (model/utils.py:4-34).
+
+`build_target_layer_ids` and `extract_context_feature` are host-side index/view logic. `sample`
+dispatches CUDA bf16 logits to the fused sampler in libdflash_b200.so.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+
+def build_target_layer_ids(num_target_layers: int, num_draft_layers: int) -> List[int]:
+    """Evenly spaced target layer ids in [1, L-3] (model/utils.py:4-14)."""
+    if num_draft_layers == 1:
+        return [num_target_layers // 2]
+    start = 1
+    end = num_target_layers - 3
+    span = end - start
+    return [int(round(start + (i * span) / (num_draft_layers - 1))) for i in range(num_draft_layers)]
+
+
+def select_context_states(hidden_states: Sequence[torch.Tensor], layer_ids: Optional[Sequence[int]]) -> List[torch.Tensor]:
+    """The tensors extract_context_feature would concatenate: hidden_states[id + 1] per selected layer
+    (entry 0 is the embedding output). The CUDA path gathers from these directly and never builds the cat."""
+    return [hidden_states[i + 1] for i in layer_ids]
+
+
+def extract_context_feature(hidden_states: Sequence[torch.Tensor], layer_ids: Optional[Sequence[int]]) -> torch.Tensor:
+    """Same result as the reference (model/utils.py:16-25); kept for callers that want the tensor."""
+    return torch.cat(select_context_states(hidden_states, layer_ids), dim=-1)
+
+
+def sample(logits: torch.Tensor, temperature: float = 0.0, *, seed: Optional[int] = None,
+           noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, S, V] logits -> [B, S] int64 tokens (model/utils.py:27-34): argmax below T=1e-5, otherwise a draw
+    from softmax(logits / T) by the exponential race torch.multinomial uses, fused into one pass over the
+    vocab in CUDA. `noise` (fp32 [B*S, V] Exp(1) draws) reproduces a given torch.multinomial stream."""
+    from . import _lib
+    from .engine import _declare, _p, _stream
+    if not logits.is_cuda:
+        raise _lib.DFlashNativeError("dflash_b200.sample needs CUDA logits; there is no CPU path")
+    lib = _lib.load()
+    _declare(lib)
+    bsz, seq_len, vocab = logits.shape
+    flat = logits.reshape(-1, vocab)
+    if flat.dtype != torch.bfloat16:
+        flat = flat.to(torch.bfloat16)
+    if flat.stride(-1) != 1:
+        flat = flat.contiguous()
+    rows, nsplit = flat.shape[0], 8
+    sv = torch.empty(rows * nsplit, dtype=torch.float32, device=flat.device)
+    si = torch.empty(rows * nsplit, dtype=torch.int32, device=flat.device)
+    out = torch.empty(rows, dtype=torch.int64, device=flat.device)
+    if seed is None:
+        seed = int(torch.randint(0, 2**62, (1,)).item()) if temperature >= 1e-5 else 0
+    with torch.cuda.device(flat.device):
+        _lib.check(lib.dflash_sample(_p(flat), flat.stride(0), rows, vocab, float(temperature), _p(noise),
+                                     int(seed), _p(sv), _p(si), nsplit, _p(out), _stream()), "dflash_sample")
+    return out.view(bsz, seq_len)

@@ -3,14 +3,17 @@
  * Plain pointers and sizes only (no torch types). Every pointer is a DEVICE pointer unless the
  * name ends in _host. `stream` is a cudaStream_t passed as void*. No entry point allocates device
  * memory or synchronises; all return DFLASH_OK (0) or a negative error (dflash_last_error() holds
- * the message for the calling thread). The library contains sm_100a code only.
+ * the message for the calling thread). The library contains sm_100a code only; there is no CPU
+ * path behind it.
  *
- * The reference (AtharvRN/dflash) is pure Python; it has no FFI. Each entry point names the
- * reference call site(s) (file:line under the reference tree) it replaces; INTEGRATION.md shows
- * the ctypes binding a reference maintainer would add.
+ * The reference (AtharvRN/dflash) is pure Python and has no FFI of its own. Each entry point names
+ * the reference call site(s) (file:line under the reference tree) it replaces; INTEGRATION.md shows
+ * the ctypes binding a reference maintainer would add to model/dflash.py.
  */
 #ifndef DFLASH_B200_H_
 #define DFLASH_B200_H_
+
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -21,7 +24,7 @@ extern "C" {
 #define DFLASH_OK 0
 #define DFLASH_ERR_ARG (-1)   /* bad argument / unsupported shape */
 #define DFLASH_ERR_CUDA (-2)  /* CUDA runtime / driver call failed */
-#define DFLASH_ERR_ARCH (-3)  /* not an sm_100a device */
+#define DFLASH_ERR_ARCH (-3)  /* not an sm_100 device */
 
 int dflash_abi_version(void);
 const char* dflash_last_error(void);
@@ -29,9 +32,147 @@ const char* dflash_last_error(void);
 /* Returns the SM count of the current device (>0) or DFLASH_ERR_ARCH if it is not sm_100. */
 int dflash_device_check(void);
 
-/* ---------------------------------------------------------------------------------------------
+/* =============================================================================================
+ * Engine: the draft+verify step for `max_requests` independent request streams on one GPU.
+ * ===========================================================================================*/
+
+/* Mirrors the Qwen3Config keys DFlashDraftModel consumes (model/dflash.py:33-56,157-163). */
+typedef struct dflash_config {
+  int hidden;           /* hidden_size */
+  int intermediate;     /* intermediate_size */
+  int n_layers;         /* num_hidden_layers of the draft */
+  int n_q_heads;        /* num_attention_heads */
+  int n_kv_heads;       /* num_key_value_heads */
+  int head_dim;         /* must be 128 */
+  int vocab;            /* rows of the target's lm_head / embed_tokens */
+  int n_sel;            /* len(target_layer_ids) */
+  int block_size;       /* slots per block (2..32); slot 0 is the last committed token */
+  int max_requests;     /* request streams resident in this engine (1 or 2 in ABI v1) */
+  int max_seq;          /* positions per request in the static draft KV cache */
+  int out_len;          /* row length of output_ids (>= prompt + max_new_tokens + block_size) */
+  int hist_len;         /* acceptance-length history entries per request */
+  float rms_eps;
+  float rope_scale;     /* rotary attention_scaling (1.0 for default rope) */
+  long long mask_token_id;
+  int attn_splits;      /* KV splits of the draft attention (0 = default 16) */
+  int post_splits;      /* vocab splits of the posterior sampler (0 = default 8) */
+  int gemm_grid;        /* CTAs per streaming GEMM (0 = SM count) */
+  int use_pdl;          /* programmatic dependent launch between the step's kernels */
+  int keep_draft_logits;/* also store the draft's bf16 logits (parity tests) */
+} dflash_config_t;
+
+/* Packed bf16 weights of one draft layer. wqkv = [q_proj; k_proj; v_proj] rows, wgu = [gate; up]. */
+typedef struct dflash_layer_weights {
+  const void* wqkv;   /* [(Hq+2Hkv)*128, hidden] */
+  const void* wo;     /* [hidden, Hq*128] */
+  const void* wgu;    /* [2*intermediate, hidden] */
+  const void* wd;     /* [hidden, intermediate] */
+  const void* ln1;    /* input_layernorm.weight [hidden] */
+  const void* ln2;    /* post_attention_layernorm.weight [hidden] */
+  const void* q_norm; /* [128] */
+  const void* k_norm; /* [128] */
+} dflash_layer_weights_t;
+
+typedef struct dflash_weights {
+  const void* embed;        /* target.model.embed_tokens.weight [vocab, hidden] */
+  const void* lm_head;      /* target.lm_head.weight [vocab, hidden] */
+  const void* fc;           /* fc.weight [hidden, n_sel*hidden] */
+  const void* hidden_norm;  /* [hidden] */
+  const void* final_norm;   /* norm.weight [hidden] */
+  const float* inv_freq;    /* rotary_emb.inv_freq [64] fp32 */
+  const dflash_layer_weights_t* layers_host; /* HOST array of n_layers entries */
+} dflash_weights_t;
+
+/* Named regions of the caller-owned workspace (dflash_engine_buffer). */
+enum dflash_buffer_id {
+  DFLASH_BUF_X = 0,        /* bf16 [R*SL, hidden] residual stream of the block rows */
+  DFLASH_BUF_A_IN,         /* bf16 [2*R*SL, hidden] context rows then normed block rows */
+  DFLASH_BUF_CTX_FEAT,     /* bf16 [R*SL, n_sel*hidden] pending target-context features */
+  DFLASH_BUF_Q,            /* bf16 [R*SL, Hq, 128] */
+  DFLASH_BUF_ATTN_OUT,     /* bf16 [R*SL, Hq*128] */
+  DFLASH_BUF_A2,           /* bf16 [R*SL, hidden] */
+  DFLASH_BUF_HMID,         /* bf16 [R*SL, intermediate] */
+  DFLASH_BUF_HN,           /* bf16 [R*SL, hidden] final-normed hidden = DFlashDraftModel.forward output */
+  DFLASH_BUF_KV,           /* bf16 [n_layers, 2, R, Hkv, max_seq, 128] static draft KV cache */
+  DFLASH_BUF_WS,           /* fp32 split-K partials */
+  DFLASH_BUF_ATTN_PO,
+  DFLASH_BUF_ATTN_ML,
+  DFLASH_BUF_CAND_VAL,
+  DFLASH_BUF_CAND_IDX,
+  DFLASH_BUF_POST_VAL,
+  DFLASH_BUF_POST_IDX,
+  DFLASH_BUF_DRAFT_TOKENS, /* int64 [R*SL] argmax of every block row */
+  DFLASH_BUF_BLOCK_IDS,    /* int64 [R, block_size] block tokens (feeds the target's verify forward) */
+  DFLASH_BUF_POSTERIOR,    /* int64 [R, block_size] */
+  DFLASH_BUF_OUTPUT_IDS,   /* int64 [R, out_len] */
+  DFLASH_BUF_START,        /* int32 [R] committed length == both cache lengths */
+  DFLASH_BUF_CTX_LEN,      /* int32 [R] pending context rows (= previous tau) */
+  DFLASH_BUF_DONE,         /* int32 [R] */
+  DFLASH_BUF_N_CYCLES,     /* int32 [R] */
+  DFLASH_BUF_BLK_LEN,      /* int32 [R] effective block length of the next cycle */
+  DFLASH_BUF_MAX_LEN,      /* int32 [R] prompt length + max_new_tokens */
+  DFLASH_BUF_ACC_HIST,     /* int32 [R, hist_len] tau per cycle */
+  DFLASH_BUF_RNG_STEP,     /* uint64 [1] */
+  DFLASH_BUF_DRAFT_LOGITS, /* bf16 [R*SL, vocab] when keep_draft_logits */
+  DFLASH_BUF_COUNT
+};
+
+typedef struct dflash_engine dflash_engine_t;
+
+/* Bytes of device workspace an engine of this config needs (0 + error on a bad config). */
+size_t dflash_workspace_bytes(const dflash_config_t* cfg_host);
+
+/* Builds the engine (host object: TMA descriptors, kernel schedule) over caller-owned memory.
+ * `workspace` must be 1024-byte aligned, zero-initialised device memory. */
+int dflash_engine_create(const dflash_config_t* cfg_host, const dflash_weights_t* weights_host,
+                         void* workspace, size_t workspace_bytes, dflash_engine_t** out_host);
+void dflash_engine_destroy(dflash_engine_t* e);
+
+/* Device pointer + size of a named workspace region. */
+int dflash_engine_buffer(const dflash_engine_t* e, int buffer_id, void** ptr_out_host, size_t* bytes_out_host);
+
+/* Prompt context for request r: P rows of each selected target hidden state
+ * (hidden_host[s] -> device [P, hidden] bf16) are projected (fc + hidden_norm) and their per-layer
+ * K/V written to cache positions [0, P). Sets start[r] = P, ctx_len[r] = 0.
+ * Replaces cycle 0 of model/dflash.py:229,238-246 (c = P) and the fc/hidden_norm/k_proj/v_proj/
+ * k_norm/RoPE call sites at :73-82,177. */
+int dflash_prefill_context(dflash_engine_t* e, int r, const void* const* hidden_host, int P, void* stream);
+
+/* One draft step for all requests: embed(block_ids) -> ctx injection of the pending context rows
+ * -> n_layers x (QKV, attention over [ctx | block], O, SwiGLU MLP) -> norm -> lm_head + argmax.
+ * Writes the drafted tokens to block_ids[:, 1:]; the final-normed hidden (what
+ * DFlashDraftModel.forward returns) stays in DFLASH_BUF_HN.
+ * noise_embedding: NULL to gather target.embed_tokens(block_ids) in-kernel, or device bf16
+ *   [R*SL, hidden] rows supplied by a forward(noise_embedding=...) caller.
+ * run_lm_head: 0 stops after the final norm (plain forward()).
+ * Replaces model/dflash.py:235-247 (embed_tokens, DFlashDraftModel.forward, target.lm_head,
+ * past_key_values_draft.crop, sample). */
+int dflash_draft_step(dflash_engine_t* e, const void* noise_embedding, int run_lm_head, void* stream);
+
+/* Verify step after the target's forward over block_ids:
+ *   posterior = sample(target_logits, temperature); acceptance = longest prefix with
+ *   block[1:] == posterior[:-1]; commit accepted tokens + bonus token to output_ids; advance
+ *   start (== crop of both caches); stop check; block_ids <- [bonus, mask...]; gather the first
+ *   tau rows of the selected hidden states as the next context features.
+ * target_logits: [R*block_size, vocab] bf16, row pitch logits_ld elements (or NULL when
+ *   posterior_in [R, block_size] int64 holds already-sampled tokens).
+ * hidden_host[s]: device [R*block_size, hidden] bf16 for each selected target layer.
+ * noise: optional fp32 [R*block_size, vocab] Exp(1) draws (torch.multinomial's race), else Philox.
+ * forced_k: optional int32 [R, forced_ld] harness hook: posterior[:k] = block[1:k+1] (k indexed by cycle).
+ * Replaces model/dflash.py:257-268 and model/utils.py:16-34. */
+int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long logits_ld,
+                       const long long* posterior_in, const void* const* hidden_host, float temperature,
+                       const float* noise, unsigned long long seed, const long long* stop_ids, int n_stop,
+                       const int* forced_k, int forced_ld, int clamp_tail, void* stream);
+
+/* tokens_out[row] = sample(logits[row, :], temperature) for standalone use (prefill's first token). */
+int dflash_sample(const void* logits, long long logits_ld, int rows, int vocab, float temperature,
+                  const float* noise, unsigned long long seed, float* scratch_val, int* scratch_idx,
+                  int nsplit, long long* tokens_out, void* stream);
+
+/* =============================================================================================
  * Raw operators (unit-test granularity).
- * ------------------------------------------------------------------------------------------- */
+ * ===========================================================================================*/
 
 /* out[m, n] = sum_k X[x_row0+m, k] * W[w_row0+n, k]   (fp32 out; bf16 in; nn.Linear layout)
  * Replaces torch.nn.Linear on the draft path (model/dflash.py:70-76,101,177; Qwen3MLP via :143).

@@ -1,0 +1,280 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Tolerances (BASELINE.json north_star): acceptance decisions / commit indices bit-exact given identical
+logits; greedy draft tokens identical except at near-ties (top-2 margin < 1e-3 relative to the logit scale
+in bf16 -- we use 2 bf16 ulps of the top logit); draft logits within 2e-2 relative in bf16.
+"""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 2e-2
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+# ------------------------------------------------------------------------------------------------
+# raw GEMMs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K,mb", [(256, 128, 16), (4096, 4096, 16), (6144, 4096, 32), (1000, 512, 16),
+                                    (4096, 12288, 16), (512, 20480, 16), (2048, 2048, 64), (1024, 1024, 256)])
+@pytest.mark.parametrize("grid", [148, 37])
+def test_gemm_skinny(N, K, mb, grid):
+    dev = _cuda()
+    from dflash_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(N + K + mb)
+    W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+    X = torch.randn(mb, K, device=dev).to(torch.bfloat16)
+    slots = lib.dflash_gemm_max_slots(N, K, grid)
+    assert slots >= 1
+    ws = torch.zeros(slots, mb, N, dtype=torch.float32, device=dev)
+    out = torch.zeros(mb, N, dtype=torch.float32, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.dflash_gemm_skinny(_ptr(W), N, 0, N, K, _ptr(X), mb, 0, mb, mb, _ptr(ws), mb, N, _ptr(out), N,
+                                      grid, 0, st))
+    torch.cuda.synchronize()
+    ref = X.float() @ W.float().t()
+    assert (out - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_argmax_matches_own_logits():
+    dev = _cuda()
+    from dflash_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    V, K = 151936 // 8 + 40, 1024  # not a multiple of 128
+    W = (torch.randn(V, K, device=dev) * 0.03).to(torch.bfloat16)
+    X = torch.randn(16, K, device=dev).to(torch.bfloat16)
+    grid = 148
+    cv = torch.empty(grid, 16, dtype=torch.float32, device=dev)
+    ci = torch.empty(grid, 16, dtype=torch.int32, device=dev)
+    logits = torch.empty(16, V, dtype=torch.bfloat16, device=dev)
+    toks = torch.empty(16, dtype=torch.int64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.dflash_gemm_argmax(_ptr(W), V, V, K, _ptr(X), 16, 0, 16, 16, _ptr(cv), _ptr(ci), _ptr(logits), V,
+                                      _ptr(toks), grid, 0, st))
+    torch.cuda.synchronize()
+    ref = X.float() @ W.float().t()
+    assert _rel_err(logits, ref) < 1e-2
+    # lowest-index argmax of the bf16 logits (torch CPU argmax semantics)
+    assert toks.cpu().tolist() == logits.float().cpu().argmax(-1).tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler: greedy ties, Gumbel race with supplied noise, Philox distribution
+# ------------------------------------------------------------------------------------------------
+def test_sample_greedy_and_noise_parity():
+    dev = _cuda()
+    from dflash_b200.utils import sample
+    torch.manual_seed(1)
+    V = 151936
+    logits = torch.randn(2, 16, V, device=dev).to(torch.bfloat16)
+    logits[0, 3, 77] = 9.0
+    logits[0, 3, 5000] = 9.0  # exact tie -> lowest index
+    got = sample(logits, 0.0)
+    assert got.cpu().tolist() == logits.float().cpu().argmax(-1).tolist()
+    assert got[0, 3].item() == 77
+    # temperature: same exponential race as torch.multinomial (argmax(p / q), q ~ Exp(1))
+    q = torch.empty(32, V, device=dev, dtype=torch.float32).exponential_(1.0)
+    got = sample(logits, 0.7, noise=q)
+    probs = torch.softmax(logits.float().view(-1, V) / 0.7, dim=-1)
+    ref = (probs / q).argmax(-1)
+    assert (got.view(-1) == ref).float().mean().item() >= 31 / 32  # fp32 rounding of p/q vs log-domain race
+
+
+def test_sample_philox_distribution():
+    dev = _cuda()
+    from dflash_b200.utils import sample
+    V = 8
+    base = torch.tensor([2.0, 1.0, 0.0, -1.0, 0.5, -3.0, 1.5, 0.0])
+    rows = 4096
+    logits = base.to(torch.bfloat16).to(dev).repeat(1, rows, 1)
+    p = torch.softmax(base.to(torch.bfloat16).float() / 1.3, -1)
+    counts = torch.zeros(V)
+    for seed in range(4):
+        t = sample(logits, 1.3, seed=1000 + seed)
+        counts += torch.bincount(t.view(-1).cpu(), minlength=V).float()
+    n = counts.sum()
+    chi2 = (((counts - n * p) ** 2) / (n * p)).sum().item()
+    assert chi2 < 30.0, (chi2, counts.tolist(), (n * p).tolist())  # 7 dof: p(chi2 > 30) ~ 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# engine vs oracle on the tiny pair: teacher-forced replay of an oracle trace
+# ------------------------------------------------------------------------------------------------
+def _tiny(bs, rigged=False, device="cuda:0"):
+    from dflash_b200 import DFlashDraftModel
+    from tests.tiny_models import build_pair, rig_lm_head
+    from tests.golden.make_golden import LIVE
+    target, draft = build_pair(DFlashDraftModel, seed=1234, block_size=bs, dtype=torch.bfloat16, device=device)
+    if rigged:
+        rig_lm_head(target, live=LIVE, seed=99)
+    return target, draft
+
+
+def _near_tie(logits_row, tok_a, tok_b):
+    """True if the two candidate tokens' oracle logits are within 2 bf16 ulps of the top logit."""
+    la, lb = logits_row[tok_a].float().item(), logits_row[tok_b].float().item()
+    top = logits_row.float().abs().max().item()
+    return abs(la - lb) <= 2 * top * 2.0 ** -8 + 1e-6
+
+
+@pytest.mark.parametrize("bs", [16, 8])
+@pytest.mark.parametrize("forced", [None, (3, 0, 7, 15, 1, 5, 2, 11)])
+def test_engine_replays_oracle_trace(bs, forced):
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY, draft_state_dict
+    target, draft = _tiny(bs)
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = draft_state_dict(draft)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 37), generator=torch.Generator().manual_seed(7)).to(dev)
+    n_new = 80
+    trace = []
+    out_ref, taus = O.spec_generate(sd, cfg, target, prompt, n_new, None, 0.0, forced_k=forced, trace=trace)
+    P = prompt.shape[1]
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=P + n_new + 3 * bs,
+                      out_len=P + n_new + 2 * bs, max_requests=1, block_size=bs, keep_draft_logits=True, use_pdl=True)
+    pre = trace[0]
+    eng.reset_request(0, prompt[0], pre["first_token"], n_new)
+    eng.prefill_context(0, pre["hidden_sel"])
+    forced_t = None if forced is None else torch.tensor([list(forced)], dtype=torch.int32, device=dev)
+    worst = 0.0
+    flips = 0
+    flip_margins = []
+    for cyc, tr in enumerate(trace[1:]):
+        torch.cuda.synchronize()
+        assert int(eng.buf["start"][0]) == tr["start"]
+        assert eng.block_ids[0, 0].item() == tr["block"][0]
+        eng.draft_step()
+        torch.cuda.synchronize()
+        # final-normed draft hidden and draft logits within 2e-2 relative (bf16)
+        hn = eng.hn[:bs]
+        e_h = _rel_err(hn, tr["draft_hidden"])
+        dl = eng.buf["draft_logits"].view(eng.R * eng.SL, eng.vocab)[1:bs]
+        e_l = _rel_err(dl, tr["draft_logits"])
+        worst = max(worst, e_h, e_l)
+        assert e_h < REL_TOL and e_l < REL_TOL, (cyc, e_h, e_l)
+        # the fused argmax is exact on the engine's own bf16 logits (lowest index on ties) ...
+        got = eng.block_ids[0].cpu().tolist()
+        assert got[1:] == dl.float().cpu().argmax(-1).tolist()
+        # ... so a token can differ from the oracle's only where the oracle's own margin between the two
+        # candidates is inside the logit tolerance (a near-tie at bf16 resolution)
+        for i in range(1, bs):
+            if got[i] != tr["block"][i]:
+                ref_row = tr["draft_logits"][i - 1].float()
+                margin = (ref_row[tr["block"][i]] - ref_row[got[i]]).item()
+                err = (dl[i - 1].float() - ref_row).abs().max().item()
+                assert 0 <= margin <= 2 * err + 1e-6, (cyc, i, got[i], tr["block"][i], margin, err)
+                assert margin <= REL_TOL * ref_row.abs().max().item(), (cyc, i, margin)
+                flips += 1
+                flip_margins.append(round(margin / ref_row.abs().max().item(), 5))
+        # teacher forcing: the target saw the oracle's block, so verify with exactly that block
+        eng.block_ids[0].copy_(torch.tensor(tr["block"], device=dev))
+        eng.verify_step(tr["target_logits"].contiguous(), [h.contiguous() for h in tr["hidden_sel"]],
+                        temperature=0.0, forced_k=forced_t)
+        torch.cuda.synchronize()
+        # acceptance / commit / rollback indices are integer work: bit-exact
+        assert eng.posterior[0].cpu().tolist() == tr["posterior"]
+        assert int(eng.buf["ctx_len"][0]) == tr["tau"]
+        assert int(eng.buf["start"][0]) == tr["start"] + tr["tau"]
+        assert int(eng.acc_hist[0, cyc]) == tr["tau"]
+        nxt = tr["ctx_feat"]  # ctx features consumed by THIS cycle came from the previous verify
+        if cyc > 0:
+            pass
+        feat = eng.buf["ctx_feat"].view(eng.R * eng.SL, -1)[:tr["tau"]]
+        exp = torch.cat(tr["hidden_sel"], dim=-1)[:tr["tau"]]
+        assert torch.equal(feat, exp)
+    n_cyc = len(trace) - 1
+    assert eng.acc_hist[0, :n_cyc].cpu().tolist() == taus
+    final = eng.output_ids[0, :P + n_new].cpu().tolist()
+    exp_final = out_ref[0].cpu().tolist()
+    assert [t for t in final if t != cfg.mask_token_id][:len(exp_final)] == exp_final
+    if forced is not None:
+        assert max(taus) == bs
+    print(f"bs={bs} forced={forced is not None}: cycles={n_cyc} worst rel err={worst:.4f} near-tie flips={flips}/{n_cyc * (bs - 1)} relative margins={flip_margins}")
+    eng.close()
+
+
+def test_forward_dropin_matches_oracle():
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200 import DFlashStaticCache
+    from tests.tiny_models import TINY, draft_state_dict
+    bs = 16
+    target, draft = _tiny(bs)
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = draft_state_dict(draft)
+    g = torch.Generator().manual_seed(11)
+    H, nsel = TINY["hidden"], len(draft.target_layer_ids)
+    th_old = torch.randn(1, 5, nsel * H, generator=g).to(dev, torch.bfloat16)
+    th_new = torch.randn(1, 3, nsel * H, generator=g).to(dev, torch.bfloat16)
+    noise = torch.randn(1, bs, H, generator=g).to(dev, torch.bfloat16)
+    oc = O.DraftCache()
+    r0 = O.draft_forward(sd, cfg, th_old, noise, torch.arange(0, 5 + bs, device=dev).unsqueeze(0), oc)
+    oc.crop(5)
+    r1 = O.draft_forward(sd, cfg, th_new, noise, torch.arange(5, 8 + bs, device=dev).unsqueeze(0), oc)
+    cache = DFlashStaticCache()
+    h0 = draft(target_hidden=th_old, noise_embedding=noise, position_ids=torch.arange(0, 5 + bs, device=dev).unsqueeze(0),
+               past_key_values=cache, use_cache=True, is_causal=False)
+    assert cache.get_seq_length() == 5 + bs
+    cache.crop(5)
+    h1 = draft(target_hidden=th_new, noise_embedding=noise,
+               position_ids=torch.arange(5, 8 + bs, device=dev).unsqueeze(0), past_key_values=cache, use_cache=True,
+               is_causal=False)
+    assert h0.shape == r0.shape and h1.shape == r1.shape
+    assert _rel_err(h0, r0) < REL_TOL and _rel_err(h1, r1) < REL_TOL, (_rel_err(h0, r0), _rel_err(h1, r1))
+    draft.release_engine()
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_spec_generate_dropin_is_lossless(temperature):
+    """Product spec_generate end to end with the HF target. Greedy: every generated token must be the target's
+    own greedy choice given the committed prefix (checked in one teacher-forced pass, near-ties excused)."""
+    dev = _cuda()
+    from tests.tiny_models import TINY
+    bs = 16
+    target, draft = _tiny(bs)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 21), generator=torch.Generator().manual_seed(3)).to(dev)
+    out = draft.spec_generate(target, prompt, max_new_tokens=40, stop_token_ids=None, temperature=temperature, seed=5)
+    assert out.shape == (1, 21 + 40) and out.dtype == torch.int64
+    assert torch.equal(out[:, :21], prompt)
+    assert sum(draft.last_acceptance_lengths) >= 40
+    if temperature == 0.0:
+        with torch.inference_mode():
+            logits = target(out).logits[0].float()
+        pred = logits.argmax(-1)
+        for i in range(21 - 1, out.shape[1] - 1):
+            tok = out[0, i + 1].item()
+            if pred[i].item() != tok:
+                assert _near_tie(logits[i], pred[i].item(), tok), (i, pred[i].item(), tok)
+    # stop token: generation ends right after its first occurrence
+    stop = [int(out[0, 21 + 7])]
+    out2 = draft.spec_generate(target, prompt, max_new_tokens=40, stop_token_ids=stop, temperature=0.0)
+    gen = out2[0, 21:].tolist()
+    if temperature == 0.0:
+        assert gen[-1] == stop[0] and stop[0] not in gen[:-1] and len(gen) <= 8
+    # tail clamp (benchmark.py:104-105) gives the same greedy tokens
+    out3 = draft.spec_generate(target, prompt, max_new_tokens=40, stop_token_ids=None, temperature=0.0, clamp_tail=True)
+    assert out3.shape == (1, 61)
+    with pytest.raises(RuntimeError):
+        draft.spec_generate(target, torch.cat([prompt, prompt]), 8, None, 0.0)
+    draft.release_engine()

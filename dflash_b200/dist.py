@@ -1,0 +1,98 @@
+"""Request-level data parallelism (the only parallelism the reference has: benchmark.py:445,
+distributed.py:18-83). One process per GPU, each with a full target + draft replica; requests are
+dealt round-robin; nothing crosses GPUs during decoding. At the end of a run the per-request accepted
+lengths and token streams are all-gathered as fixed-shape integer tensors over NCCL (NVLink/NVSwitch)
+instead of the reference's pickled `gather_object`.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend: str | None = None) -> Tuple[int, int, int]:
+    """env:// init like distributed.py:18-22 (silently single-process when RANK is unset).
+    Returns (rank, world_size, local_rank)."""
+    if "RANK" not in os.environ:
+        return 0, 1, 0
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, init_method="env://")
+    return rank, world, local
+
+
+def is_main() -> bool:
+    return (not dist.is_initialized()) or dist.get_rank() == 0
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
+    """Round-robin request assignment: range(rank, N, world) (benchmark.py:445)."""
+    return list(range(rank, n_items, world))
+
+
+def gather_streams(n_out: torch.Tensor, tokens: torch.Tensor, taus: torch.Tensor,
+                   n_items: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All-gather the per-request results of every rank and put them back in global request order.
+
+    n_out  int32 [B_local]            generated tokens per local request
+    tokens int64 [B_local, max_new]   generated token streams (padded)
+    taus   int32 [B_local, max_cyc]   acceptance lengths per cycle (0-padded)
+    Local request j of rank r is global request r + j * world (see shard_indices). Ranks that hold fewer
+    requests than ceil(N / world) pad with rows of zeros. Returns tensors of leading size n_items.
+    """
+    world = world_size()
+    if world == 1:
+        return n_out[:n_items], tokens[:n_items], taus[:n_items]
+    rank = dist.get_rank()
+    per = (n_items + world - 1) // world
+
+    def pad(t):
+        if t.shape[0] == per:
+            return t.contiguous()
+        out = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        out[: t.shape[0]] = t
+        return out
+
+    outs = []
+    for t in (n_out, tokens, taus):
+        t = pad(t)
+        buf = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t)
+        # buf row (r * per + j) is global request r + j * world
+        g = buf.view(world, per, *t.shape[1:]).transpose(0, 1).reshape(world * per, *t.shape[1:])
+        outs.append(g[:n_items].contiguous())
+    del rank
+    return outs[0], outs[1], outs[2]
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(x: float, device) -> float:
+    if not dist.is_initialized():
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x: float, device) -> float:
+    if not dist.is_initialized():
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -54,7 +54,7 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   const int H = c.hidden, I = c.intermediate, Hq = c.n_q_heads, Hkv = c.n_kv_heads;
   const int grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
   const int nsa = c.attn_splits > 0 ? c.attn_splits : 16;
-  const int nsp = c.post_splits > 0 ? c.post_splits : 8;
+  const int nsp = c.post_splits > 0 ? c.post_splits : 32;
   const int qkv_cols = (Hq + 2 * Hkv) * 128;
   // widest fp32 partial plane over all GEMMs of the step
   long long ws_elems = 0;
@@ -173,7 +173,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->V = c.vocab; e->nsel = c.n_sel; e->bs = c.block_size;
   e->grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
   e->nsplit_attn = c.attn_splits > 0 ? c.attn_splits : 16;
-  e->nsplit_post = c.post_splits > 0 ? c.post_splits : 8;
+  e->nsplit_post = c.post_splits > 0 ? c.post_splits : 32;
   e->pdl = c.use_pdl != 0;
   e->total = layout_workspace(c, e->reg, sm_count, &e->max_slots);
   if (workspace == nullptr || workspace_bytes < e->total) {
@@ -261,7 +261,7 @@ inline int enqueue_ctx_inject(Engine* e, cudaStream_t st) {
   a.valid_mode = kRowsCtx;
   a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
   a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), 0, st, e->pdl, a), "fc finalize");
+  DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "fc finalize");
   return DFLASH_OK;
 }
 
@@ -324,7 +324,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     a.resid = x;
     a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
     a.out = a_in + static_cast<size_t>(RS) * e->H;
-    DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), 0, st, e->pdl, a), "embed+ln1");
+    DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "embed+ln1");
   }
   int rc = enqueue_ctx_inject(e, st);
   if (rc) return rc;
@@ -360,7 +360,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
       a.resid = x;
       a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
       a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
-      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), 0, st, e->pdl, a), "o finalize");
+      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "o finalize");
     }
     DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
     {
@@ -370,7 +370,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
       sa.rows = RS;
       sa.I = e->I;
       sa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
-      DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I + 255) / 256, RS), dim3(256), 0, st, e->pdl, sa), "swiglu");
+      DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I / 4 + 255) / 256, RS), dim3(256), 0, st, e->pdl, sa), "swiglu");
     }
     DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
     {
@@ -385,7 +385,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
         a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
         a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
       }
-      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), 0, st, e->pdl, a), "down finalize");
+      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "down finalize");
     }
   }
   if (!run_lm_head) return DFLASH_OK;

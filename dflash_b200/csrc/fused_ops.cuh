@@ -1,6 +1,10 @@
 // Small fused kernels around the skinny GEMMs: they consume the fp32 split-K partials, apply the
 // reference's bf16 rounding points (Linear output -> bf16, RMSNorm in fp32 -> bf16 -> * weight,
 // residual add in bf16, SiLU*up in bf16, RoPE in bf16) and produce the next GEMM's activations.
+//
+// All of them are latency-bound (a few hundred KB each): 128-bit accesses, rolled loops (small code:
+// the first version unrolled 32x with 64-bit divisions inline and spent ~45 us in instruction fetch),
+// slot counts per 128-column tile computed once with 32-bit arithmetic.
 #pragma once
 #include "gemm_host.cuh"
 
@@ -9,8 +13,8 @@ namespace dfl {
 // How a consumer finds the partial slots of output column n (mirrors the GEMM's stream-K split).
 struct SlotMap {
   int k_blocks;
-  long long T;
-  long long G;
+  uint32_t T;   // n_tiles * k_blocks   (T * G < 2^31 is checked on the host)
+  uint32_t G;   // CTAs of the producing GEMM
   int ws_rows;
   long long ws_ld;
 };
@@ -18,22 +22,52 @@ struct SlotMap {
 inline SlotMap slot_map_of(const GemmPlan& p) {
   SlotMap s;
   s.k_blocks = p.args.k_blocks;
-  s.T = static_cast<long long>(p.args.n_tiles) * p.args.k_blocks;
-  s.G = p.grid;
+  s.T = static_cast<uint32_t>(p.args.n_tiles) * static_cast<uint32_t>(p.args.k_blocks);
+  s.G = static_cast<uint32_t>(p.grid);
   s.ws_rows = p.args.ws_rows;
   s.ws_ld = p.args.ws_ld;
   return s;
 }
 
+// 32-bit forms of cta_of_unit / tile_num_slots (gemm_skinny.cuh)
+__device__ __forceinline__ uint32_t cta_of_unit32(uint32_t x, uint32_t T, uint32_t G) {
+  return ((x + 1u) * G - 1u) / T;
+}
+__device__ __forceinline__ int tile_slots32(int t, const SlotMap& sm) {
+  const uint32_t kb = static_cast<uint32_t>(sm.k_blocks);
+  return static_cast<int>(cta_of_unit32((t + 1) * kb - 1u, sm.T, sm.G) - cta_of_unit32(t * kb, sm.T, sm.G)) + 1;
+}
+
 // fp32 sum over the slots of (row m, column n), in slot order.
-__device__ __forceinline__ float sum_slots(const float* __restrict__ ws, const SlotMap& sm, int m, int n) {
-  const int t = n / kTileN;
-  const int ns = tile_num_slots(t, sm.k_blocks, sm.T, sm.G);
+__device__ __forceinline__ float sum_slots_n(const float* __restrict__ ws, const SlotMap& sm, int m, int n, int ns) {
   const float* p = ws + static_cast<long long>(m) * sm.ws_ld + n;
   const long long slot_stride = static_cast<long long>(sm.ws_rows) * sm.ws_ld;
   float acc = p[0];
   for (int s = 1; s < ns; ++s) acc += p[s * slot_stride];
   return acc;
+}
+__device__ __forceinline__ float4 sum_slots_4(const float* __restrict__ ws, const SlotMap& sm, int m, int n, int ns) {
+  const float* p = ws + static_cast<long long>(m) * sm.ws_ld + n;
+  const long long slot_stride = static_cast<long long>(sm.ws_rows) * sm.ws_ld;
+  float4 acc = *reinterpret_cast<const float4*>(p);
+  for (int s = 1; s < ns; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(p + s * slot_stride);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&lo);
+  r.y = *reinterpret_cast<uint32_t*>(&hi);
+  return r;
+}
+__device__ __forceinline__ float4 unpack4_bf16(uint2 r) {
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -43,7 +77,8 @@ __global__ void sum_slots_kernel(const float* __restrict__ ws, SlotMap sm, int r
   pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
-  if (n < N && m < rows) out[static_cast<long long>(m) * out_ld + n] = sum_slots(ws, sm, m, n);
+  if (n < N && m < rows)
+    out[static_cast<long long>(m) * out_ld + n] = sum_slots_n(ws, sm, m, n, tile_slots32(n / kTileN, sm));
 }
 
 inline cudaError_t launch_sum_slots(const GemmPlan& p, float* out, long long out_ld, cudaStream_t st) {
@@ -55,14 +90,10 @@ inline cudaError_t launch_sum_slots(const GemmPlan& p, float* out, long long out
 // ---------------------------------------------------------------------------------------------
 // lm_head second stage: per activation row, max over the per-CTA candidates (ties -> lowest index,
 // matching torch.argmax on the bf16 logits: model/utils.py:27-29).
-// tokens[row] (int64) <- argmax. Rows with row_mask[row]==0 are skipped when a mask is given.
-__global__ void reduce_candidates_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
-                                         int n_cta, int mb, int rows, long long* __restrict__ tokens) {
-  pdl_wait();
-  const int row = blockIdx.x;
-  if (row >= rows) return;
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
+__device__ __forceinline__ void argmax_candidates(const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                                                  int n_cta, int mb, int row, float& bv, int& bi) {
+  bv = -INFINITY;
+  bi = 0x7fffffff;
   for (int g = threadIdx.x; g < n_cta; g += 32) {
     const float v = cand_val[static_cast<long long>(g) * mb + row];
     const int i = cand_idx[static_cast<long long>(g) * mb + row];
@@ -74,6 +105,17 @@ __global__ void reduce_candidates_kernel(const float* __restrict__ cand_val, con
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
+}
+
+__global__ void __launch_bounds__(32) reduce_candidates_kernel(const float* __restrict__ cand_val,
+                                                               const int* __restrict__ cand_idx, int n_cta, int mb,
+                                                               int rows, long long* __restrict__ tokens) {
+  pdl_wait();
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  float bv;
+  int bi;
+  argmax_candidates(cand_val, cand_idx, n_cta, mb, row, bv, bi);
   if (threadIdx.x == 0) tokens[row] = bi;
 }
 
@@ -82,7 +124,6 @@ inline cudaError_t launch_reduce_candidates(const float* cand_val, const int* ca
   reduce_candidates_kernel<<<rows, 32, 0, st>>>(cand_val, cand_idx, n_cta, mb, rows, tokens);
   return cudaGetLastError();
 }
-
 
 // Engine form of the lm_head second stage: block row (r, i) -> drafted token for slot i, written
 // into block_ids[r][i] for 1 <= i < bs (slot 0 is the committed token: dflash.py:247).
@@ -99,19 +140,9 @@ __global__ void __launch_bounds__(32) draft_tokens_kernel(const DraftTokArgs a) 
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x;
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int g = threadIdx.x; g < a.n_cta; g += 32) {
-    const float v = a.cand_val[static_cast<long long>(g) * a.mb + row];
-    const int i = a.cand_idx[static_cast<long long>(g) * a.mb + row];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-  }
+  float bv;
+  int bi;
+  argmax_candidates(a.cand_val, a.cand_idx, a.n_cta, a.mb, row, bv, bi);
   if (threadIdx.x == 0) {
     a.draft_tokens[row] = bi;
     const int r = row / a.SL, i = row % a.SL;
@@ -149,57 +180,60 @@ struct RowsArgs {
   float eps;
 };
 
-constexpr int kRowsThreads = 256;
-constexpr int kRowsMaxPerThread = 32;  // H <= 8192
+constexpr int kRowsThreads = 512;
+constexpr int kRowsMaxTiles = 64;  // H <= 8192
 
 // One CTA per row:  v = bf16(sum of partials)           (nn.Linear output dtype)
 //                   v = bf16(resid + v); resid = v       (residual add, model/dflash.py:140,144)
 //                   out = w * bf16(v * rsqrt(mean(v^2) + eps))   (Qwen3RMSNorm, fp32 inside)
+// dynamic smem: H floats (the row, kept between the two passes)
 __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsArgs a) {
   pdl_trigger();
   pdl_wait();
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float red[kRowsThreads / 32];
+  __shared__ int ns_tab[kRowsMaxTiles];
   const int row = blockIdx.x;
   if (a.valid_mode == kRowsCtx) {
     const int r = row / a.SL, j = row % a.SL;
     if (j >= a.ctx_len[r]) return;
   }
-  __shared__ float red[kRowsThreads / 32];
-  float v[kRowsMaxPerThread];
-  float ss = 0.f;
   const long long roff = static_cast<long long>(row) * a.H;
+  const bool from_embed = a.embed != nullptr;
   long long tok = 0;
-  if (a.embed != nullptr) {
+  if (from_embed) {
     const int r = row / a.SL, i = row % a.SL;
-    if (a.ids == nullptr) tok = row;  // `embed` is a [rows, H] embedding matrix already (forward(noise_embedding=...))
+    if (a.ids == nullptr) tok = row;  // `embed` already is a [rows, H] embedding matrix (forward(noise_embedding=))
     else tok = (i < a.bs) ? a.ids[static_cast<long long>(r) * a.ids_ld + i] : a.pad_token;
+  } else {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
+    __syncthreads();
   }
-#pragma unroll
-  for (int k = 0; k < kRowsMaxPerThread; ++k) {
-    const int n = k * kRowsThreads + threadIdx.x;
-    if (n < a.H) {
-      float x;
-      if (a.embed != nullptr) {
-        x = __bfloat162float(a.embed[tok * a.H + n]);
-        if (a.resid != nullptr) a.resid[roff + n] = __float2bfloat16_rn(x);
-      } else {
-        x = bf16_round(sum_slots(a.ws, a.sm, row, n));
-        if (a.resid != nullptr) {
-          x = bf16_round(__bfloat162float(a.resid[roff + n]) + x);
-          a.resid[roff + n] = __float2bfloat16_rn(x);
-        }
+  float ss = 0.f;
+  for (int n = threadIdx.x * 4; n < a.H; n += kRowsThreads * 4) {
+    float4 x;
+    if (from_embed) {
+      x = unpack4_bf16(*reinterpret_cast<const uint2*>(a.embed + tok * a.H + n));
+      if (a.resid != nullptr) *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
+    } else {
+      x = sum_slots_4(a.ws, a.sm, row, n, ns_tab[n / kTileN]);
+      x.x = bf16_round(x.x); x.y = bf16_round(x.y); x.z = bf16_round(x.z); x.w = bf16_round(x.w);
+      if (a.resid != nullptr) {
+        const float4 rsd = unpack4_bf16(*reinterpret_cast<const uint2*>(a.resid + roff + n));
+        x.x = bf16_round(rsd.x + x.x); x.y = bf16_round(rsd.y + x.y);
+        x.z = bf16_round(rsd.z + x.z); x.w = bf16_round(rsd.w + x.w);
+        *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
       }
-      v[k] = x;
-      ss += x * x;
+    }
+    if (a.norm_w == nullptr) {
+      *reinterpret_cast<uint2*>(a.out + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
+    } else {
+      *reinterpret_cast<float4*>(rowbuf + n) = x;
+      ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }
   }
-  if (a.norm_w == nullptr) {
-#pragma unroll
-    for (int k = 0; k < kRowsMaxPerThread; ++k) {
-      const int n = k * kRowsThreads + threadIdx.x;
-      if (n < a.H) a.out[roff + n] = __float2bfloat16_rn(v[k]);
-    }
-    return;
-  }
+  if (a.norm_w == nullptr) return;
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
@@ -207,13 +241,12 @@ __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsA
 #pragma unroll
   for (int w = 0; w < kRowsThreads / 32; ++w) tot += red[w];
   const float rstd = 1.0f / sqrtf(tot / static_cast<float>(a.H) + a.eps);
-#pragma unroll
-  for (int k = 0; k < kRowsMaxPerThread; ++k) {
-    const int n = k * kRowsThreads + threadIdx.x;
-    if (n < a.H) {
-      const float y = bf16_round(v[k] * rstd);
-      a.out[roff + n] = __float2bfloat16_rn(__bfloat162float(a.norm_w[n]) * y);
-    }
+  for (int n = threadIdx.x * 4; n < a.H; n += kRowsThreads * 4) {
+    const float4 x = *reinterpret_cast<const float4*>(rowbuf + n);
+    const float4 w = unpack4_bf16(*reinterpret_cast<const uint2*>(a.norm_w + n));
+    *reinterpret_cast<uint2*>(a.out + roff + n) =
+        pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
+                   w.w * bf16_round(x.w * rstd));
   }
 }
 
@@ -228,16 +261,23 @@ struct SwigluArgs {
   __nv_bfloat16* out;  // [rows, I]
 };
 
+__device__ __forceinline__ float silu_mul_bf16(float g, float u) {
+  g = bf16_round(g);
+  u = bf16_round(u);
+  const float s = bf16_round(g / (1.0f + expf(-g)));
+  return s * u;
+}
+
 __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluArgs a) {
   pdl_trigger();
   pdl_wait();
-  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
   const int m = blockIdx.y;
   if (n >= a.I) return;
-  const float g = bf16_round(sum_slots(a.ws, a.sm, m, n));
-  const float u = bf16_round(sum_slots(a.ws, a.sm, m, a.I + n));
-  const float s = bf16_round(g / (1.0f + expf(-g)));
-  a.out[static_cast<long long>(m) * a.I + n] = __float2bfloat16_rn(s * u);
+  const float4 g = sum_slots_4(a.ws, a.sm, m, n, tile_slots32(n / kTileN, a.sm));
+  const float4 u = sum_slots_4(a.ws, a.sm, m, a.I + n, tile_slots32((a.I + n) / kTileN, a.sm));
+  *reinterpret_cast<uint2*>(a.out + static_cast<long long>(m) * a.I + n) =
+      pack4_bf16(silu_mul_bf16(g.x, u.x), silu_mul_bf16(g.y, u.y), silu_mul_bf16(g.z, u.z), silu_mul_bf16(g.w, u.w));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -293,12 +333,11 @@ __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
   if (kind == 0 && !is_block) return;  // context rows carry no queries
   if (pos < 0 || pos >= a.S_max) return;
   const int head = kind == 0 ? hh : (kind == 1 ? hh - heads_q : hh - heads_q - a.Hkv);
-  const int col0 = hh * 128;
   const int ws_row = row - a.row0;
 
-  float x[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) x[t] = bf16_round(sum_slots(a.ws, a.sm, ws_row, col0 + lane + 32 * t));
+  // head hh covers output columns [hh*128, hh*128+128) = exactly stream-K tile hh
+  const float4 xv = sum_slots_4(a.ws, a.sm, ws_row, hh * 128 + lane * 4, tile_slots32(hh, a.sm));
+  float x[4] = {bf16_round(xv.x), bf16_round(xv.y), bf16_round(xv.z), bf16_round(xv.w)};  // d = 4*lane + t
 
   __nv_bfloat16* dst;
   if (kind == 0) {
@@ -308,32 +347,34 @@ __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
     dst = base + ((static_cast<long long>(r) * a.Hkv + head) * a.S_max + pos) * 128;
   }
   if (kind == 2) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) dst[lane + 32 * t] = __float2bfloat16_rn(x[t]);
+    *reinterpret_cast<uint2*>(dst + lane * 4) = pack4_bf16(x[0], x[1], x[2], x[3]);
     return;
   }
   const __nv_bfloat16* w = kind == 0 ? a.q_norm_w : a.k_norm_w;
   float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
   ss = warp_sum(ss);
   const float rstd = 1.0f / sqrtf(ss * (1.0f / 128.0f) + a.eps);
+  const float4 wv = unpack4_bf16(*reinterpret_cast<const uint2*>(w + lane * 4));
+  x[0] = bf16_round(wv.x * bf16_round(x[0] * rstd));
+  x[1] = bf16_round(wv.y * bf16_round(x[1] * rstd));
+  x[2] = bf16_round(wv.z * bf16_round(x[2] * rstd));
+  x[3] = bf16_round(wv.w * bf16_round(x[3] * rstd));
+  // RoPE: element d pairs with d +- 64 -> held by lane ^ 16; frequency index = d mod 64
+  float o[4];
 #pragma unroll
-  for (int t = 0; t < 4; ++t)
-    x[t] = bf16_round(__bfloat162float(w[lane + 32 * t]) * bf16_round(x[t] * rstd));
-  // RoPE: element d pairs with d +- 64; this lane holds d = lane, lane+32 (first half) and
-  // lane+64, lane+96 (second half); frequency index = d mod 64.
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const float ang = static_cast<float>(pos) * a.inv_freq[lane + 32 * t];
+  for (int t = 0; t < 4; ++t) {
+    const float other = __shfl_xor_sync(0xffffffffu, x[t], 16);
+    const int f = (lane & 15) * 4 + t;
+    const float ang = static_cast<float>(pos) * a.inv_freq[f];
     float sn, cs;
     sincosf(ang, &sn, &cs);
     cs = bf16_round(cs * a.rope_scale);
     sn = bf16_round(sn * a.rope_scale);
-    const float lo = x[t], hi = x[t + 2];
-    const float olo = bf16_round(bf16_round(lo * cs) + bf16_round(-hi * sn));
-    const float ohi = bf16_round(bf16_round(hi * cs) + bf16_round(lo * sn));
-    dst[lane + 32 * t] = __float2bfloat16_rn(olo);
-    dst[lane + 32 * t + 64] = __float2bfloat16_rn(ohi);
+    // first half (lane < 16): x*cos + (-x_hi)*sin ; second half: x*cos + x_lo*sin
+    const float rot = (lane < 16) ? -other : other;
+    o[t] = bf16_round(bf16_round(x[t] * cs) + bf16_round(rot * sn));
   }
+  *reinterpret_cast<uint2*>(dst + lane * 4) = pack4_bf16(o[0], o[1], o[2], o[3]);
 }
 
 }  // namespace dfl

@@ -139,6 +139,10 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   p->args.x_row0 = x_row0;
   p->args.m_valid = m_valid;
   const long long T = static_cast<long long>(p->args.n_tiles) * p->args.k_blocks;
+  if (mode != kModeArgmax && (T + 1) * grid >= (1ll << 31)) {
+    set_error("gemm: %lld work units x %d CTAs overflows the consumers' 32-bit slot arithmetic", T, grid);
+    return -1;
+  }
   if (mode == kModeArgmax) {
     p->grid = grid < p->args.n_tiles ? grid : p->args.n_tiles;
     p->max_slots = 1;

@@ -245,8 +245,8 @@ __global__ void attn_split_kernel(const AttnArgs a) {
 
 // Merge the splits: one warp per (row, q head).
 __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnArgs a) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int RS = a.R * a.SL;
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5);

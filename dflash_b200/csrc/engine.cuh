@@ -233,6 +233,20 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->lm.args.logits = c.keep_draft_logits ? e->buf<__nv_bfloat16>(DFLASH_BUF_DRAFT_LOGITS) : nullptr;
   e->lm.args.logits_ld = e->V;
 #undef DFL_PLAN
+  // Pre-wait L2 prefetch budget per GEMM (HBM work for the time the small kernel in front of it runs).
+  // OFF by default: measured on B200 (profiles/r1_summary.md) it never beat plain TMA streaming -- a byte
+  // that is prefetched crosses the L2 twice (fill, then hit), and L2 throughput is only ~1.6x HBM.
+  {
+    const long long bytes = c.prefetch_mb <= 0 ? 0 : static_cast<long long>(c.prefetch_mb) << 20;
+    set_gemm_prefetch(&e->fc, bytes);
+    for (int l = 0; l < e->L; ++l) {
+      set_gemm_prefetch(&e->qkv[l], bytes);
+      set_gemm_prefetch(&e->o[l], bytes);
+      set_gemm_prefetch(&e->gu[l], bytes);
+      set_gemm_prefetch(&e->d[l], bytes);
+    }
+    set_gemm_prefetch(&e->lm, bytes);
+  }
   cudaError_t ce = cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
   *out = e;

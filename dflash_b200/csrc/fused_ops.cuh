@@ -188,8 +188,10 @@ constexpr int kRowsMaxTiles = 64;  // H <= 8192
 //                   out = w * bf16(v * rsqrt(mean(v^2) + eps))   (Qwen3RMSNorm, fp32 inside)
 // dynamic smem: H floats (the row, kept between the two passes)
 __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsArgs a) {
-  pdl_trigger();
+  // wait first, trigger second: the GEMM behind this kernel then becomes resident exactly when this
+  // kernel starts its real work, and its pre-wait weight prefetch keeps HBM busy meanwhile
   pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float rowbuf[];
   __shared__ float red[kRowsThreads / 32];
   __shared__ int ns_tab[kRowsMaxTiles];
@@ -269,8 +271,8 @@ __device__ __forceinline__ float silu_mul_bf16(float g, float u) {
 }
 
 __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluArgs a) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
   const int m = blockIdx.y;
   if (n >= a.I) return;

@@ -113,6 +113,14 @@ inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl)
   }
 }
 
+// Pre-wait L2 prefetch budget: `bytes` of this GEMM's weights in total, split evenly over its CTAs.
+inline void set_gemm_prefetch(GemmPlan* p, long long bytes) {
+  const long long unit_bytes = static_cast<long long>(kTileN) * kTileK * 2;
+  long long per_cta = bytes <= 0 ? 0 : bytes / unit_bytes / (p->grid > 0 ? p->grid : 1);
+  if (bytes > 0 && per_cta < 1) per_cta = 1;
+  p->args.pf_units = static_cast<int>(per_cta);
+}
+
 // Fill a plan. W: [w_rows_total, K] bf16 (pitch K); the GEMM covers weight rows [w_row0, w_row0+N).
 // X: [x_rows_total, K] bf16 (pitch K); activation rows [x_row0, x_row0+mb) feed the MMA.
 inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, int w_row0, int N, int K,
@@ -130,6 +138,10 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   if (rc) return rc;
   rc = make_tmap_bf16(&p->tmX, X, x_rows_total, K, K, mb);
   if (rc) return rc;
+  p->args.w_ptr = W;
+  p->args.w_ld = K;
+  p->args.w_rows = static_cast<int>(w_rows_total);
+  p->args.pf_units = 0;
   p->mb = mb;
   p->mode = mode;
   p->args.n_tiles = (N + kTileN - 1) / kTileN;

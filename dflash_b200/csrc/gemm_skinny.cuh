@@ -49,6 +49,13 @@ struct GemmArgs {
   int* cand_idx;              // [gridDim.x][MB]
   __nv_bfloat16* logits;      // optional [m_valid][logits_ld] (bf16-rounded), may be null
   long long logits_ld;
+  // Pre-wait L2 prefetch: while this (PDL-launched) kernel waits for its predecessor, the four idle
+  // epilogue warps prefetch the CTA's next `pf_units` weight units (beyond the kStages tiles already
+  // in flight to smem) into L2 with plain prefetch.global.L2, one 128-byte weight-row segment per thread.
+  const void* w_ptr;   // weight matrix base (row-major bf16, pitch w_ld elements)
+  long long w_ld;
+  int w_rows;          // rows of the weight matrix (prefetch bound)
+  int pf_units;        // 0 = off
 };
 
 // The CTA that owns flat unit x when T units are cut into G ranges [floor(g*T/G), floor((g+1)*T/G)).
@@ -208,6 +215,21 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..3)
+    if (a.pf_units > 0) {
+      // pre-wait L2 prefetch of units [u0 + S, u0 + S + pf_units): thread t takes weight row t of each
+      // unit's 128 x 128 B box, so one pass of the 128 threads covers one 16 KB unit
+      const char* wb = static_cast<const char*>(a.w_ptr);
+      long long u = u0 + S;
+      const long long ue = u + a.pf_units < u1 ? u + a.pf_units : u1;
+      for (; u < ue; ++u) {
+        const int tile = static_cast<int>(u / a.k_blocks);
+        const int kb = static_cast<int>(u % a.k_blocks);
+        const int wrow = a.w_row0 + tile * kTileN + static_cast<int>(threadIdx.x);
+        if (wrow < a.w_rows)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;\n" ::"l"(
+              wb + (static_cast<long long>(wrow) * a.w_ld + kb * kTileK) * 2));
+      }
+    }
     pdl_wait();
     int acc = 0;
     uint32_t acc_phase = 0;

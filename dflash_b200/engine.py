@@ -7,6 +7,7 @@ runs in libdflash_b200.so. There is no fallback: a missing library or a non-sm_1
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import (POINTER, Structure, byref, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p)
 from typing import List, Optional, Sequence
 
@@ -22,6 +23,7 @@ class CConfig(Structure):
         ("max_requests", c_int), ("max_seq", c_int), ("out_len", c_int), ("hist_len", c_int),
         ("rms_eps", c_float), ("rope_scale", c_float), ("mask_token_id", c_longlong), ("attn_splits", c_int),
         ("post_splits", c_int), ("gemm_grid", c_int), ("use_pdl", c_int), ("keep_draft_logits", c_int),
+        ("prefetch_mb", c_int),
     ]
 
 
@@ -124,7 +126,7 @@ class DraftEngine:
     def __init__(self, draft, embed_weight: torch.Tensor, lm_head_weight: torch.Tensor, *, max_seq: int,
                  out_len: int, max_requests: int = 1, block_size: Optional[int] = None, use_pdl: bool = True,
                  keep_draft_logits: bool = False, gemm_grid: int = 0, attn_splits: int = 0, hist_len: int = 4096,
-                 device=None):
+                 prefetch_mb: int = 0, device=None):
         self.lib = _lib.load()
         _declare(self.lib)
         if not torch.cuda.is_available():
@@ -152,7 +154,8 @@ class DraftEngine:
             vocab=self.vocab, n_sel=self.n_sel, block_size=self.block_size, max_requests=self.R,
             max_seq=int(max_seq), out_len=int(out_len), hist_len=int(hist_len), rms_eps=float(cfg.rms_norm_eps),
             rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id, attn_splits=attn_splits,
-            post_splits=0, gemm_grid=gemm_grid, use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits))
+            post_splits=0, gemm_grid=gemm_grid, use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits),
+            prefetch_mb=int(os.environ.get("DFLASH_PREFETCH_MB", prefetch_mb)))
         self.max_seq, self.out_len = int(max_seq), int(out_len)
         with torch.cuda.device(self.device):
             nbytes = self.lib.dflash_workspace_bytes(byref(self.ccfg))

@@ -59,6 +59,8 @@ typedef struct dflash_config {
   int gemm_grid;        /* CTAs per streaming GEMM (0 = SM count) */
   int use_pdl;          /* programmatic dependent launch between the step's kernels */
   int keep_draft_logits;/* also store the draft's bf16 logits (parity tests) */
+  int prefetch_mb;      /* MB of its own weights each GEMM prefetches into L2 while it waits for the
+                           kernel in front of it (<= 0 = off, the default: it did not pay on B200) */
 } dflash_config_t;
 
 /* Packed bf16 weights of one draft layer. wqkv = [q_proj; k_proj; v_proj] rows, wgu = [gate; up]. */

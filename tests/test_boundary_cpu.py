@@ -1,0 +1,139 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports what include/dflash_b200.h
+declares, the product class keeps the reference's state-dict / attribute contract, and compute entry points
+fail loudly without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB):
+        g.build()
+    from dflash_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from dflash_b200 import _lib
+    names = _lib.exported_symbols()
+    assert {"dflash_engine_create", "dflash_draft_step", "dflash_verify_step", "dflash_prefill_context",
+            "dflash_sample", "dflash_gemm_skinny", "dflash_gemm_argmax", "dflash_workspace_bytes"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dflash_b200.h but not exported"
+    assert lib.dflash_abi_version() == 1
+
+
+def test_no_torch_types_in_abi():
+    hdr = open(os.path.join(ROOT, "include", "dflash_b200.h")).read()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    assert "at::" not in hdr and "#include <torch" not in hdr
+
+
+def test_python_struct_matches_header():
+    """ctypes mirror of dflash_config_t has the same field order as the header."""
+    from dflash_b200.engine import BUFFERS, CConfig
+    hdr = open(os.path.join(ROOT, "include", "dflash_b200.h")).read()
+    body = re.search(r"typedef struct dflash_config \{(.*?)\} dflash_config_t;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:int|float|long long)\s+(\w+)\s*;", body)
+    assert fields == [f[0] for f in CConfig._fields_]
+    enum = re.search(r"enum dflash_buffer_id \{(.*?)\};", hdr, flags=re.S).group(1)
+    enum = re.sub(r"/\*.*?\*/", "", enum, flags=re.S)
+    ids = [x.strip().split("=")[0].strip() for x in enum.split(",") if x.strip()]
+    assert ids[-1] == "DFLASH_BUF_COUNT" and len(ids) - 1 == len(BUFFERS)
+    for cid, (name, _) in zip(ids, BUFFERS):
+        assert cid == "DFLASH_BUF_" + name.upper(), (cid, name)
+
+
+def test_stream_k_slot_math(lib):
+    """dflash_gemm_max_slots is host code: cross-check the stream-K cut against a direct enumeration."""
+    for N, K, grid in [(4096, 4096, 148), (6144, 4096, 148), (24576, 4096, 148), (4096, 12288, 148),
+                       (4096, 20480, 148), (1000, 512, 37), (256, 128, 148), (4096, 4096, 7)]:
+        nt, kb = (N + 127) // 128, K // 64
+        T = nt * kb
+        G = min(grid, T)
+        owners = [set() for _ in range(nt)]
+        covered = 0
+        for g in range(G):
+            u0, u1 = g * T // G, (g + 1) * T // G
+            covered += u1 - u0
+            for u in range(u0, u1):
+                owners[u // kb].add(g)
+        assert covered == T
+        assert max(len(o) for o in owners) == lib.dflash_gemm_max_slots(N, K, grid)
+        # slots of a tile are consecutive CTAs starting at the owner of its first unit
+        for t, o in enumerate(owners):
+            first = ((t * kb + 1) * G - 1) // T
+            assert sorted(o) == list(range(first, first + len(o)))
+    assert lib.dflash_gemm_max_slots(128, 100, 4) < 0  # K not a multiple of 64 -> error code
+
+
+def test_bad_config_is_rejected(lib):
+    from dflash_b200.engine import CConfig, _declare
+    _declare(lib)
+    cfg = CConfig(hidden=4096, intermediate=12288, n_layers=5, n_q_heads=32, n_kv_heads=8, head_dim=64, vocab=1000,
+                  n_sel=5, block_size=16, max_requests=1, max_seq=4096, out_len=4096, hist_len=16, rms_eps=1e-6,
+                  rope_scale=1.0, mask_token_id=1, gemm_grid=148)
+    assert lib.dflash_workspace_bytes(ctypes.byref(cfg)) == 0
+    assert b"head_dim" in lib.dflash_last_error()
+    cfg.head_dim = 128
+    n = lib.dflash_workspace_bytes(ctypes.byref(cfg))
+    assert n > 5 * 2 * 8 * 4096 * 128 * 2  # at least the static draft KV cache
+    cfg.max_requests = 3
+    assert lib.dflash_workspace_bytes(ctypes.byref(cfg)) == 0
+
+
+def test_product_class_keeps_reference_contract():
+    from dflash_b200 import DFlashDraftModel
+    from transformers.models.qwen3.modeling_qwen3 import Qwen3Config, Qwen3PreTrainedModel
+    from tests.tiny_models import draft_config
+    m = DFlashDraftModel(draft_config(16))
+    assert isinstance(m, Qwen3PreTrainedModel) and DFlashDraftModel.config_class is Qwen3Config
+    assert DFlashDraftModel._no_split_modules == ["Qwen3DFlashDecoderLayer"]
+    assert m.block_size == 16 and m.mask_token_id == 999 and m.target_layer_ids == [1, 3]
+    keys = set(m.state_dict().keys())
+    expect = {"norm.weight", "fc.weight", "hidden_norm.weight"}
+    for i in range(2):
+        p = f"layers.{i}."
+        expect |= {p + f"self_attn.{n}_proj.weight" for n in "qkvo"}
+        expect |= {p + "self_attn.q_norm.weight", p + "self_attn.k_norm.weight"}
+        expect |= {p + f"mlp.{n}_proj.weight" for n in ("gate", "up", "down")}
+        expect |= {p + "input_layernorm.weight", p + "post_attention_layernorm.weight"}
+    assert keys == expect  # rotary inv_freq is a non-persistent buffer
+    assert m.fc.weight.shape == (256, 2 * 256)
+    import inspect
+    sig = inspect.signature(DFlashDraftModel.spec_generate)
+    assert list(sig.parameters)[:6] == ["self", "target", "input_ids", "max_new_tokens", "stop_token_ids", "temperature"]
+    sig = inspect.signature(DFlashDraftModel.forward)
+    assert list(sig.parameters)[:7] == ["self", "position_ids", "attention_mask", "noise_embedding", "target_hidden",
+                                        "past_key_values", "use_cache"]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point raises instead of silently running elsewhere."""
+    from dflash_b200 import DFlashDraftModel, DFlashNativeError, sample
+    from tests.tiny_models import build_pair
+    target, draft = build_pair(DFlashDraftModel, block_size=16, dtype=torch.bfloat16)
+    prompt = torch.randint(0, 900, (1, 8))
+    with pytest.raises(DFlashNativeError):
+        draft.spec_generate(target, prompt, 4, None, 0.0)
+    with pytest.raises(DFlashNativeError):
+        sample(torch.zeros(1, 2, 16, dtype=torch.bfloat16), 0.0)
+
+
+def test_product_never_imports_oracle():
+    """The shipped package must not reach into oracle/ (it is the checker, not the product)."""
+    pkg = os.path.join(ROOT, "dflash_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"

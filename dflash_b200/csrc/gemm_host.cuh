@@ -73,7 +73,7 @@ inline int max_slots_for(int n_tiles, int k_blocks, int grid) {
 
 template <int MB, int MODE>
 inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pdl) {
-  using Cfg = GemmCfg<MB>;
+  using Cfg = GemmCfg<MB, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<MB, MODE>,

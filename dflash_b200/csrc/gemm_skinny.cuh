@@ -74,13 +74,26 @@ __host__ __device__ inline int tile_num_slots(int t, int k_blocks, long long T, 
          tile_first_cta(t, k_blocks, T, G) + 1;
 }
 
-template <int MB>
+// smem budget of the TMA pipeline per mode (measured on B200, profiles/r1_summary.md):
+//  * partials GEMMs (33-200 MB each, 21 per step, chained by PDL): ~110 KB, so that the successor's CTA
+//    can be co-resident and pre-load its first stages while the predecessor drains (755 us/step vs 768 us
+//    with 215 KB);
+//  * lm_head argmax GEMM (1.24 GB in one launch): everything, 11 stages -> 0.967 of the measured copy
+//    bandwidth instead of 0.93.
+#ifndef DFLASH_GEMM_SMEM_KB_PARTIALS
+#define DFLASH_GEMM_SMEM_KB_PARTIALS 110
+#endif
+#ifndef DFLASH_GEMM_SMEM_KB_ARGMAX
+#define DFLASH_GEMM_SMEM_KB_ARGMAX 215
+#endif
+
+template <int MB, int MODE = 0>
 struct GemmCfg {
   static constexpr int kWBytes = kTileN * kTileK * 2;   // 16 KB
   static constexpr int kXBytes = MB * kTileK * 2;
   static constexpr int kStageBytes = kWBytes + kXBytes;
-  // keep a CTA under ~110 KB so the PDL successor's CTA can be co-resident on the SM
-  static constexpr int kStages = MB <= 16 ? 6 : MB <= 32 ? 5 : MB <= 64 ? 4 : MB <= 128 ? 3 : 4;
+  static constexpr int kBudget = (MODE == 1 ? DFLASH_GEMM_SMEM_KB_ARGMAX : DFLASH_GEMM_SMEM_KB_PARTIALS) * 1024;
+  static constexpr int kStages = kBudget / kStageBytes < 3 ? 3 : kBudget / kStageBytes;
   static constexpr int kTmemCols = (2 * MB < 32) ? 32 : 2 * MB;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -89,7 +102,7 @@ template <int MB, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                    const GemmArgs a) {
-  using Cfg = GemmCfg<MB>;
+  using Cfg = GemmCfg<MB, MODE>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &

@@ -155,6 +155,9 @@ class DraftCache:
                 self.values[i] = self.values[i][..., :n, :]
 
 
+ATTN_IMPL = "eager"  # "sdpa" = F.scaled_dot_product_attention, what the reference dispatches to by default
+
+
 def _lin(x, w):
     return F.linear(x, w)
 
@@ -177,6 +180,11 @@ def draft_attention(sd, pfx, cfg: DraftConfig, hidden, target_hidden, cos, sin, 
     q, k = apply_rotary_pos_emb(q, k, cos, sin)
     if cache is not None:
         k, v = cache.update(k, v, layer)
+    if ATTN_IMPL == "sdpa":  # transformers integrations/sdpa_attention.py: the reference's default dispatch
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False,
+                                             scale=D ** -0.5, enable_gqa=True)
+        out = out.transpose(1, 2).reshape(bsz, q_len, -1)
+        return _lin(out, sd[pfx + "self_attn.o_proj.weight"])
     rep = Hq // Hkv
     kk = k.repeat_interleave(rep, dim=1)
     vv = v.repeat_interleave(rep, dim=1)

@@ -278,3 +278,122 @@ def test_spec_generate_dropin_is_lossless(temperature):
     with pytest.raises(RuntimeError):
         draft.spec_generate(target, torch.cat([prompt, prompt]), 8, None, 0.0)
     draft.release_engine()
+
+
+# ------------------------------------------------------------------------------------------------
+# two request streams in one engine (ragged acceptance), block sizes 16 and 32, custom rope table
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bs,R,rope", [(16, 2, "default"), (32, 1, "default"), (8, 2, "scaled")])
+def test_engine_batched_ragged_vs_oracle(bs, R, rope):
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY, draft_state_dict
+    target, draft = _tiny(bs)
+    if rope == "scaled":  # llama3-style: a non-default inv_freq table and attention_scaling reach the kernels as data
+        inv = draft.rotary_emb.inv_freq.clone()
+        inv[32:] = inv[32:] / 8.0
+        draft.rotary_emb.inv_freq.copy_(inv)
+        draft.rotary_emb.attention_scaling = 0.75
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = draft_state_dict(draft)
+    H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
+    g = torch.Generator(device=dev).manual_seed(5)
+    P = [23, 40][:R]
+    n_new = 64
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=max(P) + n_new + 3 * bs,
+                      out_len=max(P) + n_new + 2 * bs, max_requests=R, block_size=bs, keep_draft_logits=True)
+    caches = [O.DraftCache() for _ in range(R)]
+    starts = list(P)
+    pend = []  # pending ctx features per request [c, nsel*H]
+    first = [3 + r for r in range(R)]
+    for r in range(R):
+        hs = [(torch.randn(P[r], H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        prompt = torch.randint(0, V - 1, (P[r],), device=dev, generator=g)
+        eng.reset_request(r, prompt, first[r], n_new)
+        eng.prefill_context(r, hs)
+        pend.append(torch.cat(hs, dim=-1))
+    blocks = [torch.tensor([first[r]] + [cfg.mask_token_id] * (bs - 1), device=dev) for r in range(R)]
+    sched = [[3, 0, bs - 1, 1, 5], [0, bs - 1, 2, 7, 1]]
+    forced = torch.tensor([[min(k, bs - 1) for k in sched[r]] for r in range(R)], dtype=torch.int32, device=dev)
+    for cyc in range(5):
+        eng.draft_step()
+        torch.cuda.synchronize()
+        tl = torch.randn(R * bs, V, device=dev, generator=g).to(torch.bfloat16)
+        hsel = [(torch.randn(R * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        ref_blocks = []
+        for r in range(R):
+            c = pend[r].shape[0]
+            pos = torch.arange(caches[r].get_seq_length(), starts[r] + bs, device=dev).unsqueeze(0)
+            assert caches[r].get_seq_length() + c == starts[r]
+            noise = target.model.embed_tokens(blocks[r].unsqueeze(0))
+            hid = O.draft_forward(sd, cfg, pend[r].unsqueeze(0), noise, pos, caches[r])
+            caches[r].crop(starts[r])
+            got = eng.hn[r * eng.SL: r * eng.SL + bs]
+            assert _rel_err(got, hid[0]) < REL_TOL, (cyc, r, _rel_err(got, hid[0]))
+            dl = eng.buf["draft_logits"].view(R * eng.SL, V)[r * eng.SL + 1: r * eng.SL + bs]
+            assert eng.block_ids[r, 1:].cpu().tolist() == dl.float().cpu().argmax(-1).tolist()
+            ref_blocks.append(eng.block_ids[r].clone())  # continue from the engine's own drafted tokens
+        eng.verify_step(tl, hsel, temperature=0.0, forced_k=forced)
+        torch.cuda.synchronize()
+        for r in range(R):
+            post = tl[r * bs:(r + 1) * bs].float().cpu().argmax(-1)
+            k = int(forced[r, cyc])
+            blk = ref_blocks[r].cpu()
+            post[:k] = blk[1:k + 1]
+            a = O.acceptance_length(blk.tolist(), post.tolist())
+            assert eng.posterior[r].cpu().tolist() == post.tolist()
+            assert int(eng.acc_hist[r, cyc]) == a + 1
+            out = eng.output_ids[r].cpu()
+            assert out[starts[r]:starts[r] + a + 1].tolist() == blk[:a + 1].tolist()
+            assert int(out[starts[r] + a + 1]) == int(post[a])
+            starts[r] += a + 1
+            assert int(eng.buf["start"][r]) == starts[r] and int(eng.buf["ctx_len"][r]) == a + 1
+            pend[r] = torch.cat([h[r * bs: r * bs + a + 1] for h in hsel], dim=-1)
+            feat = eng.buf["ctx_feat"].view(R * eng.SL, -1)[r * eng.SL: r * eng.SL + a + 1]
+            assert torch.equal(feat, pend[r])
+            blocks[r] = torch.tensor([int(post[a])] + [cfg.mask_token_id] * (bs - 1), device=dev)
+            assert eng.block_ids[r].cpu().tolist() == blocks[r].cpu().tolist()
+    eng.close()
+
+
+def test_verify_with_given_posterior_and_stop_and_clamp():
+    """Integer path only: posterior tokens supplied by the caller (e.g. sampled elsewhere at T>0), stop ids,
+    tail clamp. Exhaustive over the acceptance length."""
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200.engine import DraftEngine
+    bs = 16
+    target, draft = _tiny(bs)
+    H, nsel = 256, 2
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=512, out_len=512,
+                      max_requests=1, block_size=bs)
+    hsel = [torch.zeros(bs, H, dtype=torch.bfloat16, device=dev) for _ in range(nsel)]
+    stop = torch.tensor([777], dtype=torch.int64, device=dev)
+    for a in range(bs):
+        for stop_at in (None, a):
+            eng.reset_request(0, torch.arange(10, device=dev), 5, 300)
+            blk = torch.arange(100, 100 + bs, device=dev)
+            if stop_at is not None:
+                blk[stop_at] = 777
+            eng.block_ids[0].copy_(blk)
+            post = torch.cat([blk[1:], torch.tensor([42], device=dev)]).clone()
+            if a < bs - 1:
+                post[a] = 999
+            eng.verify_step(None, hsel, posterior_in=post.view(1, bs).contiguous(), stop_ids=stop)
+            torch.cuda.synchronize()
+            out = [0] * 400
+            ns, tau = O.verify_commit(out, 10, blk.tolist(), post.tolist())
+            assert int(eng.buf["start"][0]) == ns and int(eng.buf["ctx_len"][0]) == tau == a + 1
+            assert eng.output_ids[0, 10:ns + 1].cpu().tolist() == out[10:ns + 1]
+            assert int(eng.buf["done"][0]) == (1 if stop_at is not None else 0)
+    # tail clamp: only 5 tokens left -> effective block 5 -> at most 4 accepted + bonus
+    eng.reset_request(0, torch.arange(10, device=dev), 5, 5)
+    eng.buf["blk_len"][0] = 5
+    blk = torch.arange(100, 100 + bs, device=dev)
+    eng.block_ids[0].copy_(blk)
+    post = torch.cat([blk[1:], torch.tensor([42], device=dev)])
+    eng.verify_step(None, hsel, posterior_in=post.view(1, bs).contiguous(), clamp_tail=True)
+    torch.cuda.synchronize()
+    assert int(eng.buf["ctx_len"][0]) == 5 and int(eng.buf["start"][0]) == 15 and int(eng.buf["done"][0]) == 1
+    eng.close()

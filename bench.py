@@ -477,6 +477,9 @@ def run_cuda_arm(args):
         print(json.dumps(line), flush=True)
     ddist.barrier()
     eng.close()
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.destroy_process_group()
     return 0
 
 

@@ -175,10 +175,15 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
     @torch.inference_mode()
     def spec_generate(self, target: nn.Module, input_ids: torch.LongTensor, max_new_tokens: int,
                       stop_token_ids: Optional[List[int]], temperature: float, *, clamp_tail: bool = False,
-                      forced_k: Optional[List[int]] = None, seed: Optional[int] = None):
+                      forced_k: Optional[List[int]] = None, seed: Optional[int] = None,
+                      graph_target: Optional[bool] = None, sync_every: int = 1):
         """model/dflash.py:192-277, same signature and return value (`LongTensor[1, P + n_out]`).
         Keyword-only extras: `clamp_tail` = benchmark.py:104-105 behaviour, `forced_k` = harness hook that
-        forces the first k draft tokens of each cycle to be accepted, `seed` for T > 0."""
+        forces the first k draft tokens of each cycle to be accepted, `seed` for T > 0,
+        `graph_target` (default: `self.graph_target`, False) runs the target's verify forward from a CUDA graph
+        over a static KV cache (`dflash_b200/target_graph.py`) — the target module itself is
+        untouched, and the whole cycle then needs no host round trip, so the host may poll the device state only
+        every `sync_every` cycles."""
         self.eval()
         if input_ids.shape[0] != 1:
             raise RuntimeError("spec_generate: batch size 1 only (the expanded size of the tensor must match: "
@@ -191,12 +196,24 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         lm_head_w = target.lm_head.weight
         e = self._get_engine(embed_w, lm_head_w, max_seq=max_length + 2 * bs + 1, out_len=max_length + bs + 1)
         position_ids = torch.arange(max_length + bs, device=dev).unsqueeze(0)
-        cache_t = DynamicCache()
         if seed is None:
             seed = int(torch.randint(0, 2**62, (1,)).item()) if temperature >= 1e-5 else 0
-
-        out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
-                     logits_to_keep=1, output_hidden_states=True)
+        if graph_target is None:
+            graph_target = bool(getattr(self, "graph_target", False))
+        gt = None
+        if graph_target:
+            from .target_graph import GraphedVerifyTarget
+            key = (id(target), bs, e.buf["start"].data_ptr())
+            gt = getattr(self, "_graphed_target", None)
+            if gt is None or getattr(self, "_graphed_target_key", None) != key or gt.max_cache_len < max_length + bs:
+                cap = max(1024, 1 << (max_length + bs - 1).bit_length())
+                gt = GraphedVerifyTarget(target, bs, cap, self.target_layer_ids, e.buf["start"], e.block_ids)
+                self._graphed_target, self._graphed_target_key = gt, key
+            out = gt.prefill(input_ids)
+        else:
+            cache_t = DynamicCache()
+            out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
+                         logits_to_keep=1, output_hidden_states=True)
         first = sample(out.logits, temperature, seed=seed ^ 0x5DEECE66D)
         e.reset_request(0, input_ids[0], first.view(-1)[0], max_new_tokens)
         if clamp_tail:
@@ -211,7 +228,25 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
 
         start = P
         state = torch.empty(2, dtype=torch.int32, device="cpu").pin_memory()
-        while start < max_length:
+        cyc = 0
+        while gt is not None and start < max_length:
+            # fully device-driven cycle: draft graph -> target graph -> verify kernels, state stays on the GPU
+            e.draft_step_graphed()
+            logits, hidden = gt.verify_forward()
+            if logits.dtype != torch.bfloat16:
+                logits = logits.to(torch.bfloat16)
+            e.verify_step(logits, hidden, temperature=temperature, seed=seed, stop_ids=stop_t, forced_k=forced_t,
+                          clamp_tail=clamp_tail)
+            cyc += 1
+            if cyc % max(1, sync_every) == 0:  # blind cycles past the end are frozen on the device (`done`)
+                state[0:1].copy_(e.buf["start"][0:1], non_blocking=True)
+                state[1:2].copy_(e.buf["done"][0:1], non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                start = int(state[0])
+                cyc = 0
+                if int(state[1]):
+                    break  # stop token committed, or max_length reached (the device froze the request)
+        while gt is None and start < max_length:
             eff = min(bs, max_length - start) if clamp_tail else bs
             e.draft_step_graphed() if eff > 1 else None
             block = e.block_ids[:, :eff]

@@ -397,3 +397,45 @@ def test_verify_with_given_posterior_and_stop_and_clamp():
     torch.cuda.synchronize()
     assert int(eng.buf["ctx_len"][0]) == 5 and int(eng.buf["start"][0]) == 15 and int(eng.buf["done"][0]) == 1
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# target verify forward from a CUDA graph over a static cache
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sync_every", [1, 4])
+def test_graphed_target_matches_eager_target(sync_every):
+    dev = _cuda()
+    from tests.tiny_models import TINY
+    bs = 16
+    target, draft = _tiny(bs)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 21), generator=torch.Generator().manual_seed(3)).to(dev)
+    forced = [3, 0, 7, 15, 1, 5, 2, 11]
+    # honest greedy: the output depends only on the target's argmax -> equal to the eager-target run except at
+    # near-ties (same module math, but a different attention kernel: static length + mask)
+    ref = draft.spec_generate(target, prompt, 40, None, 0.0)
+    out = draft.spec_generate(target, prompt, 40, None, 0.0, graph_target=True, sync_every=sync_every)
+    assert out.shape == ref.shape
+    if not torch.equal(out, ref):
+        with torch.inference_mode():
+            logits = target(ref).logits[0].float()
+        i = int((out[0] != ref[0]).nonzero()[0])
+        assert _near_tie(logits[i - 1], int(out[0, i]), int(ref[0, i])), (i, out[0, i].item(), ref[0, i].item())
+    # forced acceptance: the cycle structure (tau per cycle) is integer work and must follow the schedule
+    out = draft.spec_generate(target, prompt, 48, None, 0.0, forced_k=forced, graph_target=True, sync_every=sync_every)
+    assert out.shape == (1, 21 + 48)
+    taus = draft.last_acceptance_lengths
+    assert all(t >= forced[i % len(forced)] + 1 for i, t in enumerate(taus[:-1])) and max(taus) == bs
+    # honest greedy run must be lossless w.r.t. one teacher-forced pass of the target
+    out = draft.spec_generate(target, prompt, 40, None, 0.0, graph_target=True, sync_every=sync_every)
+    with torch.inference_mode():
+        logits = target(out).logits[0].float()
+    pred = logits.argmax(-1)
+    for i in range(20, out.shape[1] - 1):
+        if pred[i].item() != out[0, i + 1].item():
+            assert _near_tie(logits[i], pred[i].item(), out[0, i + 1].item()), i
+    # stop token
+    stop = [int(out[0, 21 + 6])]
+    out2 = draft.spec_generate(target, prompt, 40, stop, 0.0, graph_target=True, sync_every=sync_every)
+    gen = out2[0, 21:].tolist()
+    assert gen[-1] == stop[0] and stop[0] not in gen[:-1]
+    draft.release_engine()

@@ -38,12 +38,12 @@ def forced_schedule(seed=0, n=TAU_SCHEDULE_LEN, bs=16):
     ks = []
     for _ in range(n):
         # geometric-like mixture clipped to [0, bs-1]
-        k = min(bs - 1, int(rng.expovariate(1.0 / 6.9)))
+        k = min(bs - 1, int(rng.expovariate(1.0 / 6.2)))  # seed 0, n 64 -> mean tau 7.28
         ks.append(k)
     return ks
 
 
-def algorithmic_bytes(dims, S, c):
+def algorithmic_bytes(dims, S, c, R=1):
     """SURVEY §8(d) per-step bytes (bf16): draft weights + lm_head + KV read + ctx features + embeddings + new KV."""
     H, I, L, V = dims["hidden"], dims["intermediate"], dims["draft_layers"], dims["vocab"]
     Hq, Hkv, D = dims["heads"], dims["kv_heads"], dims["head_dim"]
@@ -52,10 +52,10 @@ def algorithmic_bytes(dims, S, c):
     params = L * per_layer + nsel * H * H + 2 * H
     weights = 2 * params
     lm = 2 * V * H
-    kv = L * 2 * Hkv * D * 2 * (S + c + dims["block_size"])
-    ctx = nsel * H * 2 * c
-    emb = dims["block_size"] * H * 2
-    kv_new = L * 2 * Hkv * D * 2 * c
+    kv = R * L * 2 * Hkv * D * 2 * (S + c + dims["block_size"])
+    ctx = R * nsel * H * 2 * c
+    emb = R * dims["block_size"] * H * 2
+    kv_new = R * L * 2 * Hkv * D * 2 * c
     return dict(total=weights + lm + kv + ctx + emb + kv_new, draft_weights=weights, lm_head=lm, kv=kv)
 
 
@@ -202,7 +202,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
-def build_engine(dims, device, seed):
+def build_engine(dims, device, seed, R=1):
     import torch
     from transformers import Qwen3Config
     from dflash_b200 import DFlashDraftModel
@@ -228,9 +228,57 @@ def build_engine(dims, device, seed):
     embed = torch.empty(dims["vocab"], dims["hidden"], dtype=torch.bfloat16, device=device).normal_(0, 0.02, generator=g)
     lm_head = torch.empty(dims["vocab"], dims["hidden"], dtype=torch.bfloat16, device=device).normal_(0, 0.02, generator=g)
     eng = DraftEngine(draft, embed, lm_head, max_seq=PROMPT_LEN + MAX_NEW + 64, out_len=PROMPT_LEN + MAX_NEW + 64,
-                      max_requests=1, block_size=dims["block_size"],
+                      max_requests=R, block_size=dims["block_size"],
                       use_pdl=os.environ.get("DFLASH_PDL", "1") != "0", device=device)
     return draft, eng, embed, lm_head
+
+
+def full_cycle_bench(dims, draft, eng, embed, lm_head, device, ks, new_tokens=512):
+    """Whole spec-decode cycles through the public API (`draft.spec_generate`) with a random-init HF target of
+    Qwen3-8B shape: (a) the target called eagerly with a DynamicCache exactly as the reference does, (b) the same
+    module replayed from a CUDA graph over a static cache. Forced-tau schedule as above.
+    Context for the headline numbers, not part of them."""
+    import torch
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    cfg = Qwen3Config(vocab_size=dims["vocab"], hidden_size=dims["hidden"], intermediate_size=dims["intermediate"],
+                      num_hidden_layers=dims["target_layers"], num_attention_heads=dims["heads"],
+                      num_key_value_heads=dims["kv_heads"], head_dim=dims["head_dim"], max_position_embeddings=40960,
+                      rms_norm_eps=dims["eps"], tie_word_embeddings=False,
+                      rope_parameters={"rope_type": "default", "rope_theta": dims["rope_theta"]})
+    cfg._attn_implementation = "sdpa"
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(device):
+            target = Qwen3ForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    target = target.eval()
+    # share the benchmark's embedding / head tensors so the draft engine streams the same weights
+    target.model.embed_tokens.weight.data = embed
+    target.lm_head.weight.data = lm_head
+    g = torch.Generator(device=device).manual_seed(7)
+    prompt = torch.randint(0, dims["vocab"] - 1, (1, PROMPT_LEN), device=device, generator=g)
+    out = {}
+    # (attn_implementation="eager" cannot be captured: transformers builds a CPU tensor in its mask path)
+    rows = (("eager_target", False), ("graphed_target", True))
+    for name, graph in rows:
+        draft.spec_generate(target, prompt, 64, None, 0.0, forced_k=ks, graph_target=graph)  # warm-up / capture
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ids = draft.spec_generate(target, prompt, new_tokens, None, 0.0, forced_k=ks, graph_target=graph)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        taus = draft.last_acceptance_lengths
+        n = ids.shape[1] - prompt.shape[1]
+        out[name] = dict(tokens_per_s=n / dt, new_tokens=n, cycles=len(taus), mean_tau=sum(taus) / max(1, len(taus)),
+                         ms_per_cycle=dt / max(1, len(taus)) * 1e3, wall_s=dt)
+    out["note"] = ("prefill + decode wall clock of spec_generate, batch 1, random-init Qwen3-8B target (bf16, sdpa), "
+                   "forced-tau schedule; target forward is the caller's HF module in both rows")
+    draft.release_engine()
+    del target
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_cuda_arm(args):
@@ -244,16 +292,17 @@ def run_cuda_arm(args):
     dims = Q8
     bs, H, V, L = dims["block_size"], dims["hidden"], dims["vocab"], dims["draft_layers"]
     nsel = L
-    draft, eng, embed, lm_head = build_engine(dims, device, seed=rank)
+    R = args.requests
+    draft, eng, embed, lm_head = build_engine(dims, device, seed=rank, R=R)
     g = torch.Generator(device=device).manual_seed(100 + rank)
     # synthetic target outputs for the block (resident in HBM for `value`; pinned host copies for `e2e`)
-    tlogits = torch.randn(bs, V, device=device, generator=g).to(torch.bfloat16)
-    hsel = [(torch.randn(bs, H, device=device, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+    tlogits = torch.randn(R * bs, V, device=device, generator=g).to(torch.bfloat16)
+    hsel = [(torch.randn(R * bs, H, device=device, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
     prompt_hidden = [(torch.randn(PROMPT_LEN, H, device=device, generator=g) * 0.5).to(torch.bfloat16)
                      for _ in range(nsel)]
     prompt = torch.randint(0, V - 1, (PROMPT_LEN,), device=device, generator=g)
     ks = forced_schedule(seed=0)
-    forced = torch.tensor([ks], dtype=torch.int32, device=device)
+    forced = torch.tensor([ks] * R, dtype=torch.int32, device=device)  # every stream follows the same schedule
     mean_tau = sum(k + 1 for k in ks) / len(ks)
     steps_per_gen, cum = 0, 0  # cycles one 2048-token generation lasts under the schedule
     while cum + ks[steps_per_gen % len(ks)] + 1 <= MAX_NEW - bs:
@@ -261,8 +310,9 @@ def run_cuda_arm(args):
         steps_per_gen += 1
 
     def reset():
-        eng.reset_request(0, prompt, 1, MAX_NEW)
-        eng.prefill_context(0, prompt_hidden)
+        for r in range(R):
+            eng.reset_request(r, prompt, 1, MAX_NEW)
+            eng.prefill_context(r, prompt_hidden)
 
     def enqueue_step():
         eng.draft_step()
@@ -300,7 +350,7 @@ def run_cuda_arm(args):
             graph.replay()
             if events is not None:
                 events[i][1].record()
-            ctr["tokens"] += ks[ctr["since_reset"] % len(ks)] + 1
+            ctr["tokens"] += R * (ks[ctr["since_reset"] % len(ks)] + 1)
             ctr["since_reset"] += 1
 
     do_reset()
@@ -379,7 +429,7 @@ def run_cuda_arm(args):
     t0 = time.perf_counter()
     e2e_tokens = 0
     for _ in range(e2e_steps):
-        e2e_tokens += e2e_step()
+        e2e_tokens += R * e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_s_max = ddist.max_over_ranks(e2e_s, device)
@@ -425,7 +475,7 @@ def run_cuda_arm(args):
 
     # whole-step roofline at the mean cache length of the timed region
     S_mid = PROMPT_LEN + int(mean_tau * min(args.steps, steps_per_gen) / 2)
-    ab = algorithmic_bytes(dims, S_mid, round(mean_tau))
+    ab = algorithmic_bytes(dims, S_mid, round(mean_tau), R)
     step_gbs = ab["total"] / (med * 1e-6) / 1e9
 
     # ---- DP result gather over NCCL (outside the timed region; latency reported)
@@ -441,6 +491,13 @@ def run_cuda_arm(args):
     assert g_n.shape[0] == world and g_t.shape == (world, MAX_NEW)
     del n_cyc
 
+    full_cycle = None
+    if rank == 0 and world == 1 and R == 1 and not args.no_full_cycle:
+        try:
+            full_cycle = full_cycle_bench(dims, draft, eng, embed, lm_head, device, ks)
+        except Exception as ex:  # the headline numbers above do not depend on this section
+            full_cycle = dict(error=f"{type(ex).__name__}: {ex}")
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -454,7 +511,7 @@ def run_cuda_arm(args):
             warmup=args.warmup, ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak",
             vs_baseline=None, dtype="bf16", data="synthetic",
             config=dict(workload="Qwen3-8B + DFlash-b16 draft+verify step (target forward excluded, SURVEY 8d), "
-                                 "batch 1 per GPU, bs 16, prompt 128, up to 2048 new tokens, forced-tau schedule "
+                                 f"batch {R} per GPU, bs 16, prompt 128, up to 2048 new tokens, forced-tau schedule "
                                  f"mean {mean_tau:.2f} (BASELINE.json configs[1])",
                         l2="inputs larger than L2: 3.34 GB of weights streamed per step vs 126 MB L2",
                         parallelism=f"dp{world} (independent request stream per GPU, no data-path collective)",
@@ -473,6 +530,7 @@ def run_cuda_arm(args):
             launches_per_step=launches_per_step,
             clocks=clock_info,
             gather_us=gather_us,
+            full_cycle=full_cycle,
         )
         print(json.dumps(line), flush=True)
     ddist.barrier()
@@ -489,7 +547,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--requests", type=int, default=1, choices=[1, 2, 4, 8],
+                    help="request streams per GPU sharing one weight stream (headline metric is quoted at 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-cycle", action="store_true",
+                    help="skip the whole-cycle section (spec_generate with a random-init Qwen3-8B target)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -122,8 +122,8 @@ inline int check_config(const dflash_config_t& c) {
     set_error("max_requests %d unsupported: 2*R*%d activation rows must fit one 256-wide UMMA", c.max_requests, SL);
     return DFLASH_ERR_ARG;
   }
-  if ((c.max_requests & (c.max_requests - 1)) != 0 || c.max_requests * SL > 32) {
-    set_error("max_requests %d: fused lm_head argmax currently covers <= 32 block rows", c.max_requests);
+  if ((c.max_requests & (c.max_requests - 1)) != 0) {
+    set_error("max_requests %d must be a power of two (activation buffers are exact UMMA widths)", c.max_requests);
     return DFLASH_ERR_ARG;
   }
   if (c.n_sel < 1 || c.n_sel > 8) { set_error("n_sel must be in [1,8]"); return DFLASH_ERR_ARG; }

@@ -100,6 +100,8 @@ inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl)
     switch (p.mb) {
       case 16: return launch_gemm_t<16, kModeArgmax>(p, stream, pdl);
       case 32: return launch_gemm_t<32, kModeArgmax>(p, stream, pdl);
+      case 64: return launch_gemm_t<64, kModeArgmax>(p, stream, pdl);
+      case 128: return launch_gemm_t<128, kModeArgmax>(p, stream, pdl);
       default: return cudaErrorInvalidValue;
     }
   }
@@ -132,7 +134,7 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
     set_error("gemm: mb=%d unsupported", mb);
     return -1;
   }
-  if (mode == kModeArgmax && mb > 32) { set_error("gemm: argmax mode needs mb<=32"); return -1; }
+  if (mode == kModeArgmax && mb > 128) { set_error("gemm: argmax mode needs mb<=128"); return -1; }
   if (x_row0 + mb > x_rows_total) { set_error("gemm: activation buffer too small"); return -1; }
   int rc = make_tmap_bf16(&p->tmW, W, w_rows_total, K, K, kTileN);
   if (rc) return rc;

@@ -250,11 +250,20 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int row_in_tile = warp * 32 + lane;
 
     // kModeArgmax running best per activation row (this thread's weight rows only ever increase)
-    float best_v[MODE == kModeArgmax ? MB : 1];
-    int best_i[MODE == kModeArgmax ? MB : 1];
-    if (MODE == kModeArgmax) {
+    // (MB <= 32: registers; wider batches keep a per-warp running best in shared memory instead)
+    constexpr bool kRegBest = (MODE == kModeArgmax) && (MB <= 32);
+    constexpr bool kSmemBest = (MODE == kModeArgmax) && (MB > 32);
+    float best_v[kRegBest ? MB : 1];
+    int best_i[kRegBest ? MB : 1];
+    __shared__ float s_bv[kSmemBest ? 4 * MB : 1];
+    __shared__ int s_bi[kSmemBest ? 4 * MB : 1];
+    if (kRegBest) {
 #pragma unroll
       for (int j = 0; j < MB; ++j) { best_v[j] = -INFINITY; best_i[j] = 0x7fffffff; }
+    }
+    if (kSmemBest) {
+      for (int j = lane; j < MB; j += 32) { s_bv[warp * MB + j] = -INFINITY; s_bi[warp * MB + j] = 0x7fffffff; }
+      __syncwarp();
     }
 
     long long u = u0;
@@ -288,15 +297,35 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
               if (m < a.m_valid) dst[static_cast<long long>(m) * a.ws_ld] = v[j];
             }
           }
-        } else {
+        } else if (kRegBest) {
           if (n < a.N) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int m = c * 16 + j;
               const float r = bf16_round(v[j]);
-              if (r > best_v[m]) { best_v[m] = r; best_i[m] = n; }
+              if (r > best_v[kRegBest ? m : 0]) { best_v[kRegBest ? m : 0] = r; best_i[kRegBest ? m : 0] = n; }
               if (a.logits != nullptr && m < a.m_valid)
                 a.logits[static_cast<long long>(m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        } else {
+          // wide batch: reduce each activation row over the warp's 32 weight rows now, merge into smem
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = c * 16 + j;
+            float bv = (n < a.N) ? bf16_round(v[j]) : -INFINITY;
+            int bi = n;
+            if (a.logits != nullptr && n < a.N && m < a.m_valid)
+              a.logits[static_cast<long long>(m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+              const int k = kSmemBest ? warp * MB + m : 0;
+              if (bv > s_bv[k] || (bv == s_bv[k] && bi < s_bi[k])) { s_bv[k] = bv; s_bi[k] = bi; }
             }
           }
         }
@@ -308,19 +337,21 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
     if (MODE == kModeArgmax) {
       // reduce over the 128 epilogue threads: max value, ties -> lowest index
-      float* red_v = reinterpret_cast<float*>(sW);  // pipeline smem is idle by now (all MMAs retired)
-      int* red_i = reinterpret_cast<int*>(sW + 4 * MB * sizeof(float));
+      float* red_v = kSmemBest ? s_bv : reinterpret_cast<float*>(sW);  // pipeline smem is idle by now
+      int* red_i = kSmemBest ? s_bi : reinterpret_cast<int*>(sW + 4 * MB * sizeof(float));
+      if (kRegBest) {
 #pragma unroll
-      for (int j = 0; j < MB; ++j) {
-        float bv = best_v[j];
-        int bi = best_i[j];
+        for (int j = 0; j < (kRegBest ? MB : 1); ++j) {
+          float bv = best_v[j];
+          int bi = best_i[j];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          if (lane == 0) { red_v[warp * MB + j] = bv; red_i[warp * MB + j] = bi; }
         }
-        if (lane == 0) { red_v[warp * MB + j] = bv; red_i[warp * MB + j] = bi; }
       }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
       if (threadIdx.x < MB) {

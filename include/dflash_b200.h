@@ -47,7 +47,7 @@ typedef struct dflash_config {
   int vocab;            /* rows of the target's lm_head / embed_tokens */
   int n_sel;            /* len(target_layer_ids) */
   int block_size;       /* slots per block (2..32); slot 0 is the last committed token */
-  int max_requests;     /* request streams resident in this engine (1 or 2 in ABI v1) */
+  int max_requests;     /* request streams resident in this engine: 1, 2, 4 or 8 (2*R*SL <= 256 rows) */
   int max_seq;          /* positions per request in the static draft KV cache */
   int out_len;          /* row length of output_ids (>= prompt + max_new_tokens + block_size) */
   int hist_len;         /* acceptance-length history entries per request */

@@ -283,7 +283,8 @@ def test_spec_generate_dropin_is_lossless(temperature):
 # ------------------------------------------------------------------------------------------------
 # two request streams in one engine (ragged acceptance), block sizes 16 and 32, custom rope table
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("bs,R,rope", [(16, 2, "default"), (32, 1, "default"), (8, 2, "scaled")])
+@pytest.mark.parametrize("bs,R,rope", [(16, 2, "default"), (32, 1, "default"), (8, 2, "scaled"), (16, 4, "default"),
+                                        (16, 8, "default"), (32, 4, "default")])
 def test_engine_batched_ragged_vs_oracle(bs, R, rope):
     dev = _cuda()
     from oracle import dflash_oracle as O
@@ -299,7 +300,7 @@ def test_engine_batched_ragged_vs_oracle(bs, R, rope):
     sd = draft_state_dict(draft)
     H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
     g = torch.Generator(device=dev).manual_seed(5)
-    P = [23, 40][:R]
+    P = [23, 40, 17, 31, 52, 9, 44, 28][:R]
     n_new = 64
     eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=max(P) + n_new + 3 * bs,
                       out_len=max(P) + n_new + 2 * bs, max_requests=R, block_size=bs, keep_draft_logits=True)
@@ -314,7 +315,8 @@ def test_engine_batched_ragged_vs_oracle(bs, R, rope):
         eng.prefill_context(r, hs)
         pend.append(torch.cat(hs, dim=-1))
     blocks = [torch.tensor([first[r]] + [cfg.mask_token_id] * (bs - 1), device=dev) for r in range(R)]
-    sched = [[3, 0, bs - 1, 1, 5], [0, bs - 1, 2, 7, 1]]
+    base = [[3, 0, bs - 1, 1, 5], [0, bs - 1, 2, 7, 1]]
+    sched = [[(k + 3 * (r // 2)) % bs for k in base[r % 2]] for r in range(R)]
     forced = torch.tensor([[min(k, bs - 1) for k in sched[r]] for r in range(R)], dtype=torch.int32, device=dev)
     for cyc in range(5):
         eng.draft_step()

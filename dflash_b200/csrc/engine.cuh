@@ -2,6 +2,7 @@
 // The engine object is host memory only; every device byte belongs to the caller's workspace.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -132,6 +133,14 @@ inline int check_config(const dflash_config_t& c) {
     return DFLASH_ERR_ARG;
   }
   return DFLASH_OK;
+}
+
+// Timing ablation only (results become wrong): DFLASH_DEBUG_SKIP bitmask drops kernels from the schedule.
+// 1 finalize_rows, 2 swiglu, 4 attn_combine, 8 qkv_post, 16 attn_split, 32 partial GEMMs, 64 lm_head GEMM
+inline int dbg_skip() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DFLASH_DEBUG_SKIP"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 #define DFL_CUDA(expr, what)                              \
@@ -268,14 +277,14 @@ inline RowsArgs rows_args_base(const Engine* e) {
 
 // fc GEMM + hidden_norm over the pending context rows -> a_in rows [0, RS)   (dflash.py:177)
 inline int enqueue_ctx_inject(Engine* e, cudaStream_t st) {
-  DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
+  if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
   RowsArgs a = rows_args_base(e);
   a.ws = e->fc.args.ws;
   a.sm = slot_map_of(e->fc);
   a.valid_mode = kRowsCtx;
   a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
   a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "fc finalize");
+  if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "fc finalize");
   return DFLASH_OK;
 }
 
@@ -310,10 +319,10 @@ inline int enqueue_ctx_only(Engine* e, cudaStream_t st) {
   int rc = enqueue_ctx_inject(e, st);
   if (rc) return rc;
   for (int l = 0; l < e->L; ++l) {
-    DFL_CUDA(launch_gemm(e->kv[l], st, e->pdl), "kv gemm");
+    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->kv[l], st, e->pdl), "kv gemm");
     QkvPostArgs qa = qkv_post_args(e, l, e->kv[l], true);
     const int items = qa.rows * (2 * e->Hkv);
-    DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "kv post");
+    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "kv post");
   }
   return DFLASH_OK;
 }
@@ -338,7 +347,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     a.resid = x;
     a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
     a.out = a_in + static_cast<size_t>(RS) * e->H;
-    DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "embed+ln1");
+    if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "embed+ln1");
   }
   int rc = enqueue_ctx_inject(e, st);
   if (rc) return rc;
@@ -355,18 +364,18 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   aa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_ATTN_OUT);
   const int group = e->Hq / e->Hkv;
   for (int l = 0; l < e->L; ++l) {
-    DFL_CUDA(launch_gemm(e->qkv[l], st, e->pdl), "qkv gemm");
+    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->qkv[l], st, e->pdl), "qkv gemm");
     QkvPostArgs qa = qkv_post_args(e, l, e->qkv[l], false);
     const int items = qa.rows * (e->Hq + 2 * e->Hkv);
-    DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
+    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
     aa.k_cache = qa.k_cache;
     aa.v_cache = qa.v_cache;
-    DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
+    if (!(dbg_skip() & 16)) DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
                         kAttnSmem, st, e->pdl, aa),
              "attention");
-    DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + 7) / 8), dim3(256), 0, st, e->pdl, aa),
+    if (!(dbg_skip() & 4)) DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + 7) / 8), dim3(256), 0, st, e->pdl, aa),
              "attention combine");
-    DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
+    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
     {
       RowsArgs a = rows_args_base(e);
       a.ws = e->o[l].args.ws;
@@ -374,9 +383,9 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
       a.resid = x;
       a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
       a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
-      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "o finalize");
+      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "o finalize");
     }
-    DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
+    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
     {
       SwigluArgs sa;
       sa.ws = e->gu[l].args.ws;
@@ -384,9 +393,9 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
       sa.rows = RS;
       sa.I = e->I;
       sa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
-      DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I / 4 + 255) / 256, RS), dim3(256), 0, st, e->pdl, sa), "swiglu");
+      if (!(dbg_skip() & 2)) DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I / 4 + 255) / 256, RS), dim3(256), 0, st, e->pdl, sa), "swiglu");
     }
-    DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
+    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
     {
       RowsArgs a = rows_args_base(e);
       a.ws = e->d[l].args.ws;
@@ -399,11 +408,11 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
         a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
         a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
       }
-      DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "down finalize");
+      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "down finalize");
     }
   }
   if (!run_lm_head) return DFLASH_OK;
-  DFL_CUDA(launch_gemm(e->lm, st, e->pdl), "lm_head gemm");
+  if (!(dbg_skip() & 64)) DFL_CUDA(launch_gemm(e->lm, st, e->pdl), "lm_head gemm");
   DraftTokArgs ta;
   ta.cand_val = e->lm.args.cand_val;
   ta.cand_idx = e->lm.args.cand_idx;

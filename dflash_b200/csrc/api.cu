@@ -86,6 +86,10 @@ int dflash_engine_create(const dflash_config_t* cfg, const dflash_weights_t* wei
   Engine* impl = nullptr;
   rc = engine_create(*cfg, *weights, workspace, workspace_bytes, sms, &impl);
   if (rc) return rc;
+  if (impl->want_mega && mega_supported(impl)) {
+    rc = build_mega(impl);
+    if (rc) { delete impl; return rc; }
+  }
   *out = new dflash_engine{impl};
   return DFLASH_OK;
 }

@@ -2,11 +2,15 @@
 // [committed context K/V | this block's K/V] = cache positions [0, start + bs)
 // (model/dflash.py:77-99: is_causal=False, attention_mask=None, GQA, scale D^-1/2).
 //
-// Split-KV ("flash-decoding") so that short query blocks still fill the machine: CTA = (kv split,
-// kv head, request x 16-query tile); the `group` q-heads that share the kv head are the CTA's warps,
+// Split-KV ("flash-decoding") so that short query blocks still fill the machine: work item = (kv split,
+// kv head, request x 16-query tile); the `group` q-heads that share the kv head are the item's warps,
 // so each K/V byte is fetched from HBM once. Scores and PV run on mma.sync m16n8k16 (bf16 in, fp32
 // accumulate): with 16 queries per head this is <1% of the step's bytes and FLOPs, far below what
-// would amortise a TMEM round trip. A second tiny kernel merges the splits.
+// would amortise a TMEM round trip. A second tiny pass merges the splits.
+//
+// The bodies are __device__ functions over (work item, thread-in-group) so that both the stand-alone
+// kernels and the persistent step kernel (step_mega.cuh) run the same code. Data produced earlier in
+// the same step by other CTAs is read with ld.global.cg (L2), never through L1.
 #pragma once
 #include "ptx.cuh"
 
@@ -14,7 +18,8 @@ namespace dfl {
 
 constexpr int kAttnKeys = 64;  // keys per smem tile
 constexpr int kAttnD = 128;
-constexpr int kAttnSmem = 2 * 2 * kAttnKeys * kAttnD * 2;  // 2 stages x (K,V) x 16 KB
+constexpr int kAttnTileBytes = kAttnKeys * kAttnD * 2;  // 16 KB (K or V)
+constexpr int kAttnSmem = 2 * 2 * kAttnTileBytes;       // stand-alone kernel: 2 stages x (K, V)
 
 struct AttnArgs {
   int R, SL, bs, Hq, Hkv, S_max;
@@ -68,14 +73,12 @@ __host__ __device__ inline int attn_chunk(int L, int nsplit) {
   return c < kAttnKeys ? kAttnKeys : c;
 }
 
-__global__ void attn_split_kernel(const AttnArgs a) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(128) uint8_t attn_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_req = a.SL / 16;
-  const int r = blockIdx.z / tiles_per_req, qt = blockIdx.z % tiles_per_req;
-  const int h = blockIdx.y, split = blockIdx.x;
+// One (split, kv head h, request r, query tile qt) work item, executed by `group` warps
+// (tid in [0, 32*group)). NSTG = K/V smem stages (1 or 2) at smem0; bar_id = named barrier of the group.
+template <int NSTG>
+__device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt, int h, int split, int tid,
+                                                int nthreads, uint32_t smem0, int bar_id) {
+  const int warp = tid >> 5, lane = tid & 31;
   const int group = a.Hq / a.Hkv;
   const int hq = h * group + warp;
   const int RS = a.R * a.SL;
@@ -97,32 +100,30 @@ __global__ void attn_split_kernel(const AttnArgs a) {
     return;
   }
 
-  // Q fragments (A operand, 8 k-steps of 16 over D=128), straight from global
+  // Q fragments (A operand, 8 k-steps of 16 over D=128), straight from global (L2)
   uint32_t qf[8][4];
   {
-    const __nv_bfloat16* q0 = a.q + (static_cast<long long>(row_lo) * a.Hq + hq) * kAttnD;
-    const __nv_bfloat16* q1 = a.q + (static_cast<long long>(row_lo + 8) * a.Hq + hq) * kAttnD;
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(a.q + (static_cast<long long>(row_lo) * a.Hq + hq) * kAttnD);
+    const uint32_t* q1 =
+        reinterpret_cast<const uint32_t*>(a.q + (static_cast<long long>(row_lo + 8) * a.Hq + hq) * kAttnD);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      const int c = ks * 16 + tq * 2;
-      qf[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + c);
-      qf[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + c);
-      qf[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + c + 8);
-      qf[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + c + 8);
+      const int c = (ks * 16 + tq * 2) >> 1;  // in 32-bit words
+      qf[ks][0] = __ldcg(q0 + c);
+      qf[ks][1] = __ldcg(q1 + c);
+      qf[ks][2] = __ldcg(q0 + c + 4);
+      qf[ks][3] = __ldcg(q1 + c + 4);
     }
   }
 
   const __nv_bfloat16* kbase = a.k_cache + (static_cast<long long>(r) * a.Hkv + h) * a.S_max * kAttnD;
   const __nv_bfloat16* vbase = a.v_cache + (static_cast<long long>(r) * a.Hkv + h) * a.S_max * kAttnD;
-  const uint32_t smem0 = smem_u32(attn_smem);
-  constexpr int kTileBytes = kAttnKeys * kAttnD * 2;  // 16 KB
-  const int nthreads = blockDim.x;
 
   auto load_tile = [&](int t, int stage) {
     const int key0 = k0 + t * kAttnKeys;
-    const uint32_t sk = smem0 + stage * 2 * kTileBytes;
-    const uint32_t sv = sk + kTileBytes;
-    for (int idx = threadIdx.x; idx < kAttnKeys * 16; idx += nthreads) {
+    const uint32_t sk = smem0 + stage * 2 * kAttnTileBytes;
+    const uint32_t sv = sk + kAttnTileBytes;
+    for (int idx = tid; idx < kAttnKeys * 16; idx += nthreads) {
       const int key = idx >> 4, ch = idx & 15;
       const bool valid = key0 + key < k1;
       const long long goff = static_cast<long long>(valid ? key0 + key : 0) * kAttnD + ch * 8;
@@ -138,20 +139,29 @@ __global__ void attn_split_kernel(const AttnArgs a) {
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
   const int ntiles = (k1 - k0 + kAttnKeys - 1) / kAttnKeys;
-  load_tile(0, 0);
-  cp_async_commit();
+  if (NSTG == 2) {
+    load_tile(0, 0);
+    cp_async_commit();
+  }
   for (int t = 0; t < ntiles; ++t) {
-    const int stage = t & 1;
-    if (t + 1 < ntiles) {
-      load_tile(t + 1, stage ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
+    int stage = 0;
+    if (NSTG == 2) {
+      stage = t & 1;
+      if (t + 1 < ntiles) {
+        load_tile(t + 1, stage ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
     } else {
+      load_tile(t, 0);
+      cp_async_commit();
       cp_async_wait<0>();
     }
-    __syncthreads();
-    const uint32_t sk = smem0 + stage * 2 * kTileBytes;
-    const uint32_t sv = sk + kTileBytes;
+    group_sync(bar_id, nthreads);
+    const uint32_t sk = smem0 + stage * 2 * kAttnTileBytes;
+    const uint32_t sv = sk + kAttnTileBytes;
 
     // S = Q K^T : 8 n-tiles of 8 keys
     float s[8][4];
@@ -223,7 +233,7 @@ __global__ void attn_split_kernel(const AttnArgs a) {
         mma_16816(o[dp * 2 + 1], pf[kk], b2, b3);
       }
     }
-    __syncthreads();
+    group_sync(bar_id, nthreads);
   }
 
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
@@ -243,32 +253,54 @@ __global__ void attn_split_kernel(const AttnArgs a) {
   }
 }
 
-// Merge the splits: one warp per (row, q head).
-__global__ void __launch_bounds__(256) attn_combine_kernel(const AttnArgs a) {
-  pdl_wait();
+__global__ void attn_split_kernel(const AttnArgs a) {
   pdl_trigger();
-  const int lane = threadIdx.x & 31;
+  pdl_wait();
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  const int tiles_per_req = a.SL / 16;
+  attn_split_body<2>(a, blockIdx.z / tiles_per_req, blockIdx.z % tiles_per_req, blockIdx.y, blockIdx.x, threadIdx.x,
+                     blockDim.x, smem_u32(attn_smem), 0);
+}
+
+// Merge the splits of one (row, q head) item: one warp.
+__device__ __forceinline__ void attn_combine_item(const AttnArgs& a, int item, int lane) {
   const int RS = a.R * a.SL;
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (item >= RS * a.Hq) return;
+  // all (max, sum) pairs first (one L2 round trip), then the partial outputs of the live splits
+  float2 ml[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s)
+    if (s < a.nsplit) ml[s] = __ldcg(reinterpret_cast<const float2*>(a.part_ml + (static_cast<long long>(s) * RS * a.Hq + item) * 2));
   float M = -INFINITY;
-  for (int s = 0; s < a.nsplit; ++s)
-    M = fmaxf(M, a.part_ml[(static_cast<long long>(s) * RS * a.Hq + item) * 2]);
+#pragma unroll
+  for (int s = 0; s < 16; ++s)
+    if (s < a.nsplit) M = fmaxf(M, ml[s].x);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float den = 0.f;
-  for (int s = 0; s < a.nsplit; ++s) {
-    const long long p = static_cast<long long>(s) * RS * a.Hq + item;
-    const float m = a.part_ml[p * 2];
-    if (m == -INFINITY) continue;
-    const float w = exp2f(m - M);
-    den += w * a.part_ml[p * 2 + 1];
-    const float4 ov = *reinterpret_cast<const float4*>(a.part_o + p * kAttnD + lane * 4);
-    acc[0] += w * ov.x; acc[1] += w * ov.y; acc[2] += w * ov.z; acc[3] += w * ov.w;
+  float4 ov[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s)
+    if (s < a.nsplit && ml[s].x != -INFINITY)
+      ov[s] = __ldcg(reinterpret_cast<const float4*>(a.part_o + (static_cast<long long>(s) * RS * a.Hq + item) * kAttnD + lane * 4));
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    if (s < a.nsplit && ml[s].x != -INFINITY) {
+      const float w = exp2f(ml[s].x - M);
+      den += w * ml[s].y;
+      acc[0] += w * ov[s].x; acc[1] += w * ov[s].y; acc[2] += w * ov[s].z; acc[3] += w * ov[s].w;
+    }
   }
   const float inv = 1.0f / den;
   __nv_bfloat16* dst = a.out + static_cast<long long>(item) * kAttnD + lane * 4;  // item = row*Hq + head
   *reinterpret_cast<uint2*>(dst) =
       make_uint2(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv));
+}
+
+__global__ void __launch_bounds__(256) attn_combine_kernel(const AttnArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= a.R * a.SL * a.Hq) return;
+  attn_combine_item(a, item, threadIdx.x & 31);
 }
 
 }  // namespace dfl

@@ -9,6 +9,7 @@
 #include "../../include/dflash_b200.h"
 #include "attention.cuh"
 #include "fused_ops.cuh"
+#include "step_mega.cuh"
 #include "verify.cuh"
 
 namespace dfl {
@@ -34,6 +35,10 @@ struct Engine {
   std::vector<GemmPlan> kv;     // a_in ctx rows only, K/V weight rows only (prompt prefill)
   std::vector<GemmPlan> o, gu, d;
   GemmPlan lm;
+  // persistent draft-step kernel (step_mega.cuh): tables live in the workspace
+  bool mega = false;
+  bool want_mega = false;
+  int mega_phases = 0;
 
   template <class T>
   T* buf(int id) const { return reinterpret_cast<T*>(base + reg[id].off); }
@@ -98,6 +103,10 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   sz[DFLASH_BUF_ACC_HIST] = static_cast<size_t>(R) * c.hist_len * 4;
   sz[DFLASH_BUF_RNG_STEP] = 8;
   sz[DFLASH_BUF_DRAFT_LOGITS] = c.keep_draft_logits ? static_cast<size_t>(RS) * c.vocab * 2 : 0;
+  const int max_phases = 3 + 12 * c.n_layers + 2, max_gemms = 2 + 4 * c.n_layers;
+  sz[DFLASH_BUF_MEGA_GEMMS] = static_cast<size_t>(max_gemms) * sizeof(MegaGemm);
+  sz[DFLASH_BUF_MEGA_PHASES] = static_cast<size_t>(max_phases) * sizeof(MegaPhase);
+  sz[DFLASH_BUF_MEGA_SYNC] = static_cast<size_t>(4 * max_phases + 16) * 8;
   size_t off = 0;
   for (int i = 0; i < DFLASH_BUF_COUNT; ++i) {
     reg[i].off = off;
@@ -128,6 +137,7 @@ inline int check_config(const dflash_config_t& c) {
     return DFLASH_ERR_ARG;
   }
   if (c.n_sel < 1 || c.n_sel > 8) { set_error("n_sel must be in [1,8]"); return DFLASH_ERR_ARG; }
+  if (c.attn_splits > 16) { set_error("attn_splits must be <= 16"); return DFLASH_ERR_ARG; }
   if (c.max_seq < 2 * c.block_size || c.out_len < 1 || c.hist_len < 1) {
     set_error("max_seq/out_len/hist_len too small");
     return DFLASH_ERR_ARG;
@@ -258,6 +268,9 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   }
   cudaError_t ce = cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
+  ce = cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
+  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize smem attribute"); }
+  e->want_mega = c.use_mega != 0;
   *out = e;
   return DFLASH_OK;
 }
@@ -284,7 +297,7 @@ inline int enqueue_ctx_inject(Engine* e, cudaStream_t st) {
   a.valid_mode = kRowsCtx;
   a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
   a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "fc finalize");
+  if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "fc finalize");
   return DFLASH_OK;
 }
 
@@ -329,7 +342,10 @@ inline int enqueue_ctx_only(Engine* e, cudaStream_t st) {
 
 // One draft step: block embedding -> ctx inject -> L layers -> final norm -> lm_head + argmax.
 // Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247).
+inline int enqueue_draft_step_mega(Engine* e, cudaStream_t st);
+
 inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st) {
+  if (e->mega && noise_embedding == nullptr && run_lm_head) return enqueue_draft_step_mega(e, st);
   const int RS = e->RS;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
@@ -347,7 +363,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     a.resid = x;
     a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
     a.out = a_in + static_cast<size_t>(RS) * e->H;
-    if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "embed+ln1");
+    if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "embed+ln1");
   }
   int rc = enqueue_ctx_inject(e, st);
   if (rc) return rc;
@@ -383,7 +399,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
       a.resid = x;
       a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
       a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
-      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "o finalize");
+      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "o finalize");
     }
     if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
     {
@@ -408,7 +424,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
         a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
         a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
       }
-      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 4, st, e->pdl, a), "down finalize");
+      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "down finalize");
     }
   }
   if (!run_lm_head) return DFLASH_OK;
@@ -422,6 +438,174 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   ta.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
   ta.draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
   DFL_CUDA(launch_pdl(draft_tokens_kernel, dim3(RS), dim3(32), 0, st, e->pdl, ta), "draft tokens");
+  return DFLASH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent step kernel: phase / GEMM tables (same argument structs as the stand-alone schedule above).
+inline bool mega_supported(const Engine* e) {
+  return e->RS == 16 && e->Hq / e->Hkv <= 4 && e->H * 6 <= kMegaScratch && e->lm.mb == 16;
+}
+
+inline int build_mega(Engine* e) {
+  std::vector<MegaGemm> gemms;
+  std::vector<MegaPhase> phases;
+  auto add_gemm = [&](const GemmPlan& p) {
+    MegaGemm g;
+    memset(&g, 0, sizeof(g));
+    g.tmW = p.tmW; g.tmX = p.tmX; g.args = p.args; g.mb = p.mb; g.mode = p.mode; g.grid = p.grid;
+    gemms.push_back(g);
+    MegaPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.kind = kPhGemm;
+    ph.gemm = static_cast<int>(gemms.size()) - 1;
+    phases.push_back(ph);
+  };
+  const bool dup_rows = getenv("DFLASH_MEGA_DUP") != nullptr;  // timing experiment only (results wrong)
+  auto add_rows = [&](const RowsArgs& a, int rows) {
+    MegaPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.kind = kPhRows; ph.n_items = rows; ph.u.rows = a;
+    phases.push_back(ph);
+    if (dup_rows && a.resid != nullptr && a.embed == nullptr) phases.push_back(ph);
+  };
+  const int RS = e->RS;
+  __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
+  __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
+  {
+    RowsArgs a = rows_args_base(e);
+    a.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
+    a.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+    a.ids_ld = e->bs;
+    a.pad_token = e->cfg.mask_token_id;
+    a.resid = x;
+    a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
+    a.out = a_in + static_cast<size_t>(RS) * e->H;
+    add_rows(a, RS);
+  }
+  add_gemm(e->fc);
+  {
+    RowsArgs a = rows_args_base(e);
+    a.ws = e->fc.args.ws;
+    a.sm = slot_map_of(e->fc);
+    a.valid_mode = kRowsCtx;
+    a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
+    a.out = a_in;
+    add_rows(a, RS);
+  }
+  AttnArgs aa;
+  memset(&aa, 0, sizeof(aa));
+  aa.R = e->R; aa.SL = e->SL; aa.bs = e->bs; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.S_max = e->cfg.max_seq;
+  aa.nsplit = e->nsplit_attn;
+  aa.start = e->buf<int>(DFLASH_BUF_START);
+  aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  aa.q = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
+  aa.part_o = e->buf<float>(DFLASH_BUF_ATTN_PO);
+  aa.part_ml = e->buf<float>(DFLASH_BUF_ATTN_ML);
+  aa.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
+  aa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_ATTN_OUT);
+  for (int l = 0; l < e->L; ++l) {
+    add_gemm(e->qkv[l]);
+    QkvPostArgs qa = qkv_post_args(e, l, e->qkv[l], false);
+    {
+      MegaPhase ph;
+      memset(&ph, 0, sizeof(ph));
+      ph.kind = kPhQkvPost; ph.n_items = qa.rows * (e->Hq + 2 * e->Hkv); ph.u.qkv = qa;
+      phases.push_back(ph);
+    }
+    aa.k_cache = qa.k_cache;
+    aa.v_cache = qa.v_cache;
+    {
+      MegaPhase ph;
+      memset(&ph, 0, sizeof(ph));
+      ph.kind = kPhAttn; ph.n_items = e->nsplit_attn * e->Hkv * e->R * (e->SL / 16); ph.u.attn = aa;
+      phases.push_back(ph);
+      ph.kind = kPhCombine; ph.n_items = RS * e->Hq;
+      phases.push_back(ph);
+    }
+    add_gemm(e->o[l]);
+    {
+      RowsArgs a = rows_args_base(e);
+      a.ws = e->o[l].args.ws;
+      a.sm = slot_map_of(e->o[l]);
+      a.resid = x;
+      a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
+      a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
+      add_rows(a, RS);
+    }
+    add_gemm(e->gu[l]);
+    {
+      MegaPhase ph;
+      memset(&ph, 0, sizeof(ph));
+      ph.kind = kPhSwiglu; ph.n_items = RS * (e->I / 4);
+      ph.u.sw.ws = e->gu[l].args.ws;
+      ph.u.sw.sm = slot_map_of(e->gu[l]);
+      ph.u.sw.rows = RS;
+      ph.u.sw.I = e->I;
+      ph.u.sw.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
+      phases.push_back(ph);
+    }
+    add_gemm(e->d[l]);
+    {
+      RowsArgs a = rows_args_base(e);
+      a.ws = e->d[l].args.ws;
+      a.sm = slot_map_of(e->d[l]);
+      a.resid = x;
+      if (l + 1 < e->L) {
+        a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l + 1].ln1);
+        a.out = a_in + static_cast<size_t>(RS) * e->H;
+      } else {
+        a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
+        a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
+      }
+      add_rows(a, RS);
+    }
+  }
+  add_gemm(e->lm);
+  {
+    MegaPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.kind = kPhTokens; ph.n_items = RS;
+    ph.u.tok.cand_val = e->lm.args.cand_val;
+    ph.u.tok.cand_idx = e->lm.args.cand_idx;
+    ph.u.tok.n_cta = e->lm.grid;
+    ph.u.tok.mb = e->lm.mb;
+    ph.u.tok.R = e->R; ph.u.tok.SL = e->SL; ph.u.tok.bs = e->bs;
+    ph.u.tok.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+    ph.u.tok.draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
+    phases.push_back(ph);
+  }
+  for (size_t i = 0; i < phases.size(); ++i) phases[i].dep = static_cast<int>(i) - 1;
+  phases[1].dep = -1;  // fc GEMM reads ctx_feat (written before this kernel): it overlaps with the embed phase
+  if (gemms.size() * sizeof(MegaGemm) > e->reg[DFLASH_BUF_MEGA_GEMMS].bytes ||
+      phases.size() * sizeof(MegaPhase) > e->reg[DFLASH_BUF_MEGA_PHASES].bytes) {
+    set_error("mega tables do not fit their workspace regions");
+    return DFLASH_ERR_ARG;
+  }
+  DFL_CUDA(cudaMemcpy(e->buf<void>(DFLASH_BUF_MEGA_GEMMS), gemms.data(), gemms.size() * sizeof(MegaGemm),
+                      cudaMemcpyHostToDevice), "mega gemm table upload");
+  DFL_CUDA(cudaMemcpy(e->buf<void>(DFLASH_BUF_MEGA_PHASES), phases.data(), phases.size() * sizeof(MegaPhase),
+                      cudaMemcpyHostToDevice), "mega phase table upload");
+  DFL_CUDA(cudaMemset(e->buf<void>(DFLASH_BUF_MEGA_SYNC), 0, e->reg[DFLASH_BUF_MEGA_SYNC].bytes), "mega sync clear");
+  DFL_CUDA(cudaFuncSetAttribute(draft_step_mega_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMegaSmemBytes), "mega smem attribute");
+  e->mega_phases = static_cast<int>(phases.size());
+  e->mega = true;
+  return DFLASH_OK;
+}
+
+inline int enqueue_draft_step_mega(Engine* e, cudaStream_t st) {
+  MegaArgs m;
+  m.gemms = e->buf<MegaGemm>(DFLASH_BUF_MEGA_GEMMS);
+  m.phases = e->buf<MegaPhase>(DFLASH_BUF_MEGA_PHASES);
+  m.n_phases = e->mega_phases;
+  unsigned long long* sync = e->buf<unsigned long long>(DFLASH_BUF_MEGA_SYNC);
+  m.bars = sync + 8;
+  m.epoch = sync;
+  m.err = reinterpret_cast<int*>(sync + 1);
+  m.trace = getenv("DFLASH_MEGA_TRACE") ? sync + 8 + (3 + 12 * e->L + 2) : nullptr;
+  draft_step_mega_kernel<16><<<e->grid, kMegaThreads, kMegaSmemBytes, st>>>(m);
+  DFL_CUDA(cudaGetLastError(), "mega step launch");
   return DFLASH_OK;
 }
 

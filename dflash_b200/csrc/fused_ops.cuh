@@ -42,17 +42,25 @@ __device__ __forceinline__ int tile_slots32(int t, const SlotMap& sm) {
 __device__ __forceinline__ float sum_slots_n(const float* __restrict__ ws, const SlotMap& sm, int m, int n, int ns) {
   const float* p = ws + static_cast<long long>(m) * sm.ws_ld + n;
   const long long slot_stride = static_cast<long long>(sm.ws_rows) * sm.ws_ld;
-  float acc = p[0];
-  for (int s = 1; s < ns; ++s) acc += p[s * slot_stride];
+  float acc = __ldcg(p);
+  for (int s = 1; s < ns; ++s) acc += __ldcg(p + s * slot_stride);
   return acc;
 }
 __device__ __forceinline__ float4 sum_slots_4(const float* __restrict__ ws, const SlotMap& sm, int m, int n, int ns) {
   const float* p = ws + static_cast<long long>(m) * sm.ws_ld + n;
   const long long slot_stride = static_cast<long long>(sm.ws_rows) * sm.ws_ld;
-  float4 acc = *reinterpret_cast<const float4*>(p);
-  for (int s = 1; s < ns; ++s) {
-    const float4 v = *reinterpret_cast<const float4*>(p + s * slot_stride);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  // issue every slot's load before the first add (these are L2 round trips; the adds stay in slot order)
+  float4 v[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < ns) v[s] = __ldcg(reinterpret_cast<const float4*>(p + s * slot_stride));
+  float4 acc = v[0];
+#pragma unroll
+  for (int s = 1; s < 8; ++s)
+    if (s < ns) { acc.x += v[s].x; acc.y += v[s].y; acc.z += v[s].z; acc.w += v[s].w; }
+  for (int s = 8; s < ns; ++s) {
+    const float4 w = __ldcg(reinterpret_cast<const float4*>(p + s * slot_stride));
+    acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
   }
   return acc;
 }
@@ -95,8 +103,8 @@ __device__ __forceinline__ void argmax_candidates(const float* __restrict__ cand
   bv = -INFINITY;
   bi = 0x7fffffff;
   for (int g = threadIdx.x; g < n_cta; g += 32) {
-    const float v = cand_val[static_cast<long long>(g) * mb + row];
-    const int i = cand_idx[static_cast<long long>(g) * mb + row];
+    const float v = __ldcg(cand_val + static_cast<long long>(g) * mb + row);
+    const int i = __ldcg(cand_idx + static_cast<long long>(g) * mb + row);
     if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
   }
 #pragma unroll
@@ -136,18 +144,31 @@ struct DraftTokArgs {
   long long* draft_tokens;  // [R*SL] every row's argmax (slot 0 included), for inspection
 };
 
-__global__ void __launch_bounds__(32) draft_tokens_kernel(const DraftTokArgs a) {
-  pdl_trigger();
-  pdl_wait();
-  const int row = blockIdx.x;
-  float bv;
-  int bi;
-  argmax_candidates(a.cand_val, a.cand_idx, a.n_cta, a.mb, row, bv, bi);
-  if (threadIdx.x == 0) {
+__device__ __forceinline__ void draft_tokens_row(const DraftTokArgs& a, int row, int lane) {
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int g = lane; g < a.n_cta; g += 32) {
+    const float v = __ldcg(a.cand_val + static_cast<long long>(g) * a.mb + row);
+    const int i = __ldcg(a.cand_idx + static_cast<long long>(g) * a.mb + row);
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) {
     a.draft_tokens[row] = bi;
     const int r = row / a.SL, i = row % a.SL;
     if (i >= 1 && i < a.bs) a.block_ids[static_cast<long long>(r) * a.bs + i] = bi;
   }
+}
+
+__global__ void __launch_bounds__(32) draft_tokens_kernel(const DraftTokArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  draft_tokens_row(a, blockIdx.x, threadIdx.x);
 }
 
 // =============================================================================================
@@ -186,21 +207,17 @@ constexpr int kRowsMaxTiles = 64;  // H <= 8192
 // One CTA per row:  v = bf16(sum of partials)           (nn.Linear output dtype)
 //                   v = bf16(resid + v); resid = v       (residual add, model/dflash.py:140,144)
 //                   out = w * bf16(v * rsqrt(mean(v^2) + eps))   (Qwen3RMSNorm, fp32 inside)
-// dynamic smem: H floats (the row, kept between the two passes)
-__global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsArgs a) {
-  // wait first, trigger second: the GEMM behind this kernel then becomes resident exactly when this
-  // kernel starts its real work, and its pre-wait weight prefetch keeps HBM busy meanwhile
-  pdl_wait();
-  pdl_trigger();
-  extern __shared__ __align__(16) float rowbuf[];
-  __shared__ float red[kRowsThreads / 32];
-  __shared__ int ns_tab[kRowsMaxTiles];
-  const int row = blockIdx.x;
+// rowbuf: 6*H bytes of shared memory (the row as H floats + H bf16 norm weights); red: NT/32 floats; ns_tab:
+// kRowsMaxTiles ints. NT threads (tid in [0, NT)) work on one row and meet at named barrier bar_id.
+template <int NT>
+__device__ __forceinline__ void finalize_row_body(const RowsArgs& a, int row, int tid, float* rowbuf, float* red,
+                                                  int* ns_tab, int bar_id) {
   if (a.valid_mode == kRowsCtx) {
     const int r = row / a.SL, j = row % a.SL;
     if (j >= a.ctx_len[r]) return;
   }
   const long long roff = static_cast<long long>(row) * a.H;
+  __nv_bfloat16* wbuf = reinterpret_cast<__nv_bfloat16*>(rowbuf + a.H);  // H bf16 norm weights behind the H floats
   const bool from_embed = a.embed != nullptr;
   long long tok = 0;
   if (from_embed) {
@@ -209,47 +226,80 @@ __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsA
     else tok = (i < a.bs) ? a.ids[static_cast<long long>(r) * a.ids_ld + i] : a.pad_token;
   } else {
     const int nt = (a.H + kTileN - 1) / kTileN;
-    for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
-    __syncthreads();
+    for (int t = tid; t < nt; t += NT) ns_tab[t] = tile_slots32(t, a.sm);
+    group_sync(bar_id, NT);
   }
   float ss = 0.f;
-  for (int n = threadIdx.x * 4; n < a.H; n += kRowsThreads * 4) {
-    float4 x;
-    if (from_embed) {
-      x = unpack4_bf16(*reinterpret_cast<const uint2*>(a.embed + tok * a.H + n));
-      if (a.resid != nullptr) *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
-    } else {
-      x = sum_slots_4(a.ws, a.sm, row, n, ns_tab[n / kTileN]);
-      x.x = bf16_round(x.x); x.y = bf16_round(x.y); x.z = bf16_round(x.z); x.w = bf16_round(x.w);
-      if (a.resid != nullptr) {
-        const float4 rsd = unpack4_bf16(*reinterpret_cast<const uint2*>(a.resid + roff + n));
-        x.x = bf16_round(rsd.x + x.x); x.y = bf16_round(rsd.y + x.y);
-        x.z = bf16_round(rsd.z + x.z); x.w = bf16_round(rsd.w + x.w);
-        *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
+  constexpr int U = 4;  // iterations whose loads are issued together (latency-bound: ~1 us per L2 round trip)
+  for (int n0 = tid * 4; n0 < a.H; n0 += NT * 4 * U) {
+    float4 x[U];
+    uint2 rs[U], wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int n = n0 + u * NT * 4;
+      if (n < a.H) {
+        if (a.norm_w != nullptr) wv[u] = *reinterpret_cast<const uint2*>(a.norm_w + n);  // for pass 2, fetched now
+        if (from_embed) {
+          rs[u] = *reinterpret_cast<const uint2*>(a.embed + tok * a.H + n);
+        } else {
+          x[u] = sum_slots_4(a.ws, a.sm, row, n, ns_tab[n / kTileN]);
+          if (a.resid != nullptr) rs[u] = __ldcg(reinterpret_cast<const uint2*>(a.resid + roff + n));
+        }
       }
     }
-    if (a.norm_w == nullptr) {
-      *reinterpret_cast<uint2*>(a.out + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
-    } else {
-      *reinterpret_cast<float4*>(rowbuf + n) = x;
-      ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int n = n0 + u * NT * 4;
+      if (n >= a.H) continue;
+      float4 v;
+      if (from_embed) {
+        v = unpack4_bf16(rs[u]);
+        if (a.resid != nullptr) *reinterpret_cast<uint2*>(a.resid + roff + n) = rs[u];
+      } else {
+        v = x[u];
+        v.x = bf16_round(v.x); v.y = bf16_round(v.y); v.z = bf16_round(v.z); v.w = bf16_round(v.w);
+        if (a.resid != nullptr) {
+          const float4 rsd = unpack4_bf16(rs[u]);
+          v.x = bf16_round(rsd.x + v.x); v.y = bf16_round(rsd.y + v.y);
+          v.z = bf16_round(rsd.z + v.z); v.w = bf16_round(rsd.w + v.w);
+          *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(v.x, v.y, v.z, v.w);
+        }
+      }
+      if (a.norm_w == nullptr) {
+        *reinterpret_cast<uint2*>(a.out + roff + n) = pack4_bf16(v.x, v.y, v.z, v.w);
+      } else {
+        *reinterpret_cast<float4*>(rowbuf + n) = v;
+        *reinterpret_cast<uint2*>(wbuf + n) = wv[u];
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
     }
   }
   if (a.norm_w == nullptr) return;
   ss = warp_sum(ss);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  group_sync(bar_id, NT);
   float tot = 0.f;
 #pragma unroll
-  for (int w = 0; w < kRowsThreads / 32; ++w) tot += red[w];
+  for (int w = 0; w < NT / 32; ++w) tot += red[w];
   const float rstd = 1.0f / sqrtf(tot / static_cast<float>(a.H) + a.eps);
-  for (int n = threadIdx.x * 4; n < a.H; n += kRowsThreads * 4) {
+  for (int n = tid * 4; n < a.H; n += NT * 4) {
     const float4 x = *reinterpret_cast<const float4*>(rowbuf + n);
-    const float4 w = unpack4_bf16(*reinterpret_cast<const uint2*>(a.norm_w + n));
+    const float4 w = unpack4_bf16(*reinterpret_cast<const uint2*>(wbuf + n));
     *reinterpret_cast<uint2*>(a.out + roff + n) =
         pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
                    w.w * bf16_round(x.w * rstd));
   }
+}
+
+__global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsArgs a) {
+  // wait first, trigger second: the GEMM behind this kernel then becomes resident exactly when this
+  // kernel starts its real work
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float red[kRowsThreads / 32];
+  __shared__ int ns_tab[kRowsMaxTiles];
+  finalize_row_body<kRowsThreads>(a, blockIdx.x, threadIdx.x, rowbuf, red, ns_tab, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,16 +320,45 @@ __device__ __forceinline__ float silu_mul_bf16(float g, float u) {
   return s * u;
 }
 
-__global__ void __launch_bounds__(256) swiglu_kernel(const SwigluArgs a) {
-  pdl_wait();
-  pdl_trigger();
-  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
-  const int m = blockIdx.y;
-  if (n >= a.I) return;
+// four consecutive columns n..n+3 of row m
+__device__ __forceinline__ void swiglu_item(const SwigluArgs& a, int m, int n) {
   const float4 g = sum_slots_4(a.ws, a.sm, m, n, tile_slots32(n / kTileN, a.sm));
   const float4 u = sum_slots_4(a.ws, a.sm, m, a.I + n, tile_slots32((a.I + n) / kTileN, a.sm));
   *reinterpret_cast<uint2*>(a.out + static_cast<long long>(m) * a.I + n) =
       pack4_bf16(silu_mul_bf16(g.x, u.x), silu_mul_bf16(g.y, u.y), silu_mul_bf16(g.z, u.z), silu_mul_bf16(g.w, u.w));
+}
+
+// up to three items (it0, it0+stride, it0+2*stride) with all their partial loads in flight together
+__device__ __forceinline__ void swiglu_items3(const SwigluArgs& a, int it0, int stride, int n_items) {
+  const int per_row = a.I / 4;
+  float4 g[3], u[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int it = it0 + j * stride;
+    if (it < n_items) {
+      const int m = it / per_row, n = (it % per_row) * 4;
+      g[j] = sum_slots_4(a.ws, a.sm, m, n, tile_slots32(n / kTileN, a.sm));
+      u[j] = sum_slots_4(a.ws, a.sm, m, a.I + n, tile_slots32((a.I + n) / kTileN, a.sm));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int it = it0 + j * stride;
+    if (it < n_items) {
+      const int m = it / per_row, n = (it % per_row) * 4;
+      *reinterpret_cast<uint2*>(a.out + static_cast<long long>(m) * a.I + n) =
+          pack4_bf16(silu_mul_bf16(g[j].x, u[j].x), silu_mul_bf16(g[j].y, u[j].y), silu_mul_bf16(g[j].z, u[j].z),
+                     silu_mul_bf16(g[j].w, u[j].w));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) swiglu_kernel(const SwigluArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (n >= a.I) return;
+  swiglu_item(a, blockIdx.y, n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -308,14 +387,10 @@ struct QkvPostArgs {
   int S_max;
 };
 
-__global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
-  pdl_trigger();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
+// one (row, head) item per warp; item in [0, rows * (q_cols/128 + 2*Hkv))
+__device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, int lane) {
   const int heads_q = a.q_cols / 128;
   const int heads_per_row = heads_q + 2 * a.Hkv;
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (item >= a.rows * heads_per_row) return;
   const int row = a.row0 + item / heads_per_row;
   const int hh = item % heads_per_row;
   const int RS = a.R * a.SL;
@@ -377,6 +452,14 @@ __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
     o[t] = bf16_round(bf16_round(x[t] * cs) + bf16_round(rot * sn));
   }
   *reinterpret_cast<uint2*>(dst + lane * 4) = pack4_bf16(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= a.rows * (a.q_cols / 128 + 2 * a.Hkv)) return;
+  qkv_post_item(a, item, threadIdx.x & 31);
 }
 
 }  // namespace dfl

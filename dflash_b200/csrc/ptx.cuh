@@ -157,6 +157,11 @@ __device__ __forceinline__ void pdl_trigger() {
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 }
 
+// named barrier over `nthreads` threads of the CTA (id 0 with blockDim.x threads == __syncthreads)
+__device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");
+}
+
 // ----------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));

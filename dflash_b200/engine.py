@@ -23,7 +23,7 @@ class CConfig(Structure):
         ("max_requests", c_int), ("max_seq", c_int), ("out_len", c_int), ("hist_len", c_int),
         ("rms_eps", c_float), ("rope_scale", c_float), ("mask_token_id", c_longlong), ("attn_splits", c_int),
         ("post_splits", c_int), ("gemm_grid", c_int), ("use_pdl", c_int), ("keep_draft_logits", c_int),
-        ("prefetch_mb", c_int),
+        ("prefetch_mb", c_int), ("use_mega", c_int),
     ]
 
 
@@ -45,7 +45,8 @@ BUFFERS = [
     ("draft_tokens", torch.int64), ("block_ids", torch.int64), ("posterior", torch.int64),
     ("output_ids", torch.int64), ("start", torch.int32), ("ctx_len", torch.int32), ("done", torch.int32),
     ("n_cycles", torch.int32), ("blk_len", torch.int32), ("max_len", torch.int32), ("acc_hist", torch.int32),
-    ("rng_step", torch.int64), ("draft_logits", torch.bfloat16),
+    ("rng_step", torch.int64), ("draft_logits", torch.bfloat16), ("mega_gemms", torch.uint8),
+    ("mega_phases", torch.uint8), ("mega_sync", torch.int64),
 ]
 
 
@@ -126,7 +127,7 @@ class DraftEngine:
     def __init__(self, draft, embed_weight: torch.Tensor, lm_head_weight: torch.Tensor, *, max_seq: int,
                  out_len: int, max_requests: int = 1, block_size: Optional[int] = None, use_pdl: bool = True,
                  keep_draft_logits: bool = False, gemm_grid: int = 0, attn_splits: int = 0, hist_len: int = 4096,
-                 prefetch_mb: int = 0, device=None):
+                 prefetch_mb: int = 0, use_mega: Optional[bool] = None, device=None):
         self.lib = _lib.load()
         _declare(self.lib)
         if not torch.cuda.is_available():
@@ -155,7 +156,8 @@ class DraftEngine:
             max_seq=int(max_seq), out_len=int(out_len), hist_len=int(hist_len), rms_eps=float(cfg.rms_norm_eps),
             rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id, attn_splits=attn_splits,
             post_splits=0, gemm_grid=gemm_grid, use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits),
-            prefetch_mb=int(os.environ.get("DFLASH_PREFETCH_MB", prefetch_mb)))
+            prefetch_mb=int(os.environ.get("DFLASH_PREFETCH_MB", prefetch_mb)),
+            use_mega=int(os.environ.get("DFLASH_MEGA", "0")) if use_mega is None else int(use_mega))
         self.max_seq, self.out_len = int(max_seq), int(out_len)
         with torch.cuda.device(self.device):
             nbytes = self.lib.dflash_workspace_bytes(byref(self.ccfg))

@@ -61,6 +61,8 @@ typedef struct dflash_config {
   int keep_draft_logits;/* also store the draft's bf16 logits (parity tests) */
   int prefetch_mb;      /* MB of its own weights each GEMM prefetches into L2 while it waits for the
                            kernel in front of it (<= 0 = off, the default: it did not pay on B200) */
+  int use_mega;         /* 1 = run the draft step as ONE persistent kernel (one CTA per SM, grid barriers between
+                           phases, weights streamed continuously) when the shape allows it (R = 1, bs <= 16) */
 } dflash_config_t;
 
 /* Packed bf16 weights of one draft layer. wqkv = [q_proj; k_proj; v_proj] rows, wgu = [gate; up]. */
@@ -116,6 +118,9 @@ enum dflash_buffer_id {
   DFLASH_BUF_ACC_HIST,     /* int32 [R, hist_len] tau per cycle */
   DFLASH_BUF_RNG_STEP,     /* uint64 [1] */
   DFLASH_BUF_DRAFT_LOGITS, /* bf16 [R*SL, vocab] when keep_draft_logits */
+  DFLASH_BUF_MEGA_GEMMS,   /* persistent step kernel: GEMM table (TMA descriptors) */
+  DFLASH_BUF_MEGA_PHASES,  /* persistent step kernel: phase table */
+  DFLASH_BUF_MEGA_SYNC,    /* uint64: [0] steps done, [1] error code, [8..] per-phase arrival counters */
   DFLASH_BUF_COUNT
 };
 

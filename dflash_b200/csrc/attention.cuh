@@ -75,7 +75,9 @@ __host__ __device__ inline int attn_chunk(int L, int nsplit) {
 
 // One (split, kv head h, request r, query tile qt) work item, executed by `group` warps
 // (tid in [0, 32*group)). NSTG = K/V smem stages (1 or 2) at smem0; bar_id = named barrier of the group.
-template <int NSTG>
+// LOCAL: partials are indexed (row_in_tile * group + head_in_group) -- a per-CTA buffer (shared memory of the
+// cluster-fused kernel) -- instead of the global [split][row][head] layout.
+template <int NSTG, bool LOCAL = false>
 __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt, int h, int split, int tid,
                                                 int nthreads, uint32_t smem0, int bar_id) {
   const int warp = tid >> 5, lane = tid & 31;
@@ -89,7 +91,10 @@ __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt
   const int g = lane >> 2, tq = lane & 3;
   const int row_lo = r * a.SL + qt * 16 + g;  // this thread's two query rows: row_lo, row_lo + 8
 
-  auto part_index = [&](int rl) { return (static_cast<long long>(split) * RS + rl) * a.Hq + hq; };
+  auto part_index = [&](int rl) -> long long {
+    if (LOCAL) return static_cast<long long>(rl - (r * a.SL + qt * 16)) * group + warp;
+    return (static_cast<long long>(split) * RS + rl) * a.Hq + hq;
+  };
   if (k0 >= L) {
     if (tq == 0) {
       a.part_ml[part_index(row_lo) * 2 + 0] = -INFINITY;

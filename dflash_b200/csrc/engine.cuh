@@ -9,6 +9,7 @@
 #include "../../include/dflash_b200.h"
 #include "attention.cuh"
 #include "fused_ops.cuh"
+#include "attn_fused.cuh"
 #include "step_mega.cuh"
 #include "verify.cuh"
 
@@ -37,6 +38,7 @@ struct Engine {
   GemmPlan lm;
   // persistent draft-step kernel (step_mega.cuh): tables live in the workspace
   bool mega = false;
+  bool fused_attn = false;  // cluster-fused qkv_post + attention + combine (attn_fused.cuh)
   bool want_mega = false;
   int mega_phases = 0;
 
@@ -176,6 +178,27 @@ inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   return cudaLaunchKernelEx(&cfg, kern, args);
 }
 
+template <class Kern, class Args>
+inline cudaError_t launch_cluster_pdl(Kern kern, dim3 grid, dim3 block, dim3 cluster, size_t smem, cudaStream_t st,
+                                      bool pdl, const Args& args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster.x;
+  at[0].val.clusterDim.y = cluster.y;
+  at[0].val.clusterDim.z = cluster.z;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
 inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, void* workspace,
                          size_t workspace_bytes, int sm_count, Engine** out) {
   int rc = check_config(c);
@@ -270,7 +293,41 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
   ce = cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize smem attribute"); }
+  // One shared-memory carveout for every kernel of the step: consecutive kernels with different L1/smem splits
+  // cannot share an SM, which would serialise exactly the PDL overlaps the schedule relies on.
+  if (!getenv("DFLASH_NO_CARVEOUT")) {
+    const int mx = cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(gemm_skinny_kernel<16, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<32, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<64, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<128, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<256, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<16, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<32, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<64, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<128, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(swiglu_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(attn_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(draft_tokens_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(accept_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(ctx_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaGetLastError();
+  }
   e->want_mega = c.use_mega != 0;
+  {
+    const char* fe = getenv("DFLASH_FUSED_ATTN");
+    const int group = e->Hq / e->Hkv;
+    e->fused_attn = fe != nullptr && atoi(fe) != 0;  // opt-in: measured 758 vs 750 us/step, no gain
+    if (e->fused_attn) {
+      ce = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_fused_smem(group));
+      if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "fused attention smem attribute"); }
+    }
+  }
   *out = e;
   return DFLASH_OK;
 }
@@ -383,14 +440,24 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->qkv[l], st, e->pdl), "qkv gemm");
     QkvPostArgs qa = qkv_post_args(e, l, e->qkv[l], false);
     const int items = qa.rows * (e->Hq + 2 * e->Hkv);
-    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
     aa.k_cache = qa.k_cache;
     aa.v_cache = qa.v_cache;
+    if (e->fused_attn && !dbg_skip()) {
+      AttnFusedArgs fa;
+      fa.post = qa;
+      fa.attn = aa;
+      fa.attn.nsplit = kFusedSplits;
+      DFL_CUDA(launch_cluster_pdl(attn_fused_kernel, dim3(kFusedSplits, e->Hkv, e->R * (e->SL / 16)),
+                                  dim3(32 * (group + kFusedPostWarps)), dim3(kFusedSplits, 1, 1), attn_fused_smem(group), st, e->pdl, fa),
+               "fused attention");
+    } else {
+    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
     if (!(dbg_skip() & 16)) DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
                         kAttnSmem, st, e->pdl, aa),
              "attention");
     if (!(dbg_skip() & 4)) DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + 7) / 8), dim3(256), 0, st, e->pdl, aa),
              "attention combine");
+    }
     if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
     {
       RowsArgs a = rows_args_base(e);

@@ -387,12 +387,9 @@ struct QkvPostArgs {
   int S_max;
 };
 
-// one (row, head) item per warp; item in [0, rows * (q_cols/128 + 2*Hkv))
-__device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, int lane) {
+// one (activation row, head column block hh) item per warp
+__device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, int hh, int lane) {
   const int heads_q = a.q_cols / 128;
-  const int heads_per_row = heads_q + 2 * a.Hkv;
-  const int row = a.row0 + item / heads_per_row;
-  const int hh = item % heads_per_row;
   const int RS = a.R * a.SL;
   const bool is_block = row >= RS;
   const int rl = is_block ? row - RS : row;
@@ -452,6 +449,12 @@ __device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, in
     o[t] = bf16_round(bf16_round(x[t] * cs) + bf16_round(rot * sn));
   }
   *reinterpret_cast<uint2*>(dst + lane * 4) = pack4_bf16(o[0], o[1], o[2], o[3]);
+}
+
+// item in [0, rows * (q_cols/128 + 2*Hkv))
+__device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, int lane) {
+  const int heads_per_row = a.q_cols / 128 + 2 * a.Hkv;
+  qkv_post_rowhead(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
 }
 
 __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gemm_skinny.cuh"
@@ -144,6 +145,7 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   p->args.w_ld = K;
   p->args.w_rows = static_cast<int>(w_rows_total);
   p->args.pf_units = 0;
+  p->args.late_w = getenv("DFLASH_LATE_W") ? 1 : 0;
   p->mb = mb;
   p->mode = mode;
   p->args.n_tiles = (N + kTileN - 1) / kTileN;

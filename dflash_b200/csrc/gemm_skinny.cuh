@@ -56,6 +56,7 @@ struct GemmArgs {
   long long w_ld;
   int w_rows;          // rows of the weight matrix (prefetch bound)
   int pf_units;        // 0 = off
+  int late_w;          // experiment: issue the first weight tiles only after griddepcontrol.wait
 };
 
 // The CTA that owns flat unit x when T units are cut into G ranges [floor(g*T/G), floor((g+1)*T/G)).
@@ -164,6 +165,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const long long n_units = u1 - u0;
       const int npre = n_units < S ? static_cast<int>(n_units) : S;
       // weight tiles first: they do not depend on the predecessor kernel
+      if (a.late_w) pdl_wait();
       for (int i = 0; i < npre; ++i) {
         const long long u = u0 + i;
         const int tile = static_cast<int>(u / a.k_blocks);

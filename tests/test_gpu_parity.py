@@ -441,3 +441,80 @@ def test_graphed_target_matches_eager_target(sync_every):
     gen = out2[0, 21:].tolist()
     assert gen[-1] == stop[0] and stop[0] not in gen[:-1]
     draft.release_engine()
+
+
+# ------------------------------------------------------------------------------------------------
+# full BASELINE size (Qwen3-8B + DFlash-b16 dims): one prompt context + two cycles against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_full_size_qwen3_8b_step_vs_oracle():
+    dev = _cuda()
+    import bench
+    from oracle import dflash_oracle as O
+    dims = bench.Q8
+    H, V, L, bs = dims["hidden"], dims["vocab"], dims["draft_layers"], dims["block_size"]
+    draft, eng, embed, lm_head = bench.build_engine(dims, dev, seed=3)
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = {k: v.detach() for k, v in draft.state_dict().items()}
+    g = torch.Generator(device=dev).manual_seed(11)
+    P = 77
+    hs = [(torch.randn(P, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(L)]
+    prompt = torch.randint(0, V - 1, (P,), device=dev, generator=g)
+    eng.reset_request(0, prompt, 12345, 256)
+    eng.prefill_context(0, hs)
+    cache = O.DraftCache()
+    cache32 = O.DraftCache()
+    sd32 = {k: v.float() for k, v in sd.items()}
+    pend = torch.cat(hs, dim=-1).unsqueeze(0)
+    start = P
+    block = torch.tensor([[12345] + [cfg.mask_token_id] * (bs - 1)], device=dev)
+    for cyc in range(2):
+        eng.draft_step()
+        torch.cuda.synchronize()
+        with torch.inference_mode():
+            pos = torch.arange(cache.get_seq_length(), start + bs, device=dev).unsqueeze(0)
+            noise = torch.nn.functional.embedding(block, embed)
+            # the reference's default dispatch is sdpa (fp32 scores inside); "eager" additionally rounds the scores
+            # to bf16. Both in bf16, plus an fp32 run of the same weights as the yardstick for bf16 noise.
+            O.ATTN_IMPL = "sdpa"
+            c_sdpa = O.DraftCache([None if k is None else k.clone() for k in cache.keys],
+                                  [None if v is None else v.clone() for v in cache.values])
+            hid_sdpa = O.draft_forward(sd, cfg, pend, noise, pos, c_sdpa)
+            O.ATTN_IMPL = "eager"
+            c32 = O.DraftCache([None if k is None else k.float() for k in cache32.keys],
+                               [None if v is None else v.float() for v in cache32.values])
+            hid32 = O.draft_forward(sd32, cfg, pend.float(), noise.float(), pos, cache32)
+            del c32
+            cache32.crop(start)
+            hid = O.draft_forward(sd, cfg, pend, noise, pos, cache)
+            cache.crop(start)
+            ref_logits = torch.nn.functional.linear(hid_sdpa[0, 1:], lm_head)
+        e_sdpa, e_eager = _rel_err(eng.hn[:bs], hid_sdpa[0]), _rel_err(eng.hn[:bs], hid[0])
+        e_32 = _rel_err(eng.hn[:bs], hid32[0])
+        n_sdpa, n_eager = _rel_err(hid_sdpa[0], hid32[0]), _rel_err(hid[0], hid32[0])
+        print(f"cycle {cyc}: engine vs bf16-sdpa {e_sdpa:.4f}, vs bf16-eager {e_eager:.4f}, vs fp32 {e_32:.4f}; "
+              f"bf16-sdpa vs fp32 {n_sdpa:.4f}, bf16-eager vs fp32 {n_eager:.4f}")
+        # within 2e-2 of the reference's sdpa path, and no further from the fp32 result than the reference's own bf16 runs
+        assert e_sdpa < REL_TOL, (cyc, e_sdpa)
+        assert e_32 < 1.25 * max(n_sdpa, n_eager), (cyc, e_32, n_sdpa, n_eager)
+        got = eng.block_ids[0, 1:].cpu().tolist()
+        ref_tok = ref_logits.float().argmax(-1).cpu().tolist()
+        for i, (a, b) in enumerate(zip(got, ref_tok)):
+            if a != b:  # only where the oracle's own margin is inside the bf16 logit tolerance
+                row = ref_logits[i].float()
+                assert (row[b] - row[a]).item() <= REL_TOL * row.abs().max().item(), (cyc, i, a, b)
+        # verify with a synthetic target: accept 5 tokens, then the bonus
+        tl = torch.randn(bs, V, device=dev, generator=g).to(torch.bfloat16)
+        hsel = [(torch.randn(bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(L)]
+        forced = torch.tensor([[5]], dtype=torch.int32, device=dev)
+        blk = eng.block_ids[0].clone()
+        eng.verify_step(tl, hsel, forced_k=forced)
+        torch.cuda.synchronize()
+        post = tl.float().argmax(-1)
+        post[:5] = blk[1:6]
+        assert eng.posterior[0].tolist() == post.tolist()
+        assert int(eng.buf["ctx_len"][0]) == 6 and int(eng.buf["start"][0]) == start + 6
+        start += 6
+        pend = torch.cat([h[:6] for h in hsel], dim=-1).unsqueeze(0)
+        block = torch.tensor([[int(post[5])] + [cfg.mask_token_id] * (bs - 1)], device=dev)
+        assert eng.block_ids[0].tolist() == block[0].tolist()
+    eng.close()

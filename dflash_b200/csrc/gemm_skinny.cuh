@@ -93,7 +93,9 @@ struct GemmCfg {
   static constexpr int kWBytes = kTileN * kTileK * 2;   // 16 KB
   static constexpr int kXBytes = MB * kTileK * 2;
   static constexpr int kStageBytes = kWBytes + kXBytes;
-  static constexpr int kBudget = (MODE == 1 ? DFLASH_GEMM_SMEM_KB_ARGMAX : DFLASH_GEMM_SMEM_KB_PARTIALS) * 1024;
+  // wide activation tiles (batched engines) need the whole SM to keep >= 4 stages in flight
+  static constexpr int kBudget =
+      ((MODE == 1 || MB >= 64) ? DFLASH_GEMM_SMEM_KB_ARGMAX : DFLASH_GEMM_SMEM_KB_PARTIALS) * 1024;
   static constexpr int kStages = kBudget / kStageBytes < 3 ? 3 : kBudget / kStageBytes;
   static constexpr int kTmemCols = (2 * MB < 32) ? 32 : 2 * MB;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;

@@ -395,29 +395,41 @@ def run_cuda_arm(args):
     res_dev = torch.empty(2 + bs, dtype=torch.int64, device=device)
     h2d = tl_host.numel() * 2 + sum(h.numel() * 2 for h in hs_host)
     d2h = res_host.numel() * 8
-    e2e_graph = torch.cuda.CUDAGraph()
+    # Two graphs (draft / verify) and a copy stream: the step's host inputs -- the target's logits and hidden states
+    # -- are only consumed by the verify half, so their H2D copy overlaps the draft half.
+    draft_graph, verify_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    copy_stream = torch.cuda.Stream(device=device)
+    copied = torch.cuda.Event()
 
-    def e2e_enqueue():
-        eng.draft_step()
+    def verify_enqueue():
         eng.verify_step(tl_dev, hs_dev, temperature=0.0, forced_k=forced)
-
-    with torch.cuda.stream(side):
-        e2e_enqueue()
-    torch.cuda.synchronize()
-    with torch.cuda.graph(e2e_graph, stream=side):
-        e2e_enqueue()
-    torch.cuda.synchronize()
-
-    def e2e_step():
-        tl_dev.copy_(tl_host, non_blocking=True)
-        for d, h in zip(hs_dev, hs_host):
-            d.copy_(h, non_blocking=True)
-        e2e_graph.replay()
         res_dev[0] = eng.buf["start"][0]
         res_dev[1] = eng.buf["ctx_len"][0]
         res_dev[2:] = eng.posterior[0]
+
+    with torch.cuda.stream(side):
+        eng.draft_step()
+        verify_enqueue()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(draft_graph, stream=side):
+        eng.draft_step()
+    with torch.cuda.graph(verify_graph, stream=side):
+        verify_enqueue()
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)  # the previous step's verify has consumed tl_dev / hs_dev
+        with torch.cuda.stream(copy_stream):
+            tl_dev.copy_(tl_host, non_blocking=True)
+            for d, h in zip(hs_dev, hs_host):
+                d.copy_(h, non_blocking=True)
+            copied.record(copy_stream)
+        draft_graph.replay()
+        main.wait_event(copied)
+        verify_graph.replay()
         res_host.copy_(res_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the accepted length every cycle
+        main.synchronize()  # the caller reads the accepted length every cycle
         return int(res_host[1])
 
     do_reset()
@@ -521,7 +533,9 @@ def run_cuda_arm(args):
             step_roofline=dict(bound="hbm", achieved=step_gbs, peak=peak_gbs, unit="GB/s", frac=step_gbs / peak_gbs,
                                algorithmic_bytes=ab["total"], note="all 58 kernels of the step, median step time"),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
-                          traffic=None, kernel="gemm_skinny_kernel<16,argmax> (lm_head 151936x4096 + fused argmax)",
+                          traffic=1244.9e6 + 4.04e6,  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one
+                          # `ncu --set full` capture of this command (profiles/r1_summary.md); not re-measured per run
+                          kernel="gemm_skinny_kernel<16,argmax> (lm_head 151936x4096 + fused argmax)",
                           launch_us=lm_us, algorithmic_bytes=lm_bytes, peak_source=peak_src),
             cpu_baseline=cpu,
             e2e=dict(value=e2e_value, unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,

@@ -518,3 +518,25 @@ def test_full_size_qwen3_8b_step_vs_oracle():
         block = torch.tensor([[int(post[5])] + [cfg.mask_token_id] * (bs - 1)], device=dev)
         assert eng.block_ids[0].tolist() == block[0].tolist()
     eng.close()
+
+
+@pytest.mark.parametrize("bs", [8, 32])
+def test_spec_generate_block_size_override_is_lossless(bs):
+    """benchmark.py --block-size: the number of mask slots is overridden at inference (benchmark.py:104-108,419);
+    greedy output stays the target's own greedy continuation for any block size."""
+    dev = _cuda()
+    from tests.tiny_models import TINY
+    target, draft = _tiny(16)
+    draft.block_size = bs
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 33), generator=torch.Generator().manual_seed(9)).to(dev)
+    out = draft.spec_generate(target, prompt, max_new_tokens=30, stop_token_ids=None, temperature=0.0)
+    assert out.shape == (1, 63)
+    with torch.inference_mode():
+        logits = target(out).logits[0].float()
+    pred = logits.argmax(-1)
+    for i in range(32, out.shape[1] - 1):
+        if pred[i].item() != out[0, i + 1].item():
+            assert _near_tie(logits[i], pred[i].item(), out[0, i + 1].item()), i
+    out_f = draft.spec_generate(target, prompt, 30, None, 0.0, forced_k=[bs - 1, 0, 3])
+    assert max(draft.last_acceptance_lengths) == bs and out_f.shape == (1, 63)
+    draft.release_engine()

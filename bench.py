@@ -387,13 +387,19 @@ def run_cuda_arm(args):
     p10, p90 = step_us[len(step_us) // 10], step_us[(len(step_us) * 9) // 10]
 
     # ---- e2e: host buffers in, result out, through the C-ABI call sequence, copies inside the timed region
-    tl_host = tlogits.cpu().pin_memory()
-    hs_host = [h.cpu().pin_memory() for h in hsel]
-    tl_dev = torch.empty_like(tlogits)
-    hs_dev = [torch.empty_like(h) for h in hsel]
+    # the step's host inputs live in ONE pinned staging buffer (logits rows, then the n_sel hidden-state blocks) so
+    # that a step is one cudaMemcpyAsync; the device side is one buffer with views at the same offsets
+    n_tl, n_h = tlogits.numel(), hsel[0].numel()
+    stage_host = torch.empty(n_tl + nsel * n_h, dtype=torch.bfloat16).pin_memory()
+    stage_host[:n_tl].copy_(tlogits.view(-1).cpu())
+    for i, h in enumerate(hsel):
+        stage_host[n_tl + i * n_h: n_tl + (i + 1) * n_h].copy_(h.view(-1).cpu())
+    stage_dev = torch.empty_like(stage_host, device=device)
+    tl_dev = stage_dev[:n_tl].view_as(tlogits)
+    hs_dev = [stage_dev[n_tl + i * n_h: n_tl + (i + 1) * n_h].view_as(hsel[0]) for i in range(nsel)]
     res_host = torch.empty(2 + bs, dtype=torch.int64).pin_memory()
     res_dev = torch.empty(2 + bs, dtype=torch.int64, device=device)
-    h2d = tl_host.numel() * 2 + sum(h.numel() * 2 for h in hs_host)
+    h2d = stage_host.numel() * 2
     d2h = res_host.numel() * 8
     # Two graphs (draft / verify) and a copy stream: the step's host inputs -- the target's logits and hidden states
     # -- are only consumed by the verify half, so their H2D copy overlaps the draft half.
@@ -421,9 +427,7 @@ def run_cuda_arm(args):
         main = torch.cuda.current_stream()
         copy_stream.wait_stream(main)  # the previous step's verify has consumed tl_dev / hs_dev
         with torch.cuda.stream(copy_stream):
-            tl_dev.copy_(tl_host, non_blocking=True)
-            for d, h in zip(hs_dev, hs_host):
-                d.copy_(h, non_blocking=True)
+            stage_dev.copy_(stage_host, non_blocking=True)
             copied.record(copy_stream)
         draft_graph.replay()
         main.wait_event(copied)

@@ -565,7 +565,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--requests", type=int, default=1, choices=[1, 2, 4, 8],
+    ap.add_argument("--requests", type=int, default=1, choices=[1, 2, 4, 8, 16, 32, 64],
                     help="request streams per GPU sharing one weight stream (headline metric is quoted at 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-cycle", action="store_true",

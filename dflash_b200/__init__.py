@@ -15,7 +15,8 @@ def __getattr__(name):
     if name in ("DFlashDraftModel", "DFlashStaticCache", "Qwen3DFlashDecoderLayer", "Qwen3DFlashAttention"):
         from . import model
         return getattr(model, name)
-    if name in ("extract_context_feature", "sample", "build_target_layer_ids", "select_context_states"):
+    if name in ("extract_context_feature", "sample", "build_target_layer_ids", "select_context_states",
+                "ContextTap"):
         from . import utils
         return getattr(utils, name)
     if name in ("DraftEngine",):

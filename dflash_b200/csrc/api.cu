@@ -109,7 +109,13 @@ int dflash_engine_buffer(const dflash_engine_t* e, int id, void** ptr_out, size_
 
 int dflash_prefill_context(dflash_engine_t* e, int r, const void* const* hidden, int P, void* stream) {
   if (!e || !hidden) { set_error("prefill_context: null argument"); return DFLASH_ERR_ARG; }
-  return enqueue_prefill(e->impl, r, hidden, P, static_cast<cudaStream_t>(stream));
+  return enqueue_prefill(e->impl, r, hidden, P, 0, static_cast<cudaStream_t>(stream));
+}
+
+int dflash_prefill_context_at(dflash_engine_t* e, int r, const void* const* hidden, int n_rows, int pos0,
+                              void* stream) {
+  if (!e || !hidden) { set_error("prefill_context_at: null argument"); return DFLASH_ERR_ARG; }
+  return enqueue_prefill(e->impl, r, hidden, n_rows, pos0, static_cast<cudaStream_t>(stream));
 }
 
 int dflash_draft_step(dflash_engine_t* e, const void* noise_embedding, int run_lm_head, void* stream) {
@@ -194,6 +200,7 @@ int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K
   int rc = make_gemm_plan(&p, W, w_rows_total, w_row0, N, K, X, x_rows_total, x_row0, mb, m_valid,
                           kModePartials, grid);
   if (rc) return DFLASH_ERR_ARG;
+  if (ws_rows < p.groups * p.mb) { set_error("gemm_skinny: ws_rows %d < %d", ws_rows, p.groups * p.mb); return DFLASH_ERR_ARG; }
   p.args.ws = ws;
   p.args.ws_rows = ws_rows;
   p.args.ws_ld = ws_ld;
@@ -224,7 +231,7 @@ int dflash_gemm_argmax(const void* W, int w_rows_total, int N, int K, const void
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = launch_gemm(p, st, use_pdl != 0);
   if (e != cudaSuccess) return cuda_fail(e, "gemm_argmax launch");
-  e = launch_reduce_candidates(cand_val, cand_idx, p.grid, mb, m_valid, tokens_out, st);
+  e = launch_reduce_candidates(cand_val, cand_idx, p.grid, p.args.cand_ld, m_valid, tokens_out, st);
   if (e != cudaSuccess) return cuda_fail(e, "reduce_candidates launch");
   return DFLASH_OK;
 }

@@ -33,7 +33,10 @@ struct Engine {
   // plans
   GemmPlan fc;                  // ctx_feat -> partials
   std::vector<GemmPlan> qkv;    // a_in (ctx + block rows)
-  std::vector<GemmPlan> kv;     // a_in ctx rows only, K/V weight rows only (prompt prefill)
+  // prompt pass (c = P rows at once): fc and the K/V rows of wqkv over the dedicated prompt buffers,
+  // one plan per UMMA width so that short prompts do not pay for 256 columns
+  GemmPlan fc_pf[5];            // mb = 16 << i
+  std::vector<GemmPlan> kv_pf;  // [layer * 5 + i]
   std::vector<GemmPlan> o, gu, d;
   GemmPlan lm;
   // persistent draft-step kernel (step_mega.cuh): tables live in the workspace
@@ -48,11 +51,15 @@ struct Engine {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+constexpr int kPrefillRows = 256;  // prompt rows projected per pass (one full-width UMMA)
+
+// UMMA N (activation rows per MMA) for a GEMM over `rows` activation rows; more rows run as column groups.
 inline int round_mb(int rows) {
   for (int mb : {16, 32, 64, 128, 256})
     if (rows <= mb) return mb;
-  return -1;
+  return 256;
 }
+inline int groups_of(int rows) { const int mb = round_mb(rows); return (rows + mb - 1) / mb; }
 
 // Fills reg[] (offsets/sizes) for cfg; returns total bytes or 0 on a bad config.
 inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_count, int* max_slots_out) {
@@ -68,13 +75,15 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   long long ws_elems = 0;
   int max_slots = 1;
   struct G { int rows, N, K; } gs[] = {{RS, H, c.n_sel * H}, {2 * RS, qkv_cols, H}, {RS, H, Hq * 128},
-                                       {RS, 2 * I, H},       {RS, H, I}};
+                                       {RS, 2 * I, H},       {RS, H, I},
+                                       {kPrefillRows, H, c.n_sel * H}, {kPrefillRows, 2 * Hkv * 128, H}};
   for (auto& g : gs) {
     const int nt = (g.N + kTileN - 1) / kTileN, kb = g.K / kTileK;
     const long long T = static_cast<long long>(nt) * kb;
-    const int gg = T < grid ? static_cast<int>(T) : grid;
+    const int ranges = ranges_for(grid, groups_of(g.rows));
+    const int gg = T < ranges ? static_cast<int>(T) : ranges;
     const int s = max_slots_for(nt, kb, gg);
-    const long long e = static_cast<long long>(s) * round_mb(g.rows) * g.N;
+    const long long e = static_cast<long long>(s) * groups_of(g.rows) * round_mb(g.rows) * g.N;
     if (e > ws_elems) ws_elems = e;
     if (s > max_slots) max_slots = s;
   }
@@ -109,6 +118,8 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   sz[DFLASH_BUF_MEGA_GEMMS] = static_cast<size_t>(max_gemms) * sizeof(MegaGemm);
   sz[DFLASH_BUF_MEGA_PHASES] = static_cast<size_t>(max_phases) * sizeof(MegaPhase);
   sz[DFLASH_BUF_MEGA_SYNC] = static_cast<size_t>(4 * max_phases + 16) * 8;
+  sz[DFLASH_BUF_PF_FEAT] = static_cast<size_t>(kPrefillRows) * c.n_sel * H * 2;
+  sz[DFLASH_BUF_PF_A] = static_cast<size_t>(kPrefillRows) * H * 2;
   size_t off = 0;
   for (int i = 0; i < DFLASH_BUF_COUNT; ++i) {
     reg[i].off = off;
@@ -130,10 +141,11 @@ inline int check_config(const dflash_config_t& c) {
     return DFLASH_ERR_ARG;
   }
   const int SL = c.block_size <= 16 ? 16 : 32;
-  if (c.max_requests < 1 || 2 * c.max_requests * SL > 256) {
-    set_error("max_requests %d unsupported: 2*R*%d activation rows must fit one 256-wide UMMA", c.max_requests, SL);
+  if (c.max_requests < 1 || c.max_requests > 64) {
+    set_error("max_requests %d unsupported: 1..64 request streams per engine", c.max_requests);
     return DFLASH_ERR_ARG;
   }
+  (void)SL;
   if ((c.max_requests & (c.max_requests - 1)) != 0) {
     set_error("max_requests %d must be a power of two (activation buffers are exact UMMA widths)", c.max_requests);
     return DFLASH_ERR_ARG;
@@ -234,9 +246,9 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   const int qkv_cols = (e->Hq + 2 * e->Hkv) * 128;
   const int mb_blk = round_mb(RS), mb_all = round_mb(2 * RS);
   float* ws = e->buf<float>(DFLASH_BUF_WS);
-  auto finish = [&](GemmPlan& p, int ws_rows) {
+  auto finish = [&](GemmPlan& p, int) {
     p.args.ws = ws;
-    p.args.ws_rows = ws_rows;
+    p.args.ws_rows = p.groups * p.mb;
     p.args.ws_ld = p.args.N;
   };
 #define DFL_PLAN(call)        \
@@ -249,15 +261,23 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   DFL_PLAN(make_gemm_plan(&e->fc, w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_CTX_FEAT), RS, 0, mb_blk, RS,
                           kModePartials, e->grid));
   finish(e->fc, mb_blk);
-  e->qkv.resize(e->L); e->kv.resize(e->L); e->o.resize(e->L); e->gu.resize(e->L); e->d.resize(e->L);
+  e->qkv.resize(e->L); e->kv_pf.resize(e->L * 5); e->o.resize(e->L); e->gu.resize(e->L); e->d.resize(e->L);
+  for (int i = 0; i < 5; ++i) {
+    DFL_PLAN(make_gemm_plan(&e->fc_pf[i], w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_PF_FEAT), kPrefillRows, 0,
+                            16 << i, 16 << i, kModePartials, e->grid));
+    finish(e->fc_pf[i], 0);
+  }
   for (int l = 0; l < e->L; ++l) {
     const dflash_layer_weights_t& lw = e->layers[l];
     DFL_PLAN(make_gemm_plan(&e->qkv[l], lw.wqkv, qkv_cols, 0, qkv_cols, H, e->buf<void>(DFLASH_BUF_A_IN), 2 * RS, 0,
                             mb_all, 2 * RS, kModePartials, e->grid));
     finish(e->qkv[l], mb_all);
-    DFL_PLAN(make_gemm_plan(&e->kv[l], lw.wqkv, qkv_cols, e->Hq * 128, 2 * e->Hkv * 128, H,
-                            e->buf<void>(DFLASH_BUF_A_IN), 2 * RS, 0, mb_blk, RS, kModePartials, e->grid));
-    finish(e->kv[l], mb_blk);
+    for (int i = 0; i < 5; ++i) {
+      GemmPlan& kp = e->kv_pf[l * 5 + i];
+      DFL_PLAN(make_gemm_plan(&kp, lw.wqkv, qkv_cols, e->Hq * 128, 2 * e->Hkv * 128, H, e->buf<void>(DFLASH_BUF_PF_A),
+                              kPrefillRows, 0, 16 << i, 16 << i, kModePartials, e->grid));
+      finish(kp, 0);
+    }
     DFL_PLAN(make_gemm_plan(&e->o[l], lw.wo, H, 0, H, e->Hq * 128, e->buf<void>(DFLASH_BUF_ATTN_OUT), RS, 0, mb_blk, RS,
                             kModePartials, e->grid));
     finish(e->o[l], mb_blk);
@@ -383,20 +403,6 @@ inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_on
   return a;
 }
 
-// Context-only pass (prompt prefill chunks): ctx inject, then per layer K/V projection of the
-// context rows into the cache. No queries, no block rows.
-inline int enqueue_ctx_only(Engine* e, cudaStream_t st) {
-  int rc = enqueue_ctx_inject(e, st);
-  if (rc) return rc;
-  for (int l = 0; l < e->L; ++l) {
-    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->kv[l], st, e->pdl), "kv gemm");
-    QkvPostArgs qa = qkv_post_args(e, l, e->kv[l], true);
-    const int items = qa.rows * (2 * e->Hkv);
-    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "kv post");
-  }
-  return DFLASH_OK;
-}
-
 // One draft step: block embedding -> ctx inject -> L layers -> final norm -> lm_head + argmax.
 // Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247).
 inline int enqueue_draft_step_mega(Engine* e, cudaStream_t st);
@@ -500,7 +506,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   ta.cand_val = e->lm.args.cand_val;
   ta.cand_idx = e->lm.args.cand_idx;
   ta.n_cta = e->lm.grid;
-  ta.mb = e->lm.mb;
+  ta.mb = e->lm.args.cand_ld;
   ta.R = e->R; ta.SL = e->SL; ta.bs = e->bs;
   ta.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
   ta.draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
@@ -750,35 +756,54 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
   return DFLASH_OK;
 }
 
-// Prompt prefill of request r: P rows of the selected target hidden states go through the
-// context-only pass in chunks of SL rows (cycle 0 of dflash.py:229,238-246 with c = P).
-inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int P, cudaStream_t st) {
-  if (r < 0 || r >= e->R || P < 1 || P + 2 * e->bs > e->cfg.max_seq) {
-    set_error("prefill: bad request %d or prompt length %d (max_seq %d)", r, P, e->cfg.max_seq);
+// Prompt context of request r (cycle 0 of dflash.py:229,238-246 with c = P): `n_rows` rows of the selected target
+// hidden states are projected in passes of up to 256 rows -- fc + hidden_norm, then per layer the K/V rows of wqkv,
+// k_norm, RoPE -- and land at cache positions [pos0, pos0 + n_rows). Real M = P GEMMs: every weight byte is read
+// once per 256 prompt rows. Uses its own feature / activation buffers, so requests that are mid-generation in the
+// same engine keep their pending context rows. Afterwards start[r] = pos0 + n_rows and ctx_len[r] = 0.
+inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int n_rows, int pos0, cudaStream_t st) {
+  if (r < 0 || r >= e->R || n_rows < 1 || pos0 < 0 || pos0 + n_rows + 2 * e->bs > e->cfg.max_seq) {
+    set_error("prefill: bad request %d, rows %d or position %d (max_seq %d)", r, n_rows, pos0, e->cfg.max_seq);
     return DFLASH_ERR_ARG;
   }
-  for (int c0 = 0; c0 < P; c0 += e->SL) {
-    const int c = P - c0 < e->SL ? P - c0 : e->SL;
-    SetStateArgs sa;
-    sa.r = r; sa.start = c0 + c; sa.ctx_len = c;
-    sa.start_p = e->buf<int>(DFLASH_BUF_START);
-    sa.ctx_len_p = e->buf<int>(DFLASH_BUF_CTX_LEN);
-    DFL_CUDA(launch_pdl(set_state_kernel, dim3(1), dim3(1), 0, st, false, sa), "set state");
+  for (int c0 = 0; c0 < n_rows; c0 += kPrefillRows) {
+    const int n = n_rows - c0 < kPrefillRows ? n_rows - c0 : kPrefillRows;
+    int pi = 0;
+    while ((16 << pi) < n) ++pi;
     GatherArgs ga;
     memset(&ga, 0, sizeof(ga));
     for (int s = 0; s < e->nsel; ++s) ga.src[s] = static_cast<const __nv_bfloat16*>(hidden[s]);
     ga.n_sel = e->nsel; ga.H = e->H; ga.SL = e->SL;
-    ga.r0 = r; ga.nreq = 1;
-    ga.src_rows = P;
+    ga.src_rows = n_rows;
     ga.src_row0 = c0;
-    ga.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-    ga.ctx_feat = e->buf<__nv_bfloat16>(DFLASH_BUF_CTX_FEAT);
-    DFL_CUDA(launch_pdl(ctx_gather_kernel, dim3(e->SL, e->nsel), dim3(256), 0, st, false, ga), "prefill gather");
-    int rc = enqueue_ctx_only(e, st);
-    if (rc) return rc;
+    ga.pf_rows = n;
+    ga.ctx_feat = e->buf<__nv_bfloat16>(DFLASH_BUF_PF_FEAT);
+    DFL_CUDA(launch_pdl(ctx_gather_kernel, dim3(n, e->nsel), dim3(256), 0, st, false, ga), "prefill gather");
+    GemmPlan fc = e->fc_pf[pi];
+    fc.args.m_valid = n;
+    DFL_CUDA(launch_gemm(fc, st, e->pdl), "prefill fc gemm");
+    RowsArgs a = rows_args_base(e);
+    a.ws = fc.args.ws;
+    a.sm = slot_map_of(fc);
+    a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
+    a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_PF_A);
+    DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(n), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a),
+             "prefill fc finalize");
+    for (int l = 0; l < e->L; ++l) {
+      GemmPlan kp = e->kv_pf[l * 5 + pi];
+      kp.args.m_valid = n;
+      DFL_CUDA(launch_gemm(kp, st, e->pdl), "prefill kv gemm");
+      QkvPostArgs qa = qkv_post_args(e, l, kp, true);
+      qa.rows = n;
+      qa.pf_rows = n;
+      qa.pf_req = r;
+      qa.pf_pos0 = pos0 + c0;
+      const int items = n * (2 * e->Hkv);
+      DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "prefill kv post");
+    }
   }
   SetStateArgs sa;
-  sa.r = r; sa.start = P; sa.ctx_len = 0;
+  sa.r = r; sa.start = pos0 + n_rows; sa.ctx_len = 0;
   sa.start_p = e->buf<int>(DFLASH_BUF_START);
   sa.ctx_len_p = e->buf<int>(DFLASH_BUF_CTX_LEN);
   DFL_CUDA(launch_pdl(set_state_kernel, dim3(1), dim3(1), 0, st, false, sa), "set state");

@@ -385,17 +385,22 @@ struct QkvPostArgs {
   __nv_bfloat16* k_cache;  // [R][Hkv][S_max][128] (this layer)
   __nv_bfloat16* v_cache;
   int S_max;
+  // prompt pass (pf_rows > 0): every row is a context row of request pf_req at position pf_pos0 + row
+  int pf_rows, pf_req, pf_pos0;
 };
 
 // one (activation row, head column block hh) item per warp
 __device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, int hh, int lane) {
   const int heads_q = a.q_cols / 128;
   const int RS = a.R * a.SL;
-  const bool is_block = row >= RS;
+  const bool is_block = a.pf_rows == 0 && row >= RS;
   const int rl = is_block ? row - RS : row;
-  const int r = rl / a.SL, slot = rl % a.SL;
+  const int r = a.pf_rows > 0 ? a.pf_req : rl / a.SL, slot = rl % a.SL;
   int pos;
-  if (is_block) {
+  if (a.pf_rows > 0) {
+    if (row >= a.pf_rows) return;
+    pos = a.pf_pos0 + row;
+  } else if (is_block) {
     if (slot >= a.blk_len[r]) return;
     pos = a.start[r] + slot;
   } else {

@@ -57,7 +57,8 @@ struct GemmPlan {
   GemmArgs args;
   int mb;     // UMMA N (padded activation rows): 16, 32, 64, 128, 256
   int mode;   // GemmMode
-  int grid;
+  int grid;       // weight ranges (gridDim.y); the launch has groups * grid CTAs
+  int groups;     // column groups of mb activation rows (gridDim.x)
   int max_slots;  // partial slots the consumer must allocate
 };
 
@@ -84,7 +85,7 @@ inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pd
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(p.grid);
+  cfg.gridDim = dim3(p.groups, p.grid);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
@@ -103,6 +104,7 @@ inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl)
       case 32: return launch_gemm_t<32, kModeArgmax>(p, stream, pdl);
       case 64: return launch_gemm_t<64, kModeArgmax>(p, stream, pdl);
       case 128: return launch_gemm_t<128, kModeArgmax>(p, stream, pdl);
+      case 256: return launch_gemm_t<256, kModeArgmax>(p, stream, pdl);
       default: return cudaErrorInvalidValue;
     }
   }
@@ -124,8 +126,13 @@ inline void set_gemm_prefetch(GemmPlan* p, long long bytes) {
   p->args.pf_units = static_cast<int>(per_cta);
 }
 
+// Weight ranges a GEMM with `groups` column groups is cut into: the groups of one range run side by side,
+// so ranges * groups ~ one wave of CTAs.
+inline int ranges_for(int grid, int groups) { return grid / groups > 0 ? grid / groups : 1; }
+
 // Fill a plan. W: [w_rows_total, K] bf16 (pitch K); the GEMM covers weight rows [w_row0, w_row0+N).
-// X: [x_rows_total, K] bf16 (pitch K); activation rows [x_row0, x_row0+mb) feed the MMA.
+// X: [x_rows_total, K] bf16 (pitch K); activation rows [x_row0, x_row0+groups*mb) feed the MMA in `groups`
+// slabs of mb rows (groups = ceil(m_valid / mb)).
 inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, int w_row0, int N, int K,
                           const void* X, int x_rows_total, int x_row0, int mb, int m_valid, int mode,
                           int grid) {
@@ -135,8 +142,9 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
     set_error("gemm: mb=%d unsupported", mb);
     return -1;
   }
-  if (mode == kModeArgmax && mb > 128) { set_error("gemm: argmax mode needs mb<=128"); return -1; }
-  if (x_row0 + mb > x_rows_total) { set_error("gemm: activation buffer too small"); return -1; }
+  const int groups = m_valid > mb ? (m_valid + mb - 1) / mb : 1;
+  if (x_row0 + groups * mb > x_rows_total) { set_error("gemm: activation buffer too small"); return -1; }
+  grid = ranges_for(grid, groups);
   int rc = make_tmap_bf16(&p->tmW, W, w_rows_total, K, K, kTileN);
   if (rc) return rc;
   rc = make_tmap_bf16(&p->tmX, X, x_rows_total, K, K, mb);
@@ -148,6 +156,9 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   p->args.late_w = getenv("DFLASH_LATE_W") ? 1 : 0;
   p->mb = mb;
   p->mode = mode;
+  p->groups = groups;
+  p->args.groups = groups;
+  p->args.cand_ld = groups * mb;
   p->args.n_tiles = (N + kTileN - 1) / kTileN;
   p->args.k_blocks = K / kTileK;
   p->args.N = N;

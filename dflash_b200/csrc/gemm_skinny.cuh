@@ -7,7 +7,7 @@
 // activation rows are the UMMA "B" operand (N=MB), and the fp32 accumulator D[128 x MB] lives in
 // TMEM. One elected thread issues tcgen05.mma; one elected thread issues TMA; four warps drain TMEM.
 //
-// Work split ("stream-K"): the (n-tile, k-block) grid is flattened n-major and cut into gridDim.x
+// Work split ("stream-K"): the (n-tile, k-block) grid is flattened n-major and cut into gridDim.y
 // equal contiguous unit ranges, so every CTA streams the same number of bytes regardless of N/128.
 // A CTA that ends inside a tile writes an fp32 partial into slot (cta - first_cta_of_tile); the
 // consumer kernel sums the slots in slot order (deterministic, no atomics).
@@ -45,8 +45,8 @@ struct GemmArgs {
   int ws_rows;
   long long ws_ld;
   // kModeArgmax
-  float* cand_val;            // [gridDim.x][MB]
-  int* cand_idx;              // [gridDim.x][MB]
+  float* cand_val;            // [ranges][cand_ld]
+  int* cand_idx;              // [ranges][cand_ld]
   __nv_bfloat16* logits;      // optional [m_valid][logits_ld] (bf16-rounded), may be null
   long long logits_ld;
   // Pre-wait L2 prefetch: while this (PDL-launched) kernel waits for its predecessor, the four idle
@@ -57,6 +57,11 @@ struct GemmArgs {
   int w_rows;          // rows of the weight matrix (prefetch bound)
   int pf_units;        // 0 = off
   int late_w;          // experiment: issue the first weight tiles only after griddepcontrol.wait
+  // Column groups (wide batches): the activation rows are cut into `groups` slabs of MB rows; the grid is
+  // (groups, ranges) with the group index fastest, so the `groups` CTAs that stream one weight range are
+  // launched side by side and share it through L2 (HBM sees every weight byte once per step).
+  int groups;          // >= 1
+  int cand_ld;         // kModeArgmax: row pitch of cand_val/cand_idx (= groups * MB)
 };
 
 // The CTA that owns flat unit x when T units are cut into G ranges [floor(g*T/G), floor((g+1)*T/G)).
@@ -122,14 +127,17 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   const long long T = static_cast<long long>(a.n_tiles) * a.k_blocks;
-  const long long G = gridDim.x;
+  const long long G = gridDim.y;           // weight ranges
+  const int cta = blockIdx.y;              // this CTA's weight range
+  const int m0 = blockIdx.x * MB;          // first activation row of this CTA's column group
+  const int mv = a.m_valid - m0;           // valid rows in the group (may exceed MB)
   long long u0, u1;
   if (MODE == kModeArgmax) {  // whole tiles only
-    u0 = (blockIdx.x * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
-    u1 = ((blockIdx.x + 1) * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
+    u0 = (cta * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
+    u1 = ((cta + 1) * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
   } else {
-    u0 = unit_begin(blockIdx.x, T, G);
-    u1 = unit_begin(blockIdx.x + 1, T, G);
+    u0 = unit_begin(cta, T, G);
+    u1 = unit_begin(cta + 1, T, G);
   }
 
   if (threadIdx.x == 0) {
@@ -162,7 +170,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint64_t polW = l2_policy_evict_first();
+      // one group: every weight byte is read once -> evict first; several groups re-read it from L2
+      const uint64_t polW = gridDim.x == 1 ? l2_policy_evict_first() : l2_policy_evict_normal();
       const uint64_t polX = l2_policy_evict_last();
       const long long n_units = u1 - u0;
       const int npre = n_units < S ? static_cast<int>(n_units) : S;
@@ -179,7 +188,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       pdl_wait();
       for (int i = 0; i < npre; ++i) {
         const int kb = static_cast<int>((u0 + i) % a.k_blocks);
-        tma_load_2d(sX + i * Cfg::kXBytes, &tmX, &full[i], kb * kTileK, a.x_row0, polX);
+        tma_load_2d(sX + i * Cfg::kXBytes, &tmX, &full[i], kb * kTileK, a.x_row0 + m0, polX);
       }
       int stage = npre % S;
       uint32_t phase = (npre == S) ? 1u : 0u;
@@ -190,7 +199,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
         tma_load_2d(sW + stage * Cfg::kWBytes, &tmW, &full[stage], kb * kTileK,
                     a.w_row0 + tile * kTileN, polW);
-        tma_load_2d(sX + stage * Cfg::kXBytes, &tmX, &full[stage], kb * kTileK, a.x_row0, polX);
+        tma_load_2d(sX + stage * Cfg::kXBytes, &tmX, &full[stage], kb * kTileK, a.x_row0 + m0, polX);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
@@ -280,8 +289,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       tc_fence_after();
       float* dst = nullptr;
       if (MODE == kModePartials) {
-        const int slot = static_cast<int>(blockIdx.x) - tile_first_cta(tile, a.k_blocks, T, G);
-        dst = a.ws + (static_cast<long long>(slot) * a.ws_rows) * a.ws_ld + n;
+        const int slot = cta - tile_first_cta(tile, a.k_blocks, T, G);
+        dst = a.ws + (static_cast<long long>(slot) * a.ws_rows + m0) * a.ws_ld + n;
       }
 #pragma unroll
       for (int c = 0; c < MB / 16; ++c) {
@@ -298,7 +307,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int m = c * 16 + j;
-              if (m < a.m_valid) dst[static_cast<long long>(m) * a.ws_ld] = v[j];
+              if (m < mv) dst[static_cast<long long>(m) * a.ws_ld] = v[j];
             }
           }
         } else if (kRegBest) {
@@ -308,8 +317,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
               const int m = c * 16 + j;
               const float r = bf16_round(v[j]);
               if (r > best_v[kRegBest ? m : 0]) { best_v[kRegBest ? m : 0] = r; best_i[kRegBest ? m : 0] = n; }
-              if (a.logits != nullptr && m < a.m_valid)
-                a.logits[static_cast<long long>(m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
+              if (a.logits != nullptr && m < mv)
+                a.logits[static_cast<long long>(m0 + m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
             }
           }
         } else {
@@ -319,8 +328,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             const int m = c * 16 + j;
             float bv = (n < a.N) ? bf16_round(v[j]) : -INFINITY;
             int bi = n;
-            if (a.logits != nullptr && n < a.N && m < a.m_valid)
-              a.logits[static_cast<long long>(m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
+            if (a.logits != nullptr && n < a.N && m < mv)
+              a.logits[static_cast<long long>(m0 + m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
               const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -358,8 +367,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
       }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      if (threadIdx.x < MB) {
-        const int j = threadIdx.x;
+      for (int j = threadIdx.x; j < MB; j += 128) {
         float bv = red_v[j];
         int bi = red_i[j];
         for (int w = 1; w < 4; ++w) {
@@ -367,8 +375,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           const int oi = red_i[w * MB + j];
           if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        a.cand_val[static_cast<long long>(blockIdx.x) * MB + j] = bv;
-        a.cand_idx[static_cast<long long>(blockIdx.x) * MB + j] = bi;
+        a.cand_val[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bv;
+        a.cand_idx[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bi;
       }
     }
   }

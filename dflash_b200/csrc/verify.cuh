@@ -238,19 +238,28 @@ struct GatherArgs {
   int src_row0;      // first source row (prefill chunk offset)
   const int* ctx_len;
   __nv_bfloat16* ctx_feat;  // [R*SL][n_sel*H]
+  int pf_rows;       // > 0: prompt pass -- source rows [src_row0, src_row0 + pf_rows) -> ctx_feat rows [0, pf_rows)
 };
 
 __global__ void __launch_bounds__(256) ctx_gather_kernel(const GatherArgs a) {
   pdl_trigger();
   pdl_wait();
-  const int rr = blockIdx.x / a.SL, j = blockIdx.x % a.SL;
-  const int r = a.r0 + rr;
-  if (j >= a.ctx_len[r]) return;
+  int rr = blockIdx.x / a.SL, j = blockIdx.x % a.SL;
+  long long drow;
+  if (a.pf_rows > 0) {
+    rr = 0;
+    j = blockIdx.x;
+    if (j >= a.pf_rows) return;
+    drow = j;
+  } else {
+    const int r = a.r0 + rr;
+    if (j >= a.ctx_len[r]) return;
+    drow = static_cast<long long>(r) * a.SL + j;
+  }
   const int sel = blockIdx.y;
   const uint4* s = reinterpret_cast<const uint4*>(
       a.src[sel] + (static_cast<long long>(rr) * a.src_rows + a.src_row0 + j) * a.H);
-  uint4* d = reinterpret_cast<uint4*>(a.ctx_feat + (static_cast<long long>(r) * a.SL + j) * a.n_sel * a.H +
-                                      static_cast<long long>(sel) * a.H);
+  uint4* d = reinterpret_cast<uint4*>(a.ctx_feat + drow * a.n_sel * a.H + static_cast<long long>(sel) * a.H);
   for (int i = threadIdx.x; i < a.H / 8; i += 256) d[i] = s[i];
 }
 

@@ -46,7 +46,7 @@ BUFFERS = [
     ("output_ids", torch.int64), ("start", torch.int32), ("ctx_len", torch.int32), ("done", torch.int32),
     ("n_cycles", torch.int32), ("blk_len", torch.int32), ("max_len", torch.int32), ("acc_hist", torch.int32),
     ("rng_step", torch.int64), ("draft_logits", torch.bfloat16), ("mega_gemms", torch.uint8),
-    ("mega_phases", torch.uint8), ("mega_sync", torch.int64),
+    ("mega_phases", torch.uint8), ("mega_sync", torch.int64), ("pf_feat", torch.bfloat16), ("pf_a", torch.bfloat16),
 ]
 
 
@@ -63,6 +63,8 @@ def _declare(lib):
     lib.dflash_engine_buffer.argtypes = [c_void_p, c_int, POINTER(c_void_p), POINTER(c_size_t)]
     lib.dflash_prefill_context.restype = c_int
     lib.dflash_prefill_context.argtypes = [c_void_p, c_int, POINTER(c_void_p), c_int, c_void_p]
+    lib.dflash_prefill_context_at.restype = c_int
+    lib.dflash_prefill_context_at.argtypes = [c_void_p, c_int, POINTER(c_void_p), c_int, c_int, c_void_p]
     lib.dflash_draft_step.restype = c_int
     lib.dflash_draft_step.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     lib.dflash_verify_step.restype = c_int
@@ -122,7 +124,7 @@ class PackedDraftWeights:
 
 
 class DraftEngine:
-    """One GPU's draft+verify engine for `max_requests` request streams (ABI v1: 1 or 2)."""
+    """One GPU's draft+verify engine for `max_requests` request streams (a power of two, 1..64)."""
 
     def __init__(self, draft, embed_weight: torch.Tensor, lm_head_weight: torch.Tensor, *, max_seq: int,
                  out_len: int, max_requests: int = 1, block_size: Optional[int] = None, use_pdl: bool = True,
@@ -235,13 +237,15 @@ class DraftEngine:
         self.buf["blk_len"][r] = self.block_size
         self.buf["max_len"][r] = P + max_new_tokens
 
-    def prefill_context(self, r: int, hidden: Sequence[torch.Tensor]):
-        """hidden[s]: [P, H] bf16 rows of the selected target layers for the prompt."""
+    def prefill_context(self, r: int, hidden: Sequence[torch.Tensor], pos0: int = 0):
+        """hidden[s]: [P, H] bf16 rows of the selected target layers; they become the context at cache positions
+        [pos0, pos0 + P) of request r (pos0 = 0: the prompt)."""
         assert len(hidden) == self.n_sel
         hs = [h.contiguous() for h in hidden]
         P = hs[0].shape[0]
         arr = (c_void_p * self.n_sel)(*[h.data_ptr() for h in hs])
-        _lib.check(self.lib.dflash_prefill_context(self.handle, r, arr, P, _stream()), "dflash_prefill_context")
+        _lib.check(self.lib.dflash_prefill_context_at(self.handle, r, arr, P, int(pos0), _stream()),
+                   "dflash_prefill_context_at")
         self._keep = hs
 
     def draft_step(self, noise_embedding: Optional[torch.Tensor] = None, lm_head: bool = True):

@@ -19,7 +19,7 @@ from transformers.models.qwen3.modeling_qwen3 import (Qwen3Config, Qwen3MLP, Qwe
 
 from . import _lib
 from .engine import DraftEngine
-from .utils import build_target_layer_ids, sample, select_context_states
+from .utils import ContextTap, build_target_layer_ids, sample
 
 
 class Qwen3DFlashAttention(nn.Module):
@@ -151,8 +151,7 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         full = (c // e.SL) * e.SL if c > e.SL else 0
         if full:  # whole SL-row chunks go through the context-only pass
             parts = [th[:full, s * H:(s + 1) * H].contiguous() for s in range(nsel)]
-            e.buf["start"][0] = cache_len  # prefill writes rows at [cache_len, cache_len + full)
-            self._prefill_at(e, parts, cache_len)
+            e.prefill_context(0, parts, pos0=cache_len)  # rows land at [cache_len, cache_len + full)
         rem = c - full
         e.buf["ctx_feat"].view(e.R * e.SL, nsel * H)[:rem] = th[full:]
         e.buf["start"][0] = start
@@ -164,12 +163,6 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         if past_key_values is not None:
             past_key_values.length = start + q_len
         return e.hn[:q_len].clone().unsqueeze(0).to(noise_embedding.dtype)
-
-    @staticmethod
-    def _prefill_at(e: DraftEngine, parts, offset: int):
-        if offset != 0:
-            raise NotImplementedError("context chunks longer than the block rows are only supported from position 0")
-        e.prefill_context(0, parts)
 
     # ------------------------------------------------------------------------------------------
     @torch.inference_mode()
@@ -209,16 +202,21 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
                 cap = max(1024, 1 << (max_length + bs - 1).bit_length())
                 gt = GraphedVerifyTarget(target, bs, cap, self.target_layer_ids, e.buf["start"], e.block_ids)
                 self._graphed_target, self._graphed_target_key = gt, key
-            out = gt.prefill(input_ids)
+            logits0, hidden0 = gt.prefill(input_ids)
         else:
+            # the selected residual streams come from forward hooks (ContextTap), not output_hidden_states=True:
+            # same tensors, without the target keeping all L + 1 of them
             cache_t = DynamicCache()
-            out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
-                         logits_to_keep=1, output_hidden_states=True)
-        first = sample(out.logits, temperature, seed=seed ^ 0x5DEECE66D)
+            tap = ContextTap(target, self.target_layer_ids)
+            with tap:
+                out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
+                             logits_to_keep=1)
+            logits0, hidden0 = out.logits, list(tap.states)
+        first = sample(logits0, temperature, seed=seed ^ 0x5DEECE66D)
         e.reset_request(0, input_ids[0], first.view(-1)[0], max_new_tokens)
         if clamp_tail:
             e.buf["blk_len"][0] = min(bs, max_new_tokens)
-        e.prefill_context(0, [h[0] for h in select_context_states(out.hidden_states, self.target_layer_ids)])
+        e.prefill_context(0, [h[0] for h in hidden0])
         stop_t = None
         if stop_token_ids is not None and len(stop_token_ids) > 0:
             stop_t = torch.tensor(list(stop_token_ids), dtype=torch.int64, device=dev)
@@ -250,12 +248,13 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
             eff = min(bs, max_length - start) if clamp_tail else bs
             e.draft_step_graphed() if eff > 1 else None
             block = e.block_ids[:, :eff]
-            out = target(block, position_ids=position_ids[:, start:start + eff], past_key_values=cache_t,
-                         use_cache=True, output_hidden_states=True)
+            with tap:
+                out = target(block, position_ids=position_ids[:, start:start + eff], past_key_values=cache_t,
+                             use_cache=True)
             logits = out.logits[0]
             if logits.dtype != torch.bfloat16:
                 logits = logits.to(torch.bfloat16)
-            hidden = [h[0].contiguous() for h in select_context_states(out.hidden_states, self.target_layer_ids)]
+            hidden = [h[0].contiguous() for h in tap.states]
             if eff < bs:  # tail-clamped block: pad the rows the kernels index to the block stride
                 logits = torch.nn.functional.pad(logits, (0, 0, 0, bs - eff))
                 hidden = [torch.nn.functional.pad(h, (0, 0, 0, bs - eff)) for h in hidden]

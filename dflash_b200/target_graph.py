@@ -14,6 +14,8 @@ from typing import List, Sequence
 import torch
 from transformers import StaticCache
 
+from .utils import ContextTap
+
 
 class GraphedVerifyTarget:
     def __init__(self, target, block_size: int, max_cache_len: int, layer_ids: Sequence[int],
@@ -42,8 +44,9 @@ class GraphedVerifyTarget:
             if getattr(layer, "is_initialized", False):
                 layer.cumulative_length.zero_()
         pos = torch.arange(P, device=self.device).unsqueeze(0)
-        return self.target(input_ids, position_ids=pos, past_key_values=self.cache, use_cache=True, logits_to_keep=1,
-                           output_hidden_states=True)
+        with ContextTap(self.target, self.layer_ids) as tap:
+            out = self.target(input_ids, position_ids=pos, past_key_values=self.cache, use_cache=True, logits_to_keep=1)
+        return out.logits, list(tap.states)
 
     # -- one verify forward over the engine's current block -------------------------------------------
     def _forward(self):
@@ -51,9 +54,9 @@ class GraphedVerifyTarget:
         self.pos.copy_(self._arange + start)
         for layer in self.cache.layers:  # == past_key_values_target.crop(start): a length write
             layer.cumulative_length.copy_(start.view(layer.cumulative_length.shape).to(layer.cumulative_length.dtype))
-        out = self.target(self.block_ids, position_ids=self.pos, past_key_values=self.cache, use_cache=True,
-                          output_hidden_states=True)
-        return out.logits, [out.hidden_states[i + 1] for i in self.layer_ids]
+        with ContextTap(self.target, self.layer_ids) as tap:  # hooks fire during capture: their outputs are static
+            out = self.target(self.block_ids, position_ids=self.pos, past_key_values=self.cache, use_cache=True)
+        return out.logits, list(tap.states)
 
     def capture(self):
         torch.cuda.synchronize(self.device)

@@ -26,6 +26,45 @@ def select_context_states(hidden_states: Sequence[torch.Tensor], layer_ids: Opti
     return [hidden_states[i + 1] for i in layer_ids]
 
 
+class ContextTap:
+    """Forward hooks on the selected target decoder layers. `hidden_states[id + 1]` of a HF
+    causal LM is the output of decoder layer `id` (entry 0 is the embedding output; only the LAST entry is
+    post-norm, and `build_target_layer_ids` never selects it), so hooking those layers yields the same tensors
+    `output_hidden_states=True` would, without the model keeping all L + 1 residual streams alive. The target
+    module's arithmetic is untouched.
+
+        with ContextTap(target, ids) as tap:
+            out = target(input_ids, ...)          # no output_hidden_states
+        hs = tap.states                           # == [out.hidden_states[i + 1] for i in ids]
+    """
+
+    def __init__(self, target, layer_ids: Sequence[int]):
+        layers = target.model.layers
+        n = len(layers)
+        for i in layer_ids:
+            if not 0 <= i < n - 1:
+                raise ValueError(f"target layer id {i} is not a raw residual-stream output of a {n}-layer target")
+        self.layer_ids = list(layer_ids)
+        self._layers = [layers[i] for i in self.layer_ids]
+        self.states: List[Optional[torch.Tensor]] = [None] * len(self.layer_ids)
+        self._handles = []
+
+    def _hook(self, slot):
+        def fn(_module, _args, output):
+            self.states[slot] = output[0] if isinstance(output, (tuple, list)) else output
+        return fn
+
+    def __enter__(self):
+        self._handles = [m.register_forward_hook(self._hook(s)) for s, m in enumerate(self._layers)]
+        return self
+
+    def __exit__(self, *exc):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+        return False
+
+
 def extract_context_feature(hidden_states: Sequence[torch.Tensor], layer_ids: Optional[Sequence[int]]) -> torch.Tensor:
     """Same result as the reference (model/utils.py:16-25); kept for callers that want the tensor."""
     return torch.cat(select_context_states(hidden_states, layer_ids), dim=-1)

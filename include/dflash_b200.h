@@ -47,7 +47,9 @@ typedef struct dflash_config {
   int vocab;            /* rows of the target's lm_head / embed_tokens */
   int n_sel;            /* len(target_layer_ids) */
   int block_size;       /* slots per block (2..32); slot 0 is the last committed token */
-  int max_requests;     /* request streams resident in this engine: 1, 2, 4 or 8 (2*R*SL <= 256 rows) */
+  int max_requests;     /* request streams resident in this engine: a power of two, 1..64. Up to 256 activation
+                           rows ride on one UMMA; wider batches run as column groups of 256 rows inside the same
+                           launch (the groups of one weight range share it through L2) */
   int max_seq;          /* positions per request in the static draft KV cache */
   int out_len;          /* row length of output_ids (>= prompt + max_new_tokens + block_size) */
   int hist_len;         /* acceptance-length history entries per request */
@@ -121,6 +123,8 @@ enum dflash_buffer_id {
   DFLASH_BUF_MEGA_GEMMS,   /* persistent step kernel: GEMM table (TMA descriptors) */
   DFLASH_BUF_MEGA_PHASES,  /* persistent step kernel: phase table */
   DFLASH_BUF_MEGA_SYNC,    /* uint64: [0] steps done, [1] error code, [8..] per-phase arrival counters */
+  DFLASH_BUF_PF_FEAT,      /* bf16 [256, n_sel*hidden] prompt pass: gathered target features */
+  DFLASH_BUF_PF_A,         /* bf16 [256, hidden] prompt pass: hidden_norm(fc(features)) */
   DFLASH_BUF_COUNT
 };
 
@@ -140,10 +144,18 @@ int dflash_engine_buffer(const dflash_engine_t* e, int buffer_id, void** ptr_out
 
 /* Prompt context for request r: P rows of each selected target hidden state
  * (hidden_host[s] -> device [P, hidden] bf16) are projected (fc + hidden_norm) and their per-layer
- * K/V written to cache positions [0, P). Sets start[r] = P, ctx_len[r] = 0.
+ * K/V written to cache positions [0, P), in passes of up to 256 rows (M = P GEMMs: the weights are
+ * streamed once per 256 prompt rows). Sets start[r] = P, ctx_len[r] = 0. Other requests of the engine
+ * are not disturbed (the pass has its own feature / activation buffers).
  * Replaces cycle 0 of model/dflash.py:229,238-246 (c = P) and the fc/hidden_norm/k_proj/v_proj/
  * k_norm/RoPE call sites at :73-82,177. */
 int dflash_prefill_context(dflash_engine_t* e, int r, const void* const* hidden_host, int P, void* stream);
+
+/* Same, for n_rows context rows that continue an existing cache: positions [pos0, pos0 + n_rows)
+ * (a forward(target_hidden=...) call whose context is longer than one block: benchmark.py:122-129).
+ * Sets start[r] = pos0 + n_rows, ctx_len[r] = 0. */
+int dflash_prefill_context_at(dflash_engine_t* e, int r, const void* const* hidden_host, int n_rows, int pos0,
+                              void* stream);
 
 /* One draft step for all requests: embed(block_ids) -> ctx injection of the pending context rows
  * -> n_layers x (QKV, attention over [ctx | block], O, SwiGLU MLP) -> norm -> lm_head + argmax.
@@ -183,8 +195,9 @@ int dflash_sample(const void* logits, long long logits_ld, int rows, int vocab, 
 
 /* out[m, n] = sum_k X[x_row0+m, k] * W[w_row0+n, k]   (fp32 out; bf16 in; nn.Linear layout)
  * Replaces torch.nn.Linear on the draft path (model/dflash.py:70-76,101,177; Qwen3MLP via :143).
- * mb = padded row count fed to the tensor core (16/32/64/128/256), m_valid <= mb rows are written.
- * ws: fp32 scratch [dflash_gemm_max_slots(N,K,grid)][ws_rows][ws_ld] for the split-K partials. */
+ * mb = activation rows per tensor-core instruction (16/32/64/128/256); m_valid rows are written. m_valid > mb
+ * runs ceil(m_valid/mb) column groups in one launch over grid/groups weight ranges (X must hold groups*mb rows).
+ * ws: fp32 scratch [dflash_gemm_max_slots(N,K,grid/groups)][ws_rows >= groups*mb][ws_ld] for the split-K partials. */
 int dflash_gemm_max_slots(int N, int K, int grid);
 int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K, const void* X,
                        int x_rows_total, int x_row0, int mb, int m_valid, float* ws, int ws_rows,
@@ -194,7 +207,7 @@ int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K
 /* tokens_out[m] = argmax_n bf16(sum_k X[x_row0+m,k] * W[n,k]), ties -> lowest n; optionally also
  * writes the bf16 logits. Replaces target.lm_head(...) + sample(draft_logits)
  * (model/dflash.py:238-247, model/utils.py:27-29) without materialising the logits.
- * cand_val/cand_idx: scratch [grid][mb]. */
+ * cand_val/cand_idx: scratch [grid][groups*mb]. */
 int dflash_gemm_argmax(const void* W, int w_rows_total, int N, int K, const void* X, int x_rows_total,
                        int x_row0, int mb, int m_valid, float* cand_val, int* cand_idx, void* logits,
                        long long logits_ld, long long* tokens_out, int grid, int use_pdl, void* stream);

@@ -137,3 +137,28 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_context_tap_equals_output_hidden_states():
+    """forward hooks on the selected target layers give exactly hidden_states[id + 1]."""
+    import torch
+    from transformers import DynamicCache
+    from dflash_b200 import ContextTap, build_target_layer_ids
+    from tests.tiny_models import TINY, target_config, seeded_fill_
+    from transformers import Qwen3ForCausalLM
+    target = Qwen3ForCausalLM(target_config()).eval()
+    seeded_fill_(target, 5)
+    ids = build_target_layer_ids(TINY["target_layers"], TINY["draft_layers"])
+    x = torch.randint(0, TINY["vocab"] - 1, (1, 19), generator=torch.Generator().manual_seed(2))
+    with torch.inference_mode():
+        ref = target(x, output_hidden_states=True, past_key_values=DynamicCache(), use_cache=True)
+        n_hooks = [len(m._forward_hooks) for m in target.model.layers]  # transformers installs its own on first use
+        with ContextTap(target, ids) as tap:
+            out = target(x, past_key_values=DynamicCache(), use_cache=True)
+    assert out.hidden_states is None
+    assert torch.equal(out.logits, ref.logits)
+    for s, i in zip(tap.states, ids):
+        assert torch.equal(s, ref.hidden_states[i + 1])
+    assert [len(m._forward_hooks) for m in target.model.layers] == n_hooks  # our hooks are removed on exit
+    with pytest.raises(ValueError):
+        ContextTap(target, [TINY["target_layers"] - 1])  # the last entry of hidden_states is post-norm, not a layer output

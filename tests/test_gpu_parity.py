@@ -54,6 +54,52 @@ def test_gemm_skinny(N, K, mb, grid):
     assert (out - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("N,K,mb,rows", [(4096, 4096, 256, 1024), (6144, 1024, 256, 2048), (1000, 512, 128, 384),
+                                         (2048, 12288, 256, 512), (512, 2048, 16, 48)])
+def test_gemm_skinny_column_groups(N, K, mb, rows):
+    """rows > mb: the launch runs ceil(rows/mb) column groups over grid/groups weight ranges (batched engines)."""
+    dev = _cuda()
+    from dflash_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(N + K + rows)
+    grid = 148
+    groups = (rows + mb - 1) // mb
+    W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+    X = torch.randn(groups * mb, K, device=dev).to(torch.bfloat16)
+    slots = lib.dflash_gemm_max_slots(N, K, max(1, grid // groups))
+    ws = torch.zeros(slots, groups * mb, N, dtype=torch.float32, device=dev)
+    out = torch.zeros(rows, N, dtype=torch.float32, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.dflash_gemm_skinny(_ptr(W), N, 0, N, K, _ptr(X), groups * mb, 0, mb, rows, _ptr(ws), groups * mb, N,
+                                      _ptr(out), N, grid, 0, st))
+    torch.cuda.synchronize()
+    ref = X[:rows].float() @ W.float().t()
+    assert (out - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("mb,rows", [(128, 512), (256, 256), (256, 1024)])
+def test_gemm_argmax_column_groups(mb, rows):
+    dev = _cuda()
+    from dflash_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(rows)
+    V, K = 9000 + 40, 512
+    W = (torch.randn(V, K, device=dev) * 0.03).to(torch.bfloat16)
+    X = torch.randn(rows, K, device=dev).to(torch.bfloat16)
+    grid = 148
+    cv = torch.empty(grid, rows, dtype=torch.float32, device=dev)
+    ci = torch.empty(grid, rows, dtype=torch.int32, device=dev)
+    logits = torch.empty(rows, V, dtype=torch.bfloat16, device=dev)
+    toks = torch.empty(rows, dtype=torch.int64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.dflash_gemm_argmax(_ptr(W), V, V, K, _ptr(X), rows, 0, mb, rows, _ptr(cv), _ptr(ci), _ptr(logits), V,
+                                      _ptr(toks), grid, 0, st))
+    torch.cuda.synchronize()
+    ref = X.float() @ W.float().t()
+    assert _rel_err(logits, ref) < 1e-2
+    assert toks.cpu().tolist() == logits.float().cpu().argmax(-1).tolist()
+
+
 def test_gemm_argmax_matches_own_logits():
     dev = _cuda()
     from dflash_b200 import _lib
@@ -245,6 +291,39 @@ def test_forward_dropin_matches_oracle():
     draft.release_engine()
 
 
+@pytest.mark.parametrize("c0,c1", [(300, 41), (16, 270)])
+def test_forward_long_context_continues_cache(c0, c1):
+    """forward() with more context rows than one block (the prompt pass, M = c GEMMs in 256-row passes), first from
+    position 0 and then continuing a cropped cache at position c0 (benchmark.py:122-129 shapes)."""
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200 import DFlashStaticCache
+    from tests.tiny_models import TINY, draft_state_dict
+    bs = 16
+    target, draft = _tiny(bs)
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = draft_state_dict(draft)
+    g = torch.Generator().manual_seed(c0 + c1)
+    H, nsel = TINY["hidden"], len(draft.target_layer_ids)
+    th0 = torch.randn(1, c0, nsel * H, generator=g).to(dev, torch.bfloat16)
+    th1 = torch.randn(1, c1, nsel * H, generator=g).to(dev, torch.bfloat16)
+    noise = torch.randn(1, bs, H, generator=g).to(dev, torch.bfloat16)
+    oc = O.DraftCache()
+    r0 = O.draft_forward(sd, cfg, th0, noise, torch.arange(0, c0 + bs, device=dev).unsqueeze(0), oc)
+    oc.crop(c0)
+    r1 = O.draft_forward(sd, cfg, th1, noise, torch.arange(c0, c0 + c1 + bs, device=dev).unsqueeze(0), oc)
+    cache = DFlashStaticCache()
+    h0 = draft(target_hidden=th0, noise_embedding=noise, position_ids=torch.arange(0, c0 + bs, device=dev).unsqueeze(0),
+               past_key_values=cache, use_cache=True, is_causal=False)
+    cache.crop(c0)
+    h1 = draft(target_hidden=th1, noise_embedding=noise,
+               position_ids=torch.arange(c0, c0 + c1 + bs, device=dev).unsqueeze(0), past_key_values=cache,
+               use_cache=True, is_causal=False)
+    assert cache.get_seq_length() == c0 + c1 + bs
+    assert _rel_err(h0, r0) < REL_TOL and _rel_err(h1, r1) < REL_TOL, (_rel_err(h0, r0), _rel_err(h1, r1))
+    draft.release_engine()
+
+
 @pytest.mark.parametrize("temperature", [0.0, 1.0])
 def test_spec_generate_dropin_is_lossless(temperature):
     """Product spec_generate end to end with the HF target. Greedy: every generated token must be the target's
@@ -284,7 +363,8 @@ def test_spec_generate_dropin_is_lossless(temperature):
 # two request streams in one engine (ragged acceptance), block sizes 16 and 32, custom rope table
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("bs,R,rope", [(16, 2, "default"), (32, 1, "default"), (8, 2, "scaled"), (16, 4, "default"),
-                                        (16, 8, "default"), (32, 4, "default")])
+                                        (16, 8, "default"), (32, 4, "default"), (16, 16, "default"),
+                                        (8, 32, "scaled"), (16, 64, "default"), (32, 16, "default")])
 def test_engine_batched_ragged_vs_oracle(bs, R, rope):
     dev = _cuda()
     from oracle import dflash_oracle as O
@@ -300,8 +380,8 @@ def test_engine_batched_ragged_vs_oracle(bs, R, rope):
     sd = draft_state_dict(draft)
     H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
     g = torch.Generator(device=dev).manual_seed(5)
-    P = [23, 40, 17, 31, 52, 9, 44, 28][:R]
-    n_new = 64
+    P = [[23, 40, 17, 31, 52, 9, 44, 28][r % 8] + r // 8 for r in range(R)]
+    n_new = max(64, 5 * bs + 8)  # five cycles never reach max_length (a finished request is frozen on the device)
     eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=max(P) + n_new + 3 * bs,
                       out_len=max(P) + n_new + 2 * bs, max_requests=R, block_size=bs, keep_draft_logits=True)
     caches = [O.DraftCache() for _ in range(R)]

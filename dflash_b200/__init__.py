@@ -19,6 +19,12 @@ def __getattr__(name):
                 "ContextTap"):
         from . import utils
         return getattr(utils, name)
+    if name in ("dflash_generate", "cuda_time"):
+        from . import generate
+        return getattr(generate, name)
+    if name in ("spec_generate_batch",):
+        from . import batched
+        return getattr(batched, name)
     if name in ("DraftEngine",):
         from . import engine
         return getattr(engine, name)

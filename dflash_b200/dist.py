@@ -77,6 +77,35 @@ def gather_streams(n_out: torch.Tensor, tokens: torch.Tensor, taus: torch.Tensor
     return outs[0], outs[1], outs[2]
 
 
+def generate_data_parallel(local_generate, prompts: Sequence[torch.Tensor], max_new_tokens: int, device,
+                           max_cycles: int = 0):
+    """Request-level DP over the ranks of the job (benchmark.py:445,539-551 without the pickling).
+
+    Every rank passes the SAME global prompt list. `local_generate(my_prompts)` decodes this rank's share
+    (round-robin: `shard_indices`) and returns `(outputs, taus)`: `outputs[j]` = LongTensor[1, P_j + n_j] and
+    `taus[j]` = acceptance lengths per cycle -- `DFlashDraftModel.spec_generate_batch` partially applied is the
+    intended callee. One all-gather of fixed-shape integer tensors then gives every rank all results:
+    returns `(n_out int32 [N], tokens int64 [N, max_new_tokens], taus int32 [N, max_cycles])` in prompt order."""
+    n_items = len(prompts)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = world_size()
+    mine = shard_indices(n_items, rank, world)
+    outs, taus = local_generate([prompts[i] for i in mine]) if mine else ([], [])
+    max_cycles = int(max_cycles) if max_cycles > 0 else max_new_tokens
+    n_out = torch.zeros(len(mine), dtype=torch.int32, device=device)
+    tokens = torch.zeros(len(mine), max_new_tokens, dtype=torch.int64, device=device)
+    tau_t = torch.zeros(len(mine), max_cycles, dtype=torch.int32, device=device)
+    for j, i in enumerate(mine):
+        P = int(prompts[i].shape[1])
+        gen = outs[j][0, P:]
+        n_out[j] = gen.numel()
+        tokens[j, : gen.numel()] = gen.to(device)
+        t = list(taus[j])[:max_cycles]
+        if t:
+            tau_t[j, : len(t)] = torch.tensor(t, dtype=torch.int32)
+    return gather_streams(n_out, tokens, tau_t, n_items)
+
+
 def barrier():
     if dist.is_initialized():
         dist.barrier()

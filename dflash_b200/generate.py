@@ -1,0 +1,174 @@
+"""`dflash_generate`: the reference's instrumented decode loop (benchmark.py:44-272) over the CUDA engine.
+
+Same arguments and the same result record (`output_ids`, `num_input_tokens`, `num_output_tokens`,
+`time_to_first_token`, `time_per_output_token`, `acceptance_lengths`, `cycle_trace`, `profile_summary`), the same
+tail clamp (`effective_block_size = min(block_size, remaining)`, benchmark.py:104-105), the same `block_size == 1`
+autoregressive baseline, and with `collect_profile=True` the same three CUDA-event spans per cycle (draft / target /
+cycle) and the same summary keys, so numbers from this loop line up with the reference's `--collect-profile` output.
+`draft_steps > 1` (the reference's refinement experiment, which recomputes the block without a cache) is not part
+of the hot path and raises.
+"""
+from __future__ import annotations
+
+import time
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+from transformers import DynamicCache
+
+from .utils import ContextTap, sample
+
+
+def cuda_time() -> float:
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
+@torch.inference_mode()
+def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, max_new_tokens: int, block_size: int,
+                    stop_token_ids: Optional[List[int]], temperature: float = 0.0, collect_profile: bool = False,
+                    draft_steps: int = 1, seed: Optional[int] = None) -> SimpleNamespace:
+    if draft_steps != 1:
+        raise NotImplementedError("draft_steps > 1 (cache-less block refinement, benchmark.py:114-142) is a research "
+                                  "variant outside the draft-and-verify hot path")
+    if input_ids.shape[0] != 1:
+        raise RuntimeError("dflash_generate: batch size 1 (benchmark.py:58-66)")
+    dev = target.device
+    P = input_ids.shape[1]
+    max_length = P + max_new_tokens
+    bs = int(block_size)
+    if seed is None:
+        seed = int(torch.randint(0, 2**62, (1,)).item()) if temperature >= 1e-5 else 0
+    position_ids = torch.arange(max_length + bs, device=dev).unsqueeze(0)
+    cache_t = DynamicCache()
+    stop_t = None
+    if stop_token_ids is not None and len(stop_token_ids) > 0:
+        stop_t = torch.tensor(list(stop_token_ids), dtype=torch.int64, device=dev)
+
+    eng = None
+    tap = ContextTap(target, model.target_layer_ids) if bs > 1 else None
+    old_bs = model.block_size
+    prefill_start = cuda_time()
+    if bs > 1:
+        if int(mask_token_id) != int(model.mask_token_id):
+            raise ValueError("mask_token_id differs from the draft's config")
+        model.block_size = bs
+        eng = model._get_engine(target.model.embed_tokens.weight, target.lm_head.weight,
+                                max_seq=max_length + 2 * bs + 1, out_len=max_length + bs + 1)
+        with tap:
+            out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
+                         logits_to_keep=1)
+        first = sample(out.logits, temperature, seed=seed ^ 0x5DEECE66D)
+        eng.reset_request(0, input_ids[0], first.view(-1)[0], max_new_tokens)
+        eng.buf["blk_len"][0] = min(bs, max_new_tokens)
+        eng.prefill_context(0, [h[0] for h in tap.states])
+    else:
+        out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
+                     logits_to_keep=1)
+        ar_ids = torch.full((1, max_length + 1), int(mask_token_id), dtype=torch.long, device=dev)
+        ar_ids[:, :P] = input_ids
+        ar_ids[:, P] = sample(out.logits, temperature, seed=seed ^ 0x5DEECE66D).view(-1)[0]
+    time_to_first_token = cuda_time() - prefill_start
+
+    decode_start = cuda_time()
+    start = P
+    acceptance_lengths: List[int] = []
+    cycle_trace = []
+    draft_prefill = True
+    state = torch.empty(2, dtype=torch.int32).pin_memory()
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    try:
+        while start < max_length:
+            cyc_ev = (ev(), ev()) if collect_profile else None
+            if collect_profile:
+                cyc_ev[0].record()
+            eff = min(bs, max_length - start)
+            draft_ev = None
+            if eff > 1:
+                if collect_profile:
+                    draft_ev = (ev(), ev())
+                    draft_ev[0].record()
+                eng.draft_step_graphed()  # embed -> ctx injection -> layers -> lm_head + argmax (benchmark.py:110-140)
+                if collect_profile:
+                    draft_ev[1].record()
+                if draft_prefill:
+                    draft_prefill = False
+                    decode_start = cuda_time()
+            tgt_ev = (ev(), ev()) if collect_profile else None
+            if collect_profile:
+                tgt_ev[0].record()
+            if bs > 1:
+                with tap:
+                    out = target(eng.block_ids[:, :eff], position_ids=position_ids[:, start:start + eff],
+                                 past_key_values=cache_t, use_cache=True)
+            else:
+                out = target(ar_ids[:, start:start + 1], position_ids=position_ids[:, start:start + 1],
+                             past_key_values=cache_t, use_cache=True)
+            if collect_profile:
+                tgt_ev[1].record()
+            if bs > 1:
+                logits = out.logits[0]
+                if logits.dtype != torch.bfloat16:
+                    logits = logits.to(torch.bfloat16)
+                hidden = [h[0].contiguous() for h in tap.states]
+                if eff < bs:
+                    logits = torch.nn.functional.pad(logits, (0, 0, 0, bs - eff))
+                    hidden = [torch.nn.functional.pad(h, (0, 0, 0, bs - eff)) for h in hidden]
+                eng.verify_step(logits, hidden, temperature=temperature, seed=seed, stop_ids=stop_t, clamp_tail=True)
+                state[0:1].copy_(eng.buf["start"][0:1], non_blocking=True)
+                state[1:2].copy_(eng.buf["done"][0:1], non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                tau = int(state[0]) - start
+                done = bool(int(state[1]))
+            else:
+                tok = sample(out.logits, temperature, seed=seed + start).view(-1)[0]
+                ar_ids[:, start + 1] = tok
+                tau = 1
+                done = stop_t is not None and bool(torch.isin(tok, stop_t).item())
+            acceptance_lengths.append(tau)
+            if collect_profile:
+                cyc_ev[1].record()
+                cycle_trace.append({"cycle_idx": len(acceptance_lengths) - 1, "generated_tokens_before": start - P,
+                                    "effective_block_size": int(eff), "tau": int(tau),
+                                    "acceptance_ratio": float(tau / max(1, eff)),
+                                    "_events": {"draft": draft_ev, "target": tgt_ev, "cycle": cyc_ev}})
+            start += tau
+            cache_t.crop(start)
+            if done and start < max_length:
+                break
+        if bs > 1:
+            output_ids = eng.output_ids[0:1, :max_length].clone()
+        else:
+            output_ids = ar_ids[:, :max_length].clone()
+    finally:
+        model.block_size = old_bs
+    output_ids = output_ids[:, output_ids[0] != int(mask_token_id)]
+    if stop_t is not None:
+        idx = torch.isin(output_ids[0][P:], stop_t).nonzero(as_tuple=True)[0]
+        if idx.numel() > 0:
+            output_ids = output_ids[:, : P + idx[0] + 1]
+    num_output_tokens = output_ids.shape[1] - P
+    total_decode_time = cuda_time() - decode_start
+    time_per_output_token = total_decode_time / max(1, num_output_tokens)
+
+    profile_summary = None
+    if collect_profile:
+        torch.cuda.synchronize()
+        tot = {"draft": 0.0, "target": 0.0, "cycle": 0.0}
+        for row in cycle_trace:
+            evs = row.pop("_events")
+            for k in ("draft", "target", "cycle"):
+                s = 0.0 if evs[k] is None else evs[k][0].elapsed_time(evs[k][1]) / 1000.0
+                row[f"{k}_s"] = float(s)
+                tot[k] += s
+        denom = max(1e-12, tot["draft"] + tot["target"])
+        profile_summary = {"target_prefill_s": float(time_to_first_token), "target_decode_s": float(tot["target"]),
+                           "draft_decode_s": float(tot["draft"]), "cycle_decode_s_sum": float(tot["cycle"]),
+                           "decode_wall_s": float(total_decode_time), "profiled_cycles": len(cycle_trace),
+                           "draft_share_decode": float(tot["draft"] / denom),
+                           "target_share_decode": float(tot["target"] / denom)}
+    return SimpleNamespace(output_ids=output_ids, num_input_tokens=P, num_output_tokens=num_output_tokens,
+                           time_to_first_token=time_to_first_token, time_per_output_token=time_per_output_token,
+                           acceptance_lengths=acceptance_lengths, cycle_trace=cycle_trace,
+                           profile_summary=profile_summary)

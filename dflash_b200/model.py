@@ -165,6 +165,13 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         return e.hn[:q_len].clone().unsqueeze(0).to(noise_embedding.dtype)
 
     # ------------------------------------------------------------------------------------------
+    def spec_generate_batch(self, target: nn.Module, prompts, max_new_tokens: int, stop_token_ids: Optional[List[int]],
+                            temperature: float, **kwargs):
+        """Many prompts through one engine (up to 64 request streams share the draft's weight stream); see
+        `dflash_b200/batched.py`. Returns a list of `LongTensor[1, P_i + n_i]` in prompt order."""
+        from .batched import spec_generate_batch
+        return spec_generate_batch(self, target, prompts, max_new_tokens, stop_token_ids, temperature, **kwargs)
+
     @torch.inference_mode()
     def spec_generate(self, target: nn.Module, input_ids: torch.LongTensor, max_new_tokens: int,
                       stop_token_ids: Optional[List[int]], temperature: float, *, clamp_tail: bool = False,

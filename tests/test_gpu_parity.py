@@ -364,7 +364,8 @@ def test_spec_generate_dropin_is_lossless(temperature):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("bs,R,rope", [(16, 2, "default"), (32, 1, "default"), (8, 2, "scaled"), (16, 4, "default"),
                                         (16, 8, "default"), (32, 4, "default"), (16, 16, "default"),
-                                        (8, 32, "scaled"), (16, 64, "default"), (32, 16, "default")])
+                                        (8, 32, "scaled"), (16, 64, "default"), (32, 16, "default"),
+                                        (8, 64, "default"), (32, 64, "default")])
 def test_engine_batched_ragged_vs_oracle(bs, R, rope):
     dev = _cuda()
     from oracle import dflash_oracle as O
@@ -437,6 +438,144 @@ def test_engine_batched_ragged_vs_oracle(bs, R, rope):
             blocks[r] = torch.tensor([int(post[a])] + [cfg.mask_token_id] * (bs - 1), device=dev)
             assert eng.block_ids[r].cpu().tolist() == blocks[r].cpu().tolist()
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 3 shape: 16 request streams, temperature 1.0 (posterior sampled, draft greedy: SURVEY F2)
+# ------------------------------------------------------------------------------------------------
+def test_engine_verify_temperature_batch16():
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY
+    bs, R, T = 16, 16, 1.0
+    target, draft = _tiny(bs, rigged=True)
+    H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
+    g = torch.Generator(device=dev).manual_seed(21)
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=256, out_len=256,
+                      max_requests=R, block_size=bs)
+    P = [11 + 3 * r for r in range(R)]
+    for r in range(R):
+        hs = [(torch.randn(P[r], H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        eng.reset_request(r, torch.randint(0, V - 1, (P[r],), device=dev, generator=g), 3, 100)
+        eng.prefill_context(r, hs)
+    starts = list(P)
+    for cyc in range(3):
+        eng.draft_step()
+        blocks = eng.block_ids.clone().cpu()
+        # a posterior that agrees with the draft often: peaked at the drafted token for the first slots
+        tl = torch.randn(R * bs, V, device=dev, generator=g)
+        for r in range(R):
+            for i in range((r + cyc) % bs):
+                tl[r * bs + i, int(blocks[r, i + 1])] += 14.0
+        tl = tl.to(torch.bfloat16)
+        hsel = [(torch.randn(R * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        q = torch.empty(R * bs, V, device=dev, dtype=torch.float32).exponential_(1.0, generator=g)
+        eng.verify_step(tl, hsel, temperature=T, noise=q)
+        torch.cuda.synchronize()
+        ref = (torch.softmax(tl.float() / T, dim=-1) / q).argmax(-1).view(R, bs).cpu()  # torch.multinomial's race
+        got = eng.posterior.cpu()
+        assert (got == ref).float().mean().item() >= 0.99  # fp32 rounding of p/q vs the log-domain race
+        for r in range(R):
+            a = O.acceptance_length(blocks[r].tolist(), got[r].tolist())  # decisions bit-exact given the posterior
+            assert int(eng.acc_hist[r, cyc]) == a + 1
+            out = eng.output_ids[r].cpu()
+            assert out[starts[r]:starts[r] + a + 1].tolist() == blocks[r, :a + 1].tolist()
+            assert int(out[starts[r] + a + 1]) == int(got[r, a])
+            starts[r] += a + 1
+            assert int(eng.buf["start"][r]) == starts[r] and int(eng.buf["ctx_len"][r]) == a + 1
+        assert max(int(eng.acc_hist[r, cyc]) for r in range(R)) > 4
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# batched public API: many prompts through one engine, slots refilled as requests finish
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_prompts,R,temperature,rigged", [(5, 4, 0.0, False), (16, 16, 0.0, True), (6, 2, 1.0, True),
+                                                            (9, 8, 0.0, True)])
+def test_spec_generate_batch_lossless_with_refill(n_prompts, R, temperature, rigged):
+    dev = _cuda()
+    from tests.tiny_models import TINY
+    bs = 16
+    target, draft = _tiny(bs, rigged=rigged)
+    g = torch.Generator().manual_seed(n_prompts)
+    lens = [9 + (7 * i) % 30 for i in range(n_prompts)]
+    prompts = [torch.randint(0, TINY["vocab"] - 1, (1, n), generator=g).to(dev) for n in lens]
+    n_new = 24
+    outs = draft.spec_generate_batch(target, prompts, n_new, None, temperature, max_requests=R, seed=7)
+    assert len(outs) == n_prompts
+    for i, (p, o) in enumerate(zip(prompts, outs)):
+        assert o.shape == (1, lens[i] + n_new) and o.dtype == torch.int64
+        assert torch.equal(o[:, :lens[i]], p)
+        assert sum(draft.last_batch_acceptance_lengths[i]) >= n_new
+        if temperature == 0.0:  # lossless: every token is the target's own greedy choice given the prefix
+            with torch.inference_mode():
+                logits = target(o).logits[0].float()
+            pred = logits.argmax(-1)
+            for t in range(lens[i] - 1, o.shape[1] - 1):
+                tok = o[0, t + 1].item()
+                if pred[t].item() != tok:
+                    assert _near_tie(logits[t], pred[t].item(), tok), (i, t, pred[t].item(), tok)
+    if temperature == 0.0:
+        # same prompts one at a time through spec_generate: identical acceptance bookkeeping per request
+        o1 = draft.spec_generate(target, prompts[1], n_new, None, 0.0)
+        assert o1.shape == outs[1].shape
+        # stop token, ragged: every generation ends right after its first stop token
+        stop = [int(outs[0][0, lens[0] + 5])]
+        outs2 = draft.spec_generate_batch(target, prompts, n_new, stop, 0.0, max_requests=R)
+        gen0 = outs2[0][0, lens[0]:].tolist()
+        assert gen0[-1] == stop[0] and stop[0] not in gen0[:-1] and len(gen0) <= 6
+        for i, o in enumerate(outs2):
+            gen = o[0, lens[i]:].tolist()
+            assert stop[0] not in gen[:-1]
+            ref_gen = outs[i][0, lens[i]:].tolist()
+            assert gen == ref_gen[:len(gen)]  # a prefix of the unconstrained generation
+        # forced-acceptance harness hook per prompt: first cycle k = 3 -> tau >= 4
+        draft.spec_generate_batch(target, prompts, n_new, None, 0.0, max_requests=R, forced_k=[[3, 0, 7, 1]] * n_prompts)
+        for i in range(n_prompts):
+            assert draft.last_batch_acceptance_lengths[i][0] >= 4
+    draft.release_engine()
+
+
+def test_dflash_generate_twin_of_benchmark_loop():
+    """benchmark.py:44-272 twin: same record, tail clamp, block_size == 1 baseline, --collect-profile spans."""
+    dev = _cuda()
+    from dflash_b200 import dflash_generate
+    from tests.tiny_models import TINY
+    bs = 16
+    target, draft = _tiny(bs, rigged=True)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 27), generator=torch.Generator().manual_seed(4)).to(dev)
+    res = dflash_generate(draft, target, prompt, draft.mask_token_id, 40, bs, None, 0.0, collect_profile=True)
+    ref = draft.spec_generate(target, prompt, 40, None, 0.0, clamp_tail=True)
+    assert torch.equal(res.output_ids, ref)
+    assert res.num_input_tokens == 27 and res.num_output_tokens == 40
+    assert res.acceptance_lengths == draft.last_acceptance_lengths and sum(res.acceptance_lengths) >= 40
+    ps = res.profile_summary
+    assert set(ps) == {"target_prefill_s", "target_decode_s", "draft_decode_s", "cycle_decode_s_sum", "decode_wall_s",
+                       "profiled_cycles", "draft_share_decode", "target_share_decode"}
+    assert ps["profiled_cycles"] == len(res.cycle_trace) == len(res.acceptance_lengths)
+    assert abs(ps["draft_share_decode"] + ps["target_share_decode"] - 1.0) < 1e-6
+    for row in res.cycle_trace:
+        assert row["cycle_s"] >= row["target_s"] > 0 and row["tau"] <= row["effective_block_size"]
+    assert res.cycle_trace[-1]["effective_block_size"] <= bs
+    # block_size 1 = the autoregressive baseline: the target's own greedy decode
+    base = dflash_generate(draft, target, prompt, draft.mask_token_id, 12, 1, None, 0.0)
+    assert base.acceptance_lengths == [1] * 12 and base.output_ids.shape == (1, 39)
+    with torch.inference_mode():
+        logits = target(base.output_ids).logits[0].float()
+    pred = logits.argmax(-1)
+    for t in range(26, 38):
+        tok = base.output_ids[0, t + 1].item()
+        assert pred[t].item() == tok or _near_tie(logits[t], pred[t].item(), tok)
+    # the speculative output is the same continuation (lossless), modulo near-ties
+    n = min(base.output_ids.shape[1], res.output_ids.shape[1])
+    diff = (base.output_ids[0, :n] != res.output_ids[0, :n]).nonzero()
+    if diff.numel():
+        t = int(diff[0]) - 1
+        assert _near_tie(logits[t], base.output_ids[0, t + 1].item(), res.output_ids[0, t + 1].item())
+    with pytest.raises(NotImplementedError):
+        dflash_generate(draft, target, prompt, draft.mask_token_id, 8, bs, None, 0.0, draft_steps=2)
+    draft.release_engine()
 
 
 def test_verify_with_given_posterior_and_stop_and_clamp():

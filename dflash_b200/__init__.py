@@ -22,6 +22,9 @@ def __getattr__(name):
     if name in ("dflash_generate", "cuda_time"):
         from . import generate
         return getattr(generate, name)
+    if name in ("EwmaBlockScheduler",):
+        from . import schedule
+        return getattr(schedule, name)
     if name in ("spec_generate_batch",):
         from . import batched
         return getattr(batched, name)

@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdflash_b200.so")
+# DFLASH_LIB: another build of the same library (kernel-tuning experiments, scripts/sweep_*.sh); never a fallback
+LIB_PATH = os.environ.get("DFLASH_LIB") or os.path.join(_HERE, "libdflash_b200.so")
 
 OK = 0
 

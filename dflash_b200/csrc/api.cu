@@ -222,7 +222,7 @@ int dflash_gemm_argmax(const void* W, int w_rows_total, int N, int K, const void
   }
   GemmPlan p;
   int rc = make_gemm_plan(&p, W, w_rows_total, 0, N, K, X, x_rows_total, x_row0, mb, m_valid,
-                          kModeArgmax, grid);
+                          logits ? kModeArgmaxDump : kModeArgmax, grid);
   if (rc) return DFLASH_ERR_ARG;
   p.args.cand_val = cand_val;
   p.args.cand_idx = cand_idx;

@@ -289,7 +289,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     finish(e->d[l], mb_blk);
   }
   DFL_PLAN(make_gemm_plan(&e->lm, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
-                          kModeArgmax, e->grid));
+                          c.keep_draft_logits ? kModeArgmaxDump : kModeArgmax, e->grid));
   e->lm.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
   e->lm.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
   e->lm.args.logits = c.keep_draft_logits ? e->buf<__nv_bfloat16>(DFLASH_BUF_DRAFT_LOGITS) : nullptr;
@@ -326,6 +326,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     cudaFuncSetAttribute(gemm_skinny_kernel<32, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(gemm_skinny_kernel<64, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(gemm_skinny_kernel<128, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(gemm_skinny_kernel<256, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(swiglu_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);

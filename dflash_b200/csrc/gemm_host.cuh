@@ -86,7 +86,7 @@ inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pd
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(p.groups, p.grid);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -98,6 +98,16 @@ inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pd
 }
 
 inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl) {
+  if (p.mode == kModeArgmaxDump) {
+    switch (p.mb) {
+      case 16: return launch_gemm_t<16, kModeArgmaxDump>(p, stream, pdl);
+      case 32: return launch_gemm_t<32, kModeArgmaxDump>(p, stream, pdl);
+      case 64: return launch_gemm_t<64, kModeArgmaxDump>(p, stream, pdl);
+      case 128: return launch_gemm_t<128, kModeArgmaxDump>(p, stream, pdl);
+      case 256: return launch_gemm_t<256, kModeArgmaxDump>(p, stream, pdl);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (p.mode == kModeArgmax) {
     switch (p.mb) {
       case 16: return launch_gemm_t<16, kModeArgmax>(p, stream, pdl);
@@ -166,11 +176,11 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   p->args.x_row0 = x_row0;
   p->args.m_valid = m_valid;
   const long long T = static_cast<long long>(p->args.n_tiles) * p->args.k_blocks;
-  if (mode != kModeArgmax && (T + 1) * grid >= (1ll << 31)) {
+  if (mode == kModePartials && (T + 1) * grid >= (1ll << 31)) {
     set_error("gemm: %lld work units x %d CTAs overflows the consumers' 32-bit slot arithmetic", T, grid);
     return -1;
   }
-  if (mode == kModeArgmax) {
+  if (mode != kModePartials) {
     p->grid = grid < p->args.n_tiles ? grid : p->args.n_tiles;
     p->max_slots = 1;
   } else {

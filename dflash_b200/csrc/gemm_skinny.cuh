@@ -26,11 +26,13 @@ namespace dfl {
 constexpr int kTileN = 128;   // weight rows per tile (UMMA M)
 constexpr int kTileK = 64;    // bf16 elements per k-block (= one 128-byte swizzle row)
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;  // warps 0-3 epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc
+constexpr int kGemmThreads = 192;  // default role layout: warps 0-3 epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc
 
 enum GemmMode : int {
   kModePartials = 0,  // write fp32 partial sums to ws[slot][m][n]
   kModeArgmax = 1,    // whole tiles per CTA; per-CTA (max, argmax) of the bf16-rounded logits
+  kModeArgmaxDump = 2,  // kModeArgmax that also stores the bf16 logits (parity tests; keeps the store addressing
+                        // out of the hot instantiation's registers)
 };
 
 struct GemmArgs {
@@ -100,14 +102,30 @@ struct GemmCfg {
   static constexpr int kStageBytes = kWBytes + kXBytes;
   // wide activation tiles (batched engines) need the whole SM to keep >= 4 stages in flight
   static constexpr int kBudget =
-      ((MODE == 1 || MB >= 64) ? DFLASH_GEMM_SMEM_KB_ARGMAX : DFLASH_GEMM_SMEM_KB_PARTIALS) * 1024;
+      ((MODE != 0 || MB >= 64) ? DFLASH_GEMM_SMEM_KB_ARGMAX : DFLASH_GEMM_SMEM_KB_PARTIALS) * 1024;
   static constexpr int kStages = kBudget / kStageBytes < 3 ? 3 : kBudget / kStageBytes;
   static constexpr int kTmemCols = (2 * MB < 32) ? 32 : 2 * MB;
+  // epilogue warps: warp w drains TMEM lane quarter w % 4. The 256-wide argmax epilogue keeps one packed running
+  // best per activation row in registers, so it splits the columns over two warp sets (128 registers each).
+  static constexpr int kEpiWarps = (MODE != 0 && MB >= 128) ? 8 : 4;
+  static constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
+  static constexpr int kColsPerThread = MB / (kEpiWarps / 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Order-preserving 16-bit key of a bf16 value (larger value <=> larger key; -0 == +0; key 0 is below every value).
+__device__ __forceinline__ uint32_t bf16_order_key(float v) {
+  uint32_t u = __float_as_uint(bf16_round(v)) >> 16;
+  if (u == 0x8000u) u = 0;
+  return (u & 0x8000u) ? (~u & 0xFFFFu) : (u | 0x8000u);
+}
+__device__ __forceinline__ float bf16_from_order_key(uint32_t k) {
+  const uint32_t u = (k & 0x8000u) ? (k & 0x7FFFu) : (~k & 0xFFFFu);
+  return __uint_as_float(u << 16);
+}
+
 template <int MB, int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(GemmCfg<MB, MODE>::kThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                    const GemmArgs a) {
   using Cfg = GemmCfg<MB, MODE>;
@@ -132,7 +150,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int m0 = blockIdx.x * MB;          // first activation row of this CTA's column group
   const int mv = a.m_valid - m0;           // valid rows in the group (may exceed MB)
   long long u0, u1;
-  if (MODE == kModeArgmax) {  // whole tiles only
+  constexpr bool kArgmax = MODE != kModePartials;
+  if (kArgmax) {  // whole tiles only
     u0 = (cta * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
     u1 = ((cta + 1) * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
   } else {
@@ -147,15 +166,16 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], Cfg::kEpiWarps * 32);
     }
     mbar_fence_init();
   }
-  if (warp == 4 && lane == 0) {
+  constexpr int kTmaWarp = Cfg::kEpiWarps, kMmaWarp = Cfg::kEpiWarps + 1;
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmX);
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tmem_relinquish();
   }
@@ -167,7 +187,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   // Let the next kernel in the stream start its own prologue / weight prefetch right away.
   pdl_trigger();
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       // one group: every weight byte is read once -> evict first; several groups re-read it from L2
@@ -203,7 +223,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileN, MB);
@@ -240,7 +260,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0..3)
+    // ------------------------------------------------------------------ epilogue (warps 0..kEpiWarps-1)
     if (a.pf_units > 0) {
       // pre-wait L2 prefetch of units [u0 + S, u0 + S + pf_units): thread t takes weight row t of each
       // unit's 128 x 128 B box, so one pass of the 128 threads covers one 16 KB unit
@@ -251,7 +271,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int tile = static_cast<int>(u / a.k_blocks);
         const int kb = static_cast<int>(u % a.k_blocks);
         const int wrow = a.w_row0 + tile * kTileN + static_cast<int>(threadIdx.x);
-        if (wrow < a.w_rows)
+        if (threadIdx.x < kTileN && wrow < a.w_rows)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;\n" ::"l"(
               wb + (static_cast<long long>(wrow) * a.w_ld + kb * kTileK) * 2));
       }
@@ -259,24 +279,21 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     pdl_wait();
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const int row_in_tile = warp * 32 + lane;
+    const int quarter = warp & 3;                       // TMEM lanes [32 * quarter, +32)
+    constexpr int kCols = Cfg::kColsPerThread;          // activation rows this thread drains per accumulator
+    const int col0 = (warp >> 2) * kCols;               // second warp set: the upper half of the columns
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int row_in_tile = quarter * 32 + lane;
+    const int epi_tid = static_cast<int>(threadIdx.x);  // epilogue warps are warps [0, kEpiWarps)
 
-    // kModeArgmax running best per activation row (this thread's weight rows only ever increase)
-    // (MB <= 32: registers; wider batches keep a per-warp running best in shared memory instead)
-    constexpr bool kRegBest = (MODE == kModeArgmax) && (MB <= 32);
-    constexpr bool kSmemBest = (MODE == kModeArgmax) && (MB > 32);
-    float best_v[kRegBest ? MB : 1];
-    int best_i[kRegBest ? MB : 1];
-    __shared__ float s_bv[kSmemBest ? 4 * MB : 1];
-    __shared__ int s_bi[kSmemBest ? 4 * MB : 1];
-    if (kRegBest) {
+    // kModeArgmax: one running best per activation row in a register, packed as
+    //   (order key of the bf16-rounded logit) << 16 | (0xFFFF - tile)
+    // so that keeping the best is ONE integer max per logit, and a tie keeps the lower tile = the lower vocab
+    // index (this thread's weight row inside the tile is fixed). Decoded and reduced over threads at the end.
+    uint32_t best[kArgmax ? kCols : 1];
+    if (kArgmax) {
 #pragma unroll
-      for (int j = 0; j < MB; ++j) { best_v[j] = -INFINITY; best_i[j] = 0x7fffffff; }
-    }
-    if (kSmemBest) {
-      for (int j = lane; j < MB; j += 32) { s_bv[warp * MB + j] = -INFINITY; s_bi[warp * MB + j] = 0x7fffffff; }
-      __syncwarp();
+      for (int j = 0; j < kCols; ++j) best[j] = 0u;
     }
 
     long long u = u0;
@@ -292,13 +309,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int slot = cta - tile_first_cta(tile, a.k_blocks, T, G);
         dst = a.ws + (static_cast<long long>(slot) * a.ws_rows + m0) * a.ws_ld + n;
       }
+      const uint32_t tile_tag = 0xFFFFu - static_cast<uint32_t>(tile);
 #pragma unroll
-      for (int c = 0; c < MB / 16; ++c) {
+      for (int c = 0; c < kCols / 16; ++c) {
         float v[16];
-        tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + c * 16), v);
+        tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + col0 + c * 16), v);
         tmem_ld_wait();
-        if (c == MB / 16 - 1) {
-          // all of this accumulator is in registers: hand the TMEM stage back to the MMA warp
+        if (c == kCols / 16 - 1) {
+          // all of this thread's share of the accumulator is in registers: hand the TMEM stage back
           tc_fence_before();
           mbar_arrive(&tempty[acc]);
         }
@@ -306,39 +324,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           if (n < a.N) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int m = c * 16 + j;
+              const int m = col0 + c * 16 + j;
               if (m < mv) dst[static_cast<long long>(m) * a.ws_ld] = v[j];
             }
           }
-        } else if (kRegBest) {
-          if (n < a.N) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int m = c * 16 + j;
-              const float r = bf16_round(v[j]);
-              if (r > best_v[kRegBest ? m : 0]) { best_v[kRegBest ? m : 0] = r; best_i[kRegBest ? m : 0] = n; }
-              if (a.logits != nullptr && m < mv)
-                a.logits[static_cast<long long>(m0 + m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
-            }
-          }
-        } else {
-          // wide batch: reduce each activation row over the warp's 32 weight rows now, merge into smem
+        } else if (n < a.N) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int m = c * 16 + j;
-            float bv = (n < a.N) ? bf16_round(v[j]) : -INFINITY;
-            int bi = n;
-            if (a.logits != nullptr && n < a.N && m < mv)
-              a.logits[static_cast<long long>(m0 + m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) {
-              const int k = kSmemBest ? warp * MB + m : 0;
-              if (bv > s_bv[k] || (bv == s_bv[k] && bi < s_bi[k])) { s_bv[k] = bv; s_bi[k] = bi; }
+            const uint32_t key = (bf16_order_key(v[j]) << 16) | tile_tag;
+            uint32_t& b = best[kArgmax ? c * 16 + j : 0];
+            b = key > b ? key : b;
+            if (MODE == kModeArgmaxDump) {
+              const int m = col0 + c * 16 + j;
+              if (m < mv) a.logits[static_cast<long long>(m0 + m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
             }
           }
         }
@@ -348,42 +346,34 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       if (acc == 0) acc_phase ^= 1u;
     }
 
-    if (MODE == kModeArgmax) {
-      // reduce over the 128 epilogue threads: max value, ties -> lowest index
-      float* red_v = kSmemBest ? s_bv : reinterpret_cast<float*>(sW);  // pipeline smem is idle by now
-      int* red_i = kSmemBest ? s_bi : reinterpret_cast<int*>(sW + 4 * MB * sizeof(float));
-      if (kRegBest) {
+    if (kArgmax) {
+      // Reduce over the 128 weight rows of the tile shape through shared memory (the pipeline stages are idle by
+      // now): keys[row][col], padded pitch so that both the row-wise writes and the column-wise reads are
+      // conflict-free. Rows are visited in ascending order with a strict compare, so among equal keys (same value,
+      // same tile) the lowest row, i.e. the lowest vocab index, wins.
+      constexpr int kPitch = MB + 1;
+      static_assert(kTileN * kPitch * 4 <= S * Cfg::kStageBytes, "argmax reduction scratch exceeds the pipeline smem");
+      uint32_t* keys = reinterpret_cast<uint32_t*>(smem);
 #pragma unroll
-        for (int j = 0; j < (kRegBest ? MB : 1); ++j) {
-          float bv = best_v[j];
-          int bi = best_i[j];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-          }
-          if (lane == 0) { red_v[warp * MB + j] = bv; red_i[warp * MB + j] = bi; }
+      for (int j = 0; j < (kArgmax ? kCols : 1); ++j) keys[row_in_tile * kPitch + col0 + j] = best[j];
+      asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kEpiWarps * 32) : "memory");
+      for (int j = epi_tid; j < MB; j += Cfg::kEpiWarps * 32) {
+        uint32_t bk = 0u;
+        int brow = 0;
+        for (int r = 0; r < kTileN; ++r) {
+          const uint32_t k = keys[r * kPitch + j];
+          if (k > bk) { bk = k; brow = r; }
         }
-      }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      for (int j = threadIdx.x; j < MB; j += 128) {
-        float bv = red_v[j];
-        int bi = red_i[j];
-        for (int w = 1; w < 4; ++w) {
-          const float ov = red_v[w * MB + j];
-          const int oi = red_i[w * MB + j];
-          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        a.cand_val[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bv;
-        a.cand_idx[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bi;
+        a.cand_val[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bk ? bf16_from_order_key(bk >> 16) : -INFINITY;
+        a.cand_idx[static_cast<long long>(cta) * a.cand_ld + m0 + j] =
+            bk ? static_cast<int>(0xFFFFu - (bk & 0xFFFFu)) * kTileN + brow : 0x7fffffff;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
 }  // namespace dfl

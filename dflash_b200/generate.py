@@ -28,7 +28,10 @@ def cuda_time() -> float:
 @torch.inference_mode()
 def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, max_new_tokens: int, block_size: int,
                     stop_token_ids: Optional[List[int]], temperature: float = 0.0, collect_profile: bool = False,
-                    draft_steps: int = 1, seed: Optional[int] = None) -> SimpleNamespace:
+                    draft_steps: int = 1, seed: Optional[int] = None, scheduler=None) -> SimpleNamespace:
+    """`scheduler` (optional, `dflash_b200.schedule.EwmaBlockScheduler`): per-cycle block-size policy, the
+    reference's `dflash_generate_policy` (benchmark_dynamic_schedule.py:260-434). `block_size` must then be the
+    largest candidate: the engine is built for it and a smaller block is a shorter device-side `blk_len`."""
     if draft_steps != 1:
         raise NotImplementedError("draft_steps > 1 (cache-less block refinement, benchmark.py:114-142) is a research "
                                   "variant outside the draft-and-verify hot path")
@@ -38,6 +41,8 @@ def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, 
     P = input_ids.shape[1]
     max_length = P + max_new_tokens
     bs = int(block_size)
+    if scheduler is not None and (bs != scheduler.max_block_size or bs < 2):
+        raise ValueError("with a scheduler, block_size must equal its largest candidate")
     if seed is None:
         seed = int(torch.randint(0, 2**62, (1,)).item()) if temperature >= 1e-5 else 0
     position_ids = torch.arange(max_length + bs, device=dev).unsqueeze(0)
@@ -83,7 +88,11 @@ def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, 
             cyc_ev = (ev(), ev()) if collect_profile else None
             if collect_profile:
                 cyc_ev[0].record()
-            eff = min(bs, max_length - start)
+            t_cycle = time.perf_counter()
+            want = bs if scheduler is None else int(scheduler.select(len(acceptance_lengths)))
+            eff = min(want, max_length - start)
+            if scheduler is not None:
+                eng.buf["blk_len"][0] = eff  # the device-side block length of this cycle
             draft_ev = None
             if eff > 1:
                 if collect_profile:
@@ -126,6 +135,9 @@ def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, 
                 ar_ids[:, start + 1] = tok
                 tau = 1
                 done = stop_t is not None and bool(torch.isin(tok, stop_t).item())
+            if scheduler is not None:  # the host has just synchronised: wall clock == cycle time
+                scheduler.update(tau=tau, cycle_s=time.perf_counter() - t_cycle, effective_bs=eff,
+                                 cycle_idx=len(acceptance_lengths))
             acceptance_lengths.append(tau)
             if collect_profile:
                 cyc_ev[1].record()

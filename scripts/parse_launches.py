@@ -6,7 +6,7 @@ h = rows[hi]; kn = h.index('Kernel Name'); mv = h.index('Metric Value')
 data = [(r[kn], float(r[mv].replace(',', ''))) for r in rows[hi + 1:] if len(r) > mv]
 def short(n):
     n = re.sub(r'dfl::', '', n); n = re.sub(r'void ', '', n); return re.sub(r'\(.*', '', n)
-lm = [i for i, d in enumerate(data) if '<16, 1>' in d[0]]
+lm = [i for i, d in enumerate(data) if re.search(r'gemm_skinny_kernel<\d+, 1>', d[0])]  # lm_head GEMM (argmax mode)
 pairs = [(x + 1, y + 1) for x, y in zip(lm, lm[1:])]
 a, b = min(pairs, key=lambda p: p[1] - p[0])   # kernels after one lm_head GEMM up to and including the next = one step (no request reset inside)
 step = data[a:b]

@@ -578,6 +578,36 @@ def test_dflash_generate_twin_of_benchmark_loop():
     draft.release_engine()
 
 
+def test_dflash_generate_with_block_size_scheduler():
+    """the block size is chosen per cycle by a host policy; every choice is a device-side blk_len.
+    Output stays the target's greedy continuation for any schedule (verification is lossless)."""
+    dev = _cuda()
+    from dflash_b200 import EwmaBlockScheduler, dflash_generate
+    from tests.tiny_models import TINY
+    target, draft = _tiny(16, rigged=True)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 19), generator=torch.Generator().manual_seed(8)).to(dev)
+    sched = EwmaBlockScheduler([4, 8, 16, 32], warmup_cycles=8, probe_interval=5, required_streak=1, cooldown_cycles=0)
+    res = dflash_generate(draft, target, prompt, draft.mask_token_id, 96, 32, None, 0.0, collect_profile=True,
+                          scheduler=sched)
+    assert res.num_output_tokens == 96
+    ebs = [row["effective_block_size"] for row in res.cycle_trace]
+    assert ebs[:4] == [4, 8, 16, 32] and len(set(ebs)) >= 3
+    for row in res.cycle_trace:
+        assert 1 <= row["tau"] <= row["effective_block_size"]
+    # every cycle that ran a candidate size fed the estimates (clamped tail blocks are ignored)
+    assert sum(sched.n_obs.values()) == sum(1 for b in ebs if b in (4, 8, 16, 32))
+    with torch.inference_mode():
+        logits = target(res.output_ids).logits[0].float()
+    pred = logits.argmax(-1)
+    for t in range(18, res.output_ids.shape[1] - 1):
+        tok = res.output_ids[0, t + 1].item()
+        if pred[t].item() != tok:
+            assert _near_tie(logits[t], pred[t].item(), tok), (t, pred[t].item(), tok)
+    with pytest.raises(ValueError):
+        dflash_generate(draft, target, prompt, draft.mask_token_id, 8, 16, None, 0.0, scheduler=sched)
+    draft.release_engine()
+
+
 def test_verify_with_given_posterior_and_stop_and_clamp():
     """Integer path only: posterior tokens supplied by the caller (e.g. sampled elsewhere at T>0), stop ids,
     tail clamp. Exhaustive over the acceptance length."""

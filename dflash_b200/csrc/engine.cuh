@@ -61,6 +61,26 @@ inline int round_mb(int rows) {
 }
 inline int groups_of(int rows) { const int mb = round_mb(rows); return (rows + mb - 1) / mb; }
 
+// KV splits of the draft attention: enough (request, kv head, split) CTAs for about two waves, at most 16.
+// One stream needs all 16 to fill the machine; 64 streams already give 512 CTAs and would only pay for the
+// fp32 partials (16 splits x 1024 rows x 32 heads x 128 x 4 B = 268 MB per layer).
+inline int default_attn_splits(const dflash_config_t& c, int sm_count) {
+  if (c.attn_splits > 0) return c.attn_splits;
+  const int SL = c.block_size <= 16 ? 16 : 32;
+  const int ctas = c.max_requests * c.n_kv_heads * (SL / 16);
+  int n = (2 * sm_count + ctas - 1) / ctas;
+  return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+// Vocab splits of the posterior sampler: about four waves of (row, split) CTAs, 2..32 (each CTA then has enough
+// columns to keep several 128-bit loads in flight per thread).
+inline int default_post_splits(const dflash_config_t& c, int sm_count) {
+  if (c.post_splits > 0) return c.post_splits;
+  const int rows = c.max_requests * c.block_size;
+  int n = (4 * sm_count + rows - 1) / rows;
+  return n < 2 ? 2 : (n > 32 ? 32 : n);
+}
+
 // Fills reg[] (offsets/sizes) for cfg; returns total bytes or 0 on a bad config.
 inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_count, int* max_slots_out) {
   const int SL = c.block_size <= 16 ? 16 : 32;
@@ -68,8 +88,8 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   const int RS = R * SL;
   const int H = c.hidden, I = c.intermediate, Hq = c.n_q_heads, Hkv = c.n_kv_heads;
   const int grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
-  const int nsa = c.attn_splits > 0 ? c.attn_splits : 16;
-  const int nsp = c.post_splits > 0 ? c.post_splits : 32;
+  const int nsa = default_attn_splits(c, sm_count);
+  const int nsp = default_post_splits(c, sm_count);
   const int qkv_cols = (Hq + 2 * Hkv) * 128;
   // widest fp32 partial plane over all GEMMs of the step
   long long ws_elems = 0;
@@ -226,8 +246,8 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->H = c.hidden; e->I = c.intermediate; e->L = c.n_layers; e->Hq = c.n_q_heads; e->Hkv = c.n_kv_heads;
   e->V = c.vocab; e->nsel = c.n_sel; e->bs = c.block_size;
   e->grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
-  e->nsplit_attn = c.attn_splits > 0 ? c.attn_splits : 16;
-  e->nsplit_post = c.post_splits > 0 ? c.post_splits : 32;
+  e->nsplit_attn = default_attn_splits(c, sm_count);
+  e->nsplit_post = default_post_splits(c, sm_count);
   e->pdl = c.use_pdl != 0;
   e->total = layout_workspace(c, e->reg, sm_count, &e->max_slots);
   if (workspace == nullptr || workspace_bytes < e->total) {

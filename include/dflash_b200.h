@@ -56,8 +56,8 @@ typedef struct dflash_config {
   float rms_eps;
   float rope_scale;     /* rotary attention_scaling (1.0 for default rope) */
   long long mask_token_id;
-  int attn_splits;      /* KV splits of the draft attention (0 = default 16) */
-  int post_splits;      /* vocab splits of the posterior sampler (0 = default 32) */
+  int attn_splits;      /* KV splits of the draft attention (0 = about two waves of CTAs, 1..16) */
+  int post_splits;      /* vocab splits of the posterior sampler (0 = about four waves of CTAs, 2..32) */
   int gemm_grid;        /* CTAs per streaming GEMM (0 = SM count) */
   int use_pdl;          /* programmatic dependent launch between the step's kernels */
   int keep_draft_logits;/* also store the draft's bf16 logits (parity tests) */

@@ -209,7 +209,9 @@ constexpr int kRowsMaxTiles = 64;  // H <= 8192
 //                   out = w * bf16(v * rsqrt(mean(v^2) + eps))   (Qwen3RMSNorm, fp32 inside)
 // rowbuf: 6*H bytes of shared memory (the row as H floats + H bf16 norm weights); red: NT/32 floats; ns_tab:
 // kRowsMaxTiles ints. NT threads (tid in [0, NT)) work on one row and meet at named barrier bar_id.
-template <int NT>
+// NS_READY: the caller has already filled ns_tab (and synchronised) -- the stand-alone kernel does that before
+// griddepcontrol.wait, since the slot counts do not depend on the producing GEMM's data.
+template <int NT, bool NS_READY = false>
 __device__ __forceinline__ void finalize_row_body(const RowsArgs& a, int row, int tid, float* rowbuf, float* red,
                                                   int* ns_tab, int bar_id) {
   if (a.valid_mode == kRowsCtx) {
@@ -224,7 +226,7 @@ __device__ __forceinline__ void finalize_row_body(const RowsArgs& a, int row, in
     const int r = row / a.SL, i = row % a.SL;
     if (a.ids == nullptr) tok = row;  // `embed` already is a [rows, H] embedding matrix (forward(noise_embedding=))
     else tok = (i < a.bs) ? a.ids[static_cast<long long>(r) * a.ids_ld + i] : a.pad_token;
-  } else {
+  } else if (!NS_READY) {
     const int nt = (a.H + kTileN - 1) / kTileN;
     for (int t = tid; t < nt; t += NT) ns_tab[t] = tile_slots32(t, a.sm);
     group_sync(bar_id, NT);
@@ -292,14 +294,20 @@ __device__ __forceinline__ void finalize_row_body(const RowsArgs& a, int row, in
 }
 
 __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsArgs a) {
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float red[kRowsThreads / 32];
+  __shared__ int ns_tab[kRowsMaxTiles];
+  // everything that does not depend on the producing GEMM happens while this kernel waits for it
+  if (a.embed == nullptr) {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
+  }
+  __syncthreads();
   // wait first, trigger second: the GEMM behind this kernel then becomes resident exactly when this
   // kernel starts its real work
   pdl_wait();
   pdl_trigger();
-  extern __shared__ __align__(16) float rowbuf[];
-  __shared__ float red[kRowsThreads / 32];
-  __shared__ int ns_tab[kRowsMaxTiles];
-  finalize_row_body<kRowsThreads>(a, blockIdx.x, threadIdx.x, rowbuf, red, ns_tab, 0);
+  finalize_row_body<kRowsThreads, true>(a, blockIdx.x, threadIdx.x, rowbuf, red, ns_tab, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,11 +362,20 @@ __device__ __forceinline__ void swiglu_items3(const SwigluArgs& a, int it0, int 
 }
 
 __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluArgs a) {
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int m = blockIdx.y;
+  int ns_g = 1, ns_u = 1;  // slot counts do not depend on the GEMM's data: computed while waiting for it
+  if (n < a.I) {
+    ns_g = tile_slots32(n / kTileN, a.sm);
+    ns_u = tile_slots32((a.I + n) / kTileN, a.sm);
+  }
   pdl_wait();
   pdl_trigger();
-  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (n >= a.I) return;
-  swiglu_item(a, blockIdx.y, n);
+  const float4 g = sum_slots_4(a.ws, a.sm, m, n, ns_g);
+  const float4 u = sum_slots_4(a.ws, a.sm, m, a.I + n, ns_u);
+  *reinterpret_cast<uint2*>(a.out + static_cast<long long>(m) * a.I + n) =
+      pack4_bf16(silu_mul_bf16(g.x, u.x), silu_mul_bf16(g.y, u.y), silu_mul_bf16(g.z, u.z), silu_mul_bf16(g.w, u.w));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -389,8 +406,20 @@ struct QkvPostArgs {
   int pf_rows, pf_req, pf_pos0;
 };
 
-// one (activation row, head column block hh) item per warp
-__device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, int hh, int lane) {
+// one (activation row, head column block hh) item per warp. Split in two so that the stand-alone kernel can run the
+// part that only reads request state, weights and the rope table BEFORE griddepcontrol.wait (request state is written
+// by the previous step's accept kernel, never by the GEMM in front of this kernel).
+struct QkvItem {
+  int kind;        // 0 q, 1 k, 2 v, -1 nothing to do
+  int ws_row, hh;
+  __nv_bfloat16* dst;
+  float4 wv;       // norm weights of this lane's 4 elements
+  float cs[4], sn[4];
+};
+
+__device__ __forceinline__ QkvItem qkv_post_prepare(const QkvPostArgs& a, int row, int hh, int lane) {
+  QkvItem it;
+  it.kind = -1;
   const int heads_q = a.q_cols / 128;
   const int RS = a.R * a.SL;
   const bool is_block = a.pf_rows == 0 && row >= RS;
@@ -398,62 +427,75 @@ __device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, 
   const int r = a.pf_rows > 0 ? a.pf_req : rl / a.SL, slot = rl % a.SL;
   int pos;
   if (a.pf_rows > 0) {
-    if (row >= a.pf_rows) return;
+    if (row >= a.pf_rows) return it;
     pos = a.pf_pos0 + row;
   } else if (is_block) {
-    if (slot >= a.blk_len[r]) return;
+    if (slot >= a.blk_len[r]) return it;
     pos = a.start[r] + slot;
   } else {
     const int c = a.ctx_len[r];
-    if (slot >= c) return;
+    if (slot >= c) return it;
     pos = a.start[r] - c + slot;
   }
   const int kind = hh < heads_q ? 0 : (hh < heads_q + a.Hkv ? 1 : 2);  // q, k, v
-  if (kind == 0 && !is_block) return;  // context rows carry no queries
-  if (pos < 0 || pos >= a.S_max) return;
+  if (kind == 0 && !is_block) return it;  // context rows carry no queries
+  if (pos < 0 || pos >= a.S_max) return it;
   const int head = kind == 0 ? hh : (kind == 1 ? hh - heads_q : hh - heads_q - a.Hkv);
-  const int ws_row = row - a.row0;
-
-  // head hh covers output columns [hh*128, hh*128+128) = exactly stream-K tile hh
-  const float4 xv = sum_slots_4(a.ws, a.sm, ws_row, hh * 128 + lane * 4, tile_slots32(hh, a.sm));
-  float x[4] = {bf16_round(xv.x), bf16_round(xv.y), bf16_round(xv.z), bf16_round(xv.w)};  // d = 4*lane + t
-
-  __nv_bfloat16* dst;
+  it.ws_row = row - a.row0;
+  it.hh = hh;
   if (kind == 0) {
-    dst = a.q_out + (static_cast<long long>(rl) * a.Hq + head) * 128;
+    it.dst = a.q_out + (static_cast<long long>(rl) * a.Hq + head) * 128;
   } else {
     __nv_bfloat16* base = kind == 1 ? a.k_cache : a.v_cache;
-    dst = base + ((static_cast<long long>(r) * a.Hkv + head) * a.S_max + pos) * 128;
+    it.dst = base + ((static_cast<long long>(r) * a.Hkv + head) * a.S_max + pos) * 128;
   }
-  if (kind == 2) {
-    *reinterpret_cast<uint2*>(dst + lane * 4) = pack4_bf16(x[0], x[1], x[2], x[3]);
-    return;
-  }
+  it.kind = kind;
+  if (kind == 2) return it;
   const __nv_bfloat16* w = kind == 0 ? a.q_norm_w : a.k_norm_w;
-  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
-  ss = warp_sum(ss);
-  const float rstd = 1.0f / sqrtf(ss * (1.0f / 128.0f) + a.eps);
-  const float4 wv = unpack4_bf16(*reinterpret_cast<const uint2*>(w + lane * 4));
-  x[0] = bf16_round(wv.x * bf16_round(x[0] * rstd));
-  x[1] = bf16_round(wv.y * bf16_round(x[1] * rstd));
-  x[2] = bf16_round(wv.z * bf16_round(x[2] * rstd));
-  x[3] = bf16_round(wv.w * bf16_round(x[3] * rstd));
+  it.wv = unpack4_bf16(*reinterpret_cast<const uint2*>(w + lane * 4));
   // RoPE: element d pairs with d +- 64 -> held by lane ^ 16; frequency index = d mod 64
-  float o[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const float other = __shfl_xor_sync(0xffffffffu, x[t], 16);
     const int f = (lane & 15) * 4 + t;
     const float ang = static_cast<float>(pos) * a.inv_freq[f];
     float sn, cs;
     sincosf(ang, &sn, &cs);
-    cs = bf16_round(cs * a.rope_scale);
-    sn = bf16_round(sn * a.rope_scale);
+    it.cs[t] = bf16_round(cs * a.rope_scale);
+    it.sn[t] = bf16_round(sn * a.rope_scale);
+  }
+  return it;
+}
+
+__device__ __forceinline__ void qkv_post_apply(const QkvPostArgs& a, const QkvItem& it, int lane) {
+  if (it.kind < 0) return;
+  // head hh covers output columns [hh*128, hh*128+128) = exactly stream-K tile hh
+  const float4 xv = sum_slots_4(a.ws, a.sm, it.ws_row, it.hh * 128 + lane * 4, tile_slots32(it.hh, a.sm));
+  float x[4] = {bf16_round(xv.x), bf16_round(xv.y), bf16_round(xv.z), bf16_round(xv.w)};  // d = 4*lane + t
+  if (it.kind == 2) {
+    *reinterpret_cast<uint2*>(it.dst + lane * 4) = pack4_bf16(x[0], x[1], x[2], x[3]);
+    return;
+  }
+  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+  ss = warp_sum(ss);
+  const float rstd = 1.0f / sqrtf(ss * (1.0f / 128.0f) + a.eps);
+  x[0] = bf16_round(it.wv.x * bf16_round(x[0] * rstd));
+  x[1] = bf16_round(it.wv.y * bf16_round(x[1] * rstd));
+  x[2] = bf16_round(it.wv.z * bf16_round(x[2] * rstd));
+  x[3] = bf16_round(it.wv.w * bf16_round(x[3] * rstd));
+  float o[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float other = __shfl_xor_sync(0xffffffffu, x[t], 16);
     // first half (lane < 16): x*cos + (-x_hi)*sin ; second half: x*cos + x_lo*sin
     const float rot = (lane < 16) ? -other : other;
-    o[t] = bf16_round(bf16_round(x[t] * cs) + bf16_round(rot * sn));
+    o[t] = bf16_round(bf16_round(x[t] * it.cs[t]) + bf16_round(rot * it.sn[t]));
   }
-  *reinterpret_cast<uint2*>(dst + lane * 4) = pack4_bf16(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<uint2*>(it.dst + lane * 4) = pack4_bf16(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, int hh, int lane) {
+  const QkvItem it = qkv_post_prepare(a, row, hh, lane);
+  qkv_post_apply(a, it, lane);
 }
 
 // item in [0, rows * (q_cols/128 + 2*Hkv))
@@ -464,10 +506,15 @@ __device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, in
 
 __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
   pdl_trigger();
-  pdl_wait();
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (item >= a.rows * (a.q_cols / 128 + 2 * a.Hkv)) return;
-  qkv_post_item(a, item, threadIdx.x & 31);
+  const int heads_per_row = a.q_cols / 128 + 2 * a.Hkv;
+  const int lane = threadIdx.x & 31;
+  QkvItem it;
+  it.kind = -1;
+  // positions, rope table and norm weights while the QKV GEMM in front of this kernel is still running
+  if (item < a.rows * heads_per_row) it = qkv_post_prepare(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
+  pdl_wait();
+  qkv_post_apply(a, it, lane);
 }
 
 }  // namespace dfl

@@ -25,6 +25,14 @@ sys.path.insert(0, ROOT)
 
 Q8 = dict(hidden=4096, intermediate=12288, draft_layers=5, heads=32, kv_heads=8, head_dim=128, vocab=151936,
           target_layers=36, eps=1e-6, rope_theta=1_000_000.0, mask_token_id=151669, block_size=16)
+# BASELINE.json configs[2] / configs[3] draft shapes (parity-test cases, not bench lines)
+LLAMA31_8B = dict(hidden=4096, intermediate=14336, draft_layers=5, heads=32, kv_heads=8, head_dim=128, vocab=128256,
+                  target_layers=32, eps=1e-5, rope_theta=500000.0, mask_token_id=128255, block_size=16,
+                  rope_parameters={"rope_type": "llama3", "rope_theta": 500000.0, "factor": 8.0, "low_freq_factor": 1.0,
+                                   "high_freq_factor": 4.0, "original_max_position_embeddings": 8192})
+QWEN3_CODER_30B_A3B = dict(hidden=2048, intermediate=6144, draft_layers=8, heads=32, kv_heads=4, head_dim=128,
+                           vocab=151936, target_layers=48, eps=1e-6, rope_theta=10_000_000.0, mask_token_id=151669,
+                           block_size=16)
 PROMPT_LEN = 128
 MAX_NEW = 2048
 TAU_SCHEDULE_LEN = 64
@@ -202,7 +210,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
-def build_engine(dims, device, seed, R=1):
+def build_engine(dims, device, seed, R=1, max_new=None, keep_draft_logits=False):
     import torch
     from transformers import Qwen3Config
     from dflash_b200 import DFlashDraftModel
@@ -211,7 +219,8 @@ def build_engine(dims, device, seed, R=1):
                       num_hidden_layers=dims["draft_layers"], num_attention_heads=dims["heads"],
                       num_key_value_heads=dims["kv_heads"], head_dim=dims["head_dim"], max_position_embeddings=40960,
                       rms_norm_eps=dims["eps"],
-                      rope_parameters={"rope_type": "default", "rope_theta": dims["rope_theta"]})
+                      rope_parameters=dims.get("rope_parameters",
+                                               {"rope_type": "default", "rope_theta": dims["rope_theta"]}))
     cfg.num_target_layers = dims["target_layers"]
     cfg.block_size = dims["block_size"]
     cfg.dflash_config = {"mask_token_id": dims["mask_token_id"]}
@@ -227,8 +236,9 @@ def build_engine(dims, device, seed, R=1):
     g = torch.Generator(device=device).manual_seed(seed + 1)
     embed = torch.empty(dims["vocab"], dims["hidden"], dtype=torch.bfloat16, device=device).normal_(0, 0.02, generator=g)
     lm_head = torch.empty(dims["vocab"], dims["hidden"], dtype=torch.bfloat16, device=device).normal_(0, 0.02, generator=g)
-    eng = DraftEngine(draft, embed, lm_head, max_seq=PROMPT_LEN + MAX_NEW + 64, out_len=PROMPT_LEN + MAX_NEW + 64,
-                      max_requests=R, block_size=dims["block_size"],
+    span = PROMPT_LEN + (MAX_NEW if max_new is None else max_new) + 64
+    eng = DraftEngine(draft, embed, lm_head, max_seq=span, out_len=span,
+                      max_requests=R, block_size=dims["block_size"], keep_draft_logits=keep_draft_logits,
                       use_pdl=os.environ.get("DFLASH_PDL", "1") != "0", device=device)
     return draft, eng, embed, lm_head
 
@@ -321,7 +331,7 @@ def run_cuda_arm(args):
     reset()
     enqueue_step()
     torch.cuda.synchronize()
-    # one CUDA graph = one whole draft+verify step (58 kernels, device-resident state, PDL edges)
+    # one CUDA graph = one whole draft+verify step (57 kernels, device-resident state, PDL edges)
     side = torch.cuda.Stream(device=device)
     side.wait_stream(torch.cuda.current_stream())
     graph = torch.cuda.CUDAGraph()
@@ -535,7 +545,7 @@ def run_cuda_arm(args):
             step_us=dict(median=med, p10=p10, p90=p90),
             hbm_gbs_step=step_gbs,
             step_roofline=dict(bound="hbm", achieved=step_gbs, peak=peak_gbs, unit="GB/s", frac=step_gbs / peak_gbs,
-                               algorithmic_bytes=ab["total"], note="all 58 kernels of the step, median step time"),
+                               algorithmic_bytes=ab["total"], note=f"all {launches_per_step} kernels of the step, median step time"),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
                           traffic=1244.9e6 + 4.04e6,  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one
                           # `ncu --set full` capture of this command (profiles/r1_summary.md); not re-measured per run

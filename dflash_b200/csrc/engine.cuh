@@ -333,6 +333,8 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
   ce = cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize smem attribute"); }
+  ce = cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
+  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize2 smem attribute"); }
   // One shared-memory carveout for every kernel of the step: consecutive kernels with different L1/smem splits
   // cannot share an SM, which would serialise exactly the PDL overlaps the schedule relies on.
   if (!getenv("DFLASH_NO_CARVEOUT")) {
@@ -348,6 +350,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     cudaFuncSetAttribute(gemm_skinny_kernel<128, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(gemm_skinny_kernel<256, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(swiglu_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
@@ -387,16 +390,14 @@ inline RowsArgs rows_args_base(const Engine* e) {
 }
 
 // fc GEMM + hidden_norm over the pending context rows -> a_in rows [0, RS)   (dflash.py:177)
-inline int enqueue_ctx_inject(Engine* e, cudaStream_t st) {
-  if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
+inline RowsArgs ctx_finalize_args(Engine* e) {
   RowsArgs a = rows_args_base(e);
   a.ws = e->fc.args.ws;
   a.sm = slot_map_of(e->fc);
   a.valid_mode = kRowsCtx;
   a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
   a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "fc finalize");
-  return DFLASH_OK;
+  return a;
 }
 
 inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_only) {
@@ -433,6 +434,10 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   const int RS = e->RS;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
+  // ctx injection GEMM first (it only reads the features gathered by the previous verify step), then ONE row kernel
+  // for both the context finalize (fc -> hidden_norm -> a_in ctx rows) and the block rows
+  // (embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows)
+  if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
   {
     RowsArgs a = rows_args_base(e);
     if (noise_embedding != nullptr) {
@@ -447,10 +452,22 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     a.resid = x;
     a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
     a.out = a_in + static_cast<size_t>(RS) * e->H;
-    if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "embed+ln1");
+    const RowsArgs c = ctx_finalize_args(e);
+    if (!(dbg_skip() & 1)) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * RS);
+      cfg.blockDim = dim3(kRowsThreads);
+      cfg.dynamicSmemBytes = static_cast<size_t>(e->H) * 6;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = e->pdl ? 1 : 0;
+      DFL_CUDA(cudaLaunchKernelEx(&cfg, finalize_rows2_kernel, c, a, RS), "ctx finalize + embed + ln1");
+    }
   }
-  int rc = enqueue_ctx_inject(e, st);
-  if (rc) return rc;
   AttnArgs aa;
   memset(&aa, 0, sizeof(aa));
   aa.R = e->R; aa.SL = e->SL; aa.bs = e->bs; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.S_max = e->cfg.max_seq;

@@ -310,6 +310,25 @@ __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsA
   finalize_row_body<kRowsThreads, true>(a, blockIdx.x, threadIdx.x, rowbuf, red, ns_tab, 0);
 }
 
+// Two independent row passes in one launch (CTAs [0, rows0) run a0, the rest run a1): the step's first small
+// kernel does both the context finalize (fc -> hidden_norm) and the block embedding + first input_layernorm.
+__global__ void __launch_bounds__(kRowsThreads) finalize_rows2_kernel(const RowsArgs a0, const RowsArgs a1,
+                                                                     const int rows0) {
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float red[kRowsThreads / 32];
+  __shared__ int ns_tab[kRowsMaxTiles];
+  const bool first = static_cast<int>(blockIdx.x) < rows0;
+  const RowsArgs& a = first ? a0 : a1;
+  if (a.embed == nullptr) {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  finalize_row_body<kRowsThreads, true>(a, first ? blockIdx.x : blockIdx.x - rows0, threadIdx.x, rowbuf, red, ns_tab, 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // SwiGLU: out[m, n] = bf16( bf16(silu(gate[m,n])) * up[m,n] ), gate = cols [0,I), up = cols [I,2I) of
 // the fused gate/up GEMM (Qwen3MLP: down_proj(act_fn(gate_proj(x)) * up_proj(x))).

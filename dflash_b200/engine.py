@@ -194,12 +194,12 @@ class DraftEngine:
         self.acc_hist = self.buf["acc_hist"].view(R, hist_len)
         self.SL = 16 if bs <= 16 else 32
         self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
-        # launches per draft step of the schedule actually enqueued (engine.cuh): embed, fc GEMM, fc finalize,
-        # per layer {qkv GEMM, qkv_post, attn, combine, o GEMM, finalize, gate/up GEMM, swiglu, down GEMM, finalize},
-        # lm_head GEMM, token reduce
+        # launches per draft step of the schedule actually enqueued (engine.cuh): fc GEMM, one row kernel (context
+        # finalize + block embedding + first layernorm), per layer {qkv GEMM, qkv_post, attn, combine, o GEMM, finalize,
+        # gate/up GEMM, swiglu, down GEMM, finalize}, lm_head GEMM, token reduce
         mega = bool(self.ccfg.use_mega) and self.R * (16 if self.block_size <= 16 else 32) == 16
         fused = os.environ.get("DFLASH_FUSED_ATTN", "0") not in ("", "0")
-        self.kernels_per_draft_step = 1 if mega else 3 + (8 if fused else 10) * cfg.num_hidden_layers + 2
+        self.kernels_per_draft_step = 1 if mega else 2 + (8 if fused else 10) * cfg.num_hidden_layers + 2
         self.kernels_per_verify_step = 3
         self._graph = None
 

@@ -769,6 +769,88 @@ def test_full_size_qwen3_8b_step_vs_oracle():
     eng.close()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[2] and configs[3] at their full draft dimensions, several request streams per engine:
+#   LLaMA-3.1-8B shape (I = 14336, V = 128256, llama3 rope table) with the posterior sampled at temperature 1.0;
+#   Qwen3-Coder-30B-A3B shape (H = 2048, 8 draft layers / 8 selected target layers, GQA 8:1), greedy.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,R,temperature", [("llama31", 16, 1.0), ("coder30b", 4, 0.0)])
+def test_full_size_batched_configs_vs_oracle(name, R, temperature):
+    dev = _cuda()
+    import bench
+    from oracle import dflash_oracle as O
+    dims = bench.LLAMA31_8B if name == "llama31" else bench.QWEN3_CODER_30B_A3B
+    H, V, L, bs = dims["hidden"], dims["vocab"], dims["draft_layers"], dims["block_size"]
+    draft, eng, embed, lm_head = bench.build_engine(dims, dev, seed=5, R=R, max_new=128)
+    assert len(draft.target_layer_ids) == L
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = {k: v.detach() for k, v in draft.state_dict().items()}
+    sd32 = {k: v.float() for k, v in sd.items()}  # fp32 run of the same weights: the yardstick for bf16 noise
+    g = torch.Generator(device=dev).manual_seed(13)
+    P = [40 + 9 * r for r in range(R)]
+    first = [100 + r for r in range(R)]
+    caches, caches32, pend, blocks, starts = [], [], [], [], list(P)
+    for r in range(R):
+        hs = [(torch.randn(P[r], H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(L)]
+        eng.reset_request(r, torch.randint(0, V - 1, (P[r],), device=dev, generator=g), first[r], 100)
+        eng.prefill_context(r, hs)
+        caches.append(O.DraftCache())
+        caches32.append(O.DraftCache())
+        pend.append(torch.cat(hs, dim=-1).unsqueeze(0))
+        blocks.append(torch.tensor([[first[r]] + [cfg.mask_token_id] * (bs - 1)], device=dev))
+    O.ATTN_IMPL = "sdpa"
+    worst = 0.0
+    for cyc in range(2):
+        eng.draft_step()
+        torch.cuda.synchronize()
+        for r in range(R):
+            with torch.inference_mode():
+                pos = torch.arange(caches[r].get_seq_length(), starts[r] + bs, device=dev).unsqueeze(0)
+                noise = torch.nn.functional.embedding(blocks[r], embed)
+                hid = O.draft_forward(sd, cfg, pend[r], noise, pos, caches[r])
+                caches[r].crop(starts[r])
+                hid32 = O.draft_forward(sd32, cfg, pend[r].float(), noise.float(), pos, caches32[r])
+                caches32[r].crop(starts[r])
+                ref_logits = torch.nn.functional.linear(hid[0, 1:], lm_head).float()
+            got_h = eng.hn[r * eng.SL: r * eng.SL + bs]
+            err, e32, n32 = _rel_err(got_h, hid[0]), _rel_err(got_h, hid32[0]), _rel_err(hid[0], hid32[0])
+            worst = max(worst, err)
+            # within 2e-2 of the reference's bf16 path, or (deep drafts, where bf16 noise alone reaches that) no
+            # further from the fp32 result than the reference's own bf16 run is
+            assert err < REL_TOL or e32 <= 1.1 * n32, (cyc, r, err, e32, n32)
+            got = eng.block_ids[r, 1:].cpu().tolist()
+            for i, (a, b) in enumerate(zip(got, ref_logits.argmax(-1).cpu().tolist())):
+                if a != b:  # only where the oracle's own margin is inside the bf16 logit tolerance
+                    assert (ref_logits[i, b] - ref_logits[i, a]).item() <= REL_TOL * ref_logits[i].abs().max().item()
+        # synthetic target outputs; posterior at the config's temperature with supplied Exp(1) noise
+        blk = eng.block_ids.clone().cpu()
+        tl = torch.randn(R * bs, V, device=dev, generator=g)
+        for r in range(R):
+            for i in range((3 * r + cyc) % bs):
+                tl[r * bs + i, int(blk[r, i + 1])] += 16.0  # the target agrees with the first drafted tokens
+        tl = tl.to(torch.bfloat16)
+        hsel = [(torch.randn(R * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(L)]
+        q = torch.empty(R * bs, V, device=dev, dtype=torch.float32).exponential_(1.0, generator=g)
+        eng.verify_step(tl, hsel, temperature=temperature, noise=q if temperature > 0 else None)
+        torch.cuda.synchronize()
+        if temperature > 0:
+            ref_post = (torch.softmax(tl.float() / temperature, dim=-1) / q).argmax(-1).view(R, bs).cpu()
+            assert (eng.posterior.cpu() == ref_post).float().mean().item() >= 0.99
+        else:
+            assert torch.equal(eng.posterior.cpu(), tl.float().argmax(-1).view(R, bs).cpu())
+        post = eng.posterior.cpu()
+        for r in range(R):
+            a = O.acceptance_length(blk[r].tolist(), post[r].tolist())  # bit-exact given the posterior
+            assert int(eng.acc_hist[r, cyc]) == a + 1 and int(eng.buf["start"][r]) == starts[r] + a + 1
+            starts[r] += a + 1
+            pend[r] = torch.cat([h[r * bs: r * bs + a + 1] for h in hsel], dim=-1).unsqueeze(0)
+            assert torch.equal(eng.buf["ctx_feat"].view(R * eng.SL, -1)[r * eng.SL: r * eng.SL + a + 1], pend[r][0])
+            blocks[r] = torch.tensor([[int(post[r, a])] + [cfg.mask_token_id] * (bs - 1)], device=dev)
+        assert max(int(eng.acc_hist[r, cyc]) for r in range(R)) >= 4
+    print(f"{name}: worst relative error of the draft hidden vs the bf16 sdpa oracle {worst:.4f}")
+    eng.close()
+
+
 @pytest.mark.parametrize("bs", [8, 32])
 def test_spec_generate_block_size_override_is_lossless(bs):
     """benchmark.py --block-size: the number of mask slots is overridden at inference (benchmark.py:104-108,419);

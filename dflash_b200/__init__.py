@@ -19,7 +19,7 @@ def __getattr__(name):
                 "ContextTap"):
         from . import utils
         return getattr(utils, name)
-    if name in ("dflash_generate", "cuda_time"):
+    if name in ("dflash_generate", "dflash_generate_candidates", "cuda_time"):
         from . import generate
         return getattr(generate, name)
     if name in ("EwmaBlockScheduler",):

@@ -151,6 +151,43 @@ int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long 
   return enqueue_verify_step(e->impl, v, static_cast<cudaStream_t>(stream));
 }
 
+int dflash_draft_step_candidates(dflash_engine_t* e, int n_candidates, int fixed_prefix_len, void* stream) {
+  if (!e) { set_error("draft_step_candidates: null engine"); return DFLASH_ERR_ARG; }
+  if (n_candidates < 2 || n_candidates > e->impl->max_cand || fixed_prefix_len < 0) {
+    set_error("draft_step_candidates: n_candidates %d outside [2, %d] (dflash_config_t.max_candidates)", n_candidates,
+              e->impl->max_cand);
+    return DFLASH_ERR_ARG;
+  }
+  return enqueue_draft_step(e->impl, nullptr, true, static_cast<cudaStream_t>(stream), n_candidates, fixed_prefix_len);
+}
+
+int dflash_verify_step_candidates(dflash_engine_t* e, int n_candidates, const void* target_logits, long long logits_ld,
+                                  const void* const* hidden, float temperature, const float* noise,
+                                  unsigned long long seed, const long long* stop_ids, int n_stop, int clamp_tail,
+                                  void* stream) {
+  if (!e || !hidden || !target_logits) { set_error("verify_step_candidates: null argument"); return DFLASH_ERR_ARG; }
+  if (n_candidates < 2 || n_candidates > e->impl->max_cand) {
+    set_error("verify_step_candidates: n_candidates %d outside [2, %d]", n_candidates, e->impl->max_cand);
+    return DFLASH_ERR_ARG;
+  }
+  VerifyInputs v;
+  memset(&v, 0, sizeof(v));
+  v.target_logits = target_logits;
+  v.logits_ld = logits_ld;
+  for (int s = 0; s < e->impl->nsel; ++s) {
+    if (!hidden[s]) { set_error("verify_step_candidates: hidden[%d] is null", s); return DFLASH_ERR_ARG; }
+    v.hidden[s] = hidden[s];
+  }
+  v.temperature = temperature;
+  v.noise = noise;
+  v.seed = seed;
+  v.stop_ids = stop_ids;
+  v.n_stop = stop_ids ? n_stop : 0;
+  v.clamp_tail = clamp_tail;
+  v.n_candidates = n_candidates;
+  return enqueue_verify_step(e->impl, v, static_cast<cudaStream_t>(stream));
+}
+
 int dflash_sample(const void* logits, long long logits_ld, int rows, int vocab, float temperature,
                   const float* noise, unsigned long long seed, float* scratch_val, int* scratch_idx,
                   int nsplit, long long* tokens_out, void* stream) {

@@ -39,6 +39,8 @@ struct Engine {
   std::vector<GemmPlan> kv_pf;  // [layer * 5 + i]
   std::vector<GemmPlan> o, gu, d;
   GemmPlan lm;
+  GemmPlan lm_topk;             // same GEMM with the top-4 epilogue (multi-candidate drafting)
+  int max_cand = 1;
   // persistent draft-step kernel (step_mega.cuh): tables live in the workspace
   bool mega = false;
   bool fused_attn = false;  // cluster-fused qkv_post + attention + combine (attn_fused.cuh)
@@ -121,10 +123,16 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   sz[DFLASH_BUF_WS] = static_cast<size_t>(ws_elems) * 4;
   sz[DFLASH_BUF_ATTN_PO] = static_cast<size_t>(nsa) * RS * Hq * 128 * 4;
   sz[DFLASH_BUF_ATTN_ML] = static_cast<size_t>(nsa) * RS * Hq * 2 * 4;
-  sz[DFLASH_BUF_CAND_VAL] = static_cast<size_t>(grid) * RS * 4;
-  sz[DFLASH_BUF_CAND_IDX] = static_cast<size_t>(grid) * RS * 4;
-  sz[DFLASH_BUF_POST_VAL] = static_cast<size_t>(R) * c.block_size * nsp * 4;
-  sz[DFLASH_BUF_POST_IDX] = static_cast<size_t>(R) * c.block_size * nsp * 4;
+  const int ncand = c.max_candidates > 1 ? 4 : 1;
+  sz[DFLASH_BUF_CAND_VAL] = static_cast<size_t>(grid) * RS * 4 * ncand;
+  sz[DFLASH_BUF_CAND_IDX] = static_cast<size_t>(grid) * RS * 4 * ncand;
+  sz[DFLASH_BUF_POST_VAL] = static_cast<size_t>(R) * c.block_size * nsp * 4 * ncand;
+  sz[DFLASH_BUF_POST_IDX] = static_cast<size_t>(R) * c.block_size * nsp * 4 * ncand;
+  sz[DFLASH_BUF_TOPK_IDX] = static_cast<size_t>(RS) * 4 * 4;
+  sz[DFLASH_BUF_TOPK_VAL] = static_cast<size_t>(RS) * 4 * 4;
+  sz[DFLASH_BUF_CAND_IDS] = static_cast<size_t>(R) * 4 * c.block_size * 8;
+  sz[DFLASH_BUF_CAND_SCORES] = static_cast<size_t>(R) * 4 * 4;
+  sz[DFLASH_BUF_CHOSEN] = static_cast<size_t>(R) * 4;
   sz[DFLASH_BUF_DRAFT_TOKENS] = static_cast<size_t>(RS) * 8;
   sz[DFLASH_BUF_BLOCK_IDS] = static_cast<size_t>(R) * c.block_size * 8;
   sz[DFLASH_BUF_POSTERIOR] = static_cast<size_t>(R) * c.block_size * 8;
@@ -165,9 +173,12 @@ inline int check_config(const dflash_config_t& c) {
     set_error("max_requests %d unsupported: 1..64 request streams per engine", c.max_requests);
     return DFLASH_ERR_ARG;
   }
-  (void)SL;
   if ((c.max_requests & (c.max_requests - 1)) != 0) {
     set_error("max_requests %d must be a power of two (activation buffers are exact UMMA widths)", c.max_requests);
+    return DFLASH_ERR_ARG;
+  }
+  if (c.max_candidates < 0 || c.max_candidates > 4 || (c.max_candidates > 1 && c.max_requests * SL > 32)) {
+    set_error("max_candidates must be 0..4 and needs max_requests * row slots <= 32");
     return DFLASH_ERR_ARG;
   }
   if (c.n_sel < 1 || c.n_sel > 8) { set_error("n_sel must be in [1,8]"); return DFLASH_ERR_ARG; }
@@ -314,6 +325,13 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->lm.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
   e->lm.args.logits = c.keep_draft_logits ? e->buf<__nv_bfloat16>(DFLASH_BUF_DRAFT_LOGITS) : nullptr;
   e->lm.args.logits_ld = e->V;
+  e->max_cand = c.max_candidates > 1 ? c.max_candidates : 1;
+  if (e->max_cand > 1) {
+    DFL_PLAN(make_gemm_plan(&e->lm_topk, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
+                            kModeTopK, e->grid));
+    e->lm_topk.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
+    e->lm_topk.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
+  }
 #undef DFL_PLAN
   // Pre-wait L2 prefetch budget per GEMM (HBM work for the time the small kernel in front of it runs).
   // OFF by default: measured on B200 (profiles/r1_summary.md) it never beat plain TMA streaming -- a byte
@@ -429,8 +447,10 @@ inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_on
 // Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247).
 inline int enqueue_draft_step_mega(Engine* e, cudaStream_t st);
 
-inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st) {
-  if (e->mega && noise_embedding == nullptr && run_lm_head) return enqueue_draft_step_mega(e, st);
+// n_candidates > 1: top-4 lm_head epilogue + candidate blocks (fixed_prefix_rank) instead of the plain argmax tail
+inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st,
+                              int n_candidates = 1, int fixed_prefix_len = 0) {
+  if (e->mega && noise_embedding == nullptr && run_lm_head && n_candidates <= 1) return enqueue_draft_step_mega(e, st);
   const int RS = e->RS;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
@@ -539,6 +559,25 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     }
   }
   if (!run_lm_head) return DFLASH_OK;
+  if (n_candidates > 1) {
+    DFL_CUDA(launch_gemm(e->lm_topk, st, e->pdl), "lm_head top-k gemm");
+    CandArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.cand_val = e->lm_topk.args.cand_val;
+    ca.cand_idx = e->lm_topk.args.cand_idx;
+    ca.n_cta = e->lm_topk.grid;
+    ca.cand_ld = e->lm_topk.args.cand_ld;
+    ca.R = e->R; ca.SL = e->SL; ca.bs = e->bs; ca.prefix_len = fixed_prefix_len;
+    ca.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+    ca.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+    ca.draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
+    ca.topk_idx = e->buf<int>(DFLASH_BUF_TOPK_IDX);
+    ca.topk_val = e->buf<float>(DFLASH_BUF_TOPK_VAL);
+    ca.cand_ids = e->buf<long long>(DFLASH_BUF_CAND_IDS);
+    ca.cand_scores = e->buf<float>(DFLASH_BUF_CAND_SCORES);
+    DFL_CUDA(launch_pdl(candidates_kernel, dim3(e->R), dim3(256), 0, st, e->pdl, ca), "candidate blocks");
+    return DFLASH_OK;
+  }
   if (!(dbg_skip() & 64)) DFL_CUDA(launch_gemm(e->lm, st, e->pdl), "lm_head gemm");
   DraftTokArgs ta;
   ta.cand_val = e->lm.args.cand_val;
@@ -733,11 +772,13 @@ struct VerifyInputs {
   const int* forced_k;
   int forced_ld;
   int clamp_tail;
+  int n_candidates;  // > 1: rows are [R][n_candidates][bs]
 };
 
 // Posterior sampling -> acceptance/commit/state -> next-cycle context gather  (dflash.py:257-268)
 inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st) {
-  const int rows = e->R * e->bs;
+  const int K = v.n_candidates > 1 ? v.n_candidates : 1;
+  const int rows = e->R * K * e->bs;
   if (v.posterior_in == nullptr) {
     PosteriorArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -780,6 +821,10 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
   aa.forced_ld = v.forced_ld > 0 ? v.forced_ld : 1;
   aa.clamp_tail = v.clamp_tail;
   aa.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
+  aa.K = K;
+  aa.cand_ids = e->buf<long long>(DFLASH_BUF_CAND_IDS);
+  aa.cand_scores = e->buf<float>(DFLASH_BUF_CAND_SCORES);
+  aa.chosen = e->buf<int>(DFLASH_BUF_CHOSEN);
   DFL_CUDA(launch_pdl(accept_kernel, dim3(e->R), dim3(32), 0, st, e->pdl, aa), "accept");
   GatherArgs ga;
   memset(&ga, 0, sizeof(ga));
@@ -790,6 +835,8 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
   ga.src_row0 = 0;
   ga.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
   ga.ctx_feat = e->buf<__nv_bfloat16>(DFLASH_BUF_CTX_FEAT);
+  ga.K = K;
+  ga.chosen = K > 1 ? e->buf<int>(DFLASH_BUF_CHOSEN) : nullptr;
   DFL_CUDA(launch_pdl(ctx_gather_kernel, dim3(e->RS, e->nsel), dim3(256), 0, st, e->pdl, ga), "ctx gather");
   return DFLASH_OK;
 }

@@ -33,7 +33,10 @@ enum GemmMode : int {
   kModeArgmax = 1,    // whole tiles per CTA; per-CTA (max, argmax) of the bf16-rounded logits
   kModeArgmaxDump = 2,  // kModeArgmax that also stores the bf16 logits (parity tests; keeps the store addressing
                         // out of the hot instantiation's registers)
+  kModeTopK = 3,      // whole tiles per CTA; per-CTA top-4 of the bf16-rounded logits per activation row
+                      // (multi-candidate drafting: benchmark_candidate_solutions.py:181-249)
 };
+constexpr int kTopK = 4;
 
 struct GemmArgs {
   int n_tiles;    // ceil(N / 128)
@@ -47,7 +50,7 @@ struct GemmArgs {
   int ws_rows;
   long long ws_ld;
   // kModeArgmax
-  float* cand_val;            // [ranges][cand_ld]
+  float* cand_val;            // [ranges][cand_ld] (kModeTopK: [ranges][cand_ld][4], best first)
   int* cand_idx;              // [ranges][cand_ld]
   __nv_bfloat16* logits;      // optional [m_valid][logits_ld] (bf16-rounded), may be null
   long long logits_ld;
@@ -290,10 +293,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     //   (order key of the bf16-rounded logit) << 16 | (0xFFFF - tile)
     // so that keeping the best is ONE integer max per logit, and a tie keeps the lower tile = the lower vocab
     // index (this thread's weight row inside the tile is fixed). Decoded and reduced over threads at the end.
-    uint32_t best[kArgmax ? kCols : 1];
+    constexpr int kKeep = MODE == kModeTopK ? kTopK : 1;  // running bests per activation row (sorted, descending)
+    uint32_t best[kArgmax ? kCols * kKeep : 1];
     if (kArgmax) {
 #pragma unroll
-      for (int j = 0; j < kCols; ++j) best[j] = 0u;
+      for (int j = 0; j < kCols * kKeep; ++j) best[j] = 0u;
     }
 
     long long u = u0;
@@ -331,9 +335,20 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         } else if (n < a.N) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const uint32_t key = (bf16_order_key(v[j]) << 16) | tile_tag;
-            uint32_t& b = best[kArgmax ? c * 16 + j : 0];
-            b = key > b ? key : b;
+            uint32_t key = (bf16_order_key(v[j]) << 16) | tile_tag;
+            if (MODE == kModeTopK) {
+              // insertion into the sorted 4-entry list: a compare-exchange per entry
+#pragma unroll
+              for (int q = 0; q < kKeep; ++q) {
+                uint32_t& b = best[kArgmax ? (c * 16 + j) * kKeep + q : 0];
+                const uint32_t hi = key > b ? key : b;
+                key = key > b ? b : key;
+                b = hi;
+              }
+            } else {
+              uint32_t& b = best[kArgmax ? c * 16 + j : 0];
+              b = key > b ? key : b;
+            }
             if (MODE == kModeArgmaxDump) {
               const int m = col0 + c * 16 + j;
               if (m < mv) a.logits[static_cast<long long>(m0 + m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
@@ -351,22 +366,37 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       // now): keys[row][col], padded pitch so that both the row-wise writes and the column-wise reads are
       // conflict-free. Rows are visited in ascending order with a strict compare, so among equal keys (same value,
       // same tile) the lowest row, i.e. the lowest vocab index, wins.
-      constexpr int kPitch = MB + 1;
+      constexpr int kPitch = MB * kKeep + 1;
       static_assert(kTileN * kPitch * 4 <= S * Cfg::kStageBytes, "argmax reduction scratch exceeds the pipeline smem");
       uint32_t* keys = reinterpret_cast<uint32_t*>(smem);
 #pragma unroll
-      for (int j = 0; j < (kArgmax ? kCols : 1); ++j) keys[row_in_tile * kPitch + col0 + j] = best[j];
+      for (int j = 0; j < (kArgmax ? kCols * kKeep : 1); ++j) keys[row_in_tile * kPitch + col0 * kKeep + j] = best[j];
       asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kEpiWarps * 32) : "memory");
       for (int j = epi_tid; j < MB; j += Cfg::kEpiWarps * 32) {
-        uint32_t bk = 0u;
-        int brow = 0;
+        uint32_t bk[kKeep];
+        int brow[kKeep];
+#pragma unroll
+        for (int q = 0; q < kKeep; ++q) { bk[q] = 0u; brow[q] = 0; }
         for (int r = 0; r < kTileN; ++r) {
-          const uint32_t k = keys[r * kPitch + j];
-          if (k > bk) { bk = k; brow = r; }
+#pragma unroll
+          for (int e = 0; e < kKeep; ++e) {
+            uint32_t k = keys[r * kPitch + j * kKeep + e];
+            int kr = r;
+#pragma unroll
+            for (int q = 0; q < kKeep; ++q) {  // strict compare: among equal keys the lower row stays in front
+              if (k > bk[q]) {
+                const uint32_t tk = bk[q]; bk[q] = k; k = tk;
+                const int tr = brow[q]; brow[q] = kr; kr = tr;
+              }
+            }
+          }
         }
-        a.cand_val[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bk ? bf16_from_order_key(bk >> 16) : -INFINITY;
-        a.cand_idx[static_cast<long long>(cta) * a.cand_ld + m0 + j] =
-            bk ? static_cast<int>(0xFFFFu - (bk & 0xFFFFu)) * kTileN + brow : 0x7fffffff;
+        const long long o = (static_cast<long long>(cta) * a.cand_ld + m0 + j) * kKeep;
+#pragma unroll
+        for (int q = 0; q < kKeep; ++q) {
+          a.cand_val[o + q] = bk[q] ? bf16_from_order_key(bk[q] >> 16) : -INFINITY;
+          a.cand_idx[o + q] = bk[q] ? static_cast<int>(0xFFFFu - (bk[q] & 0xFFFFu)) * kTileN + brow[q] : 0x7fffffff;
+        }
       }
     }
   }

@@ -160,6 +160,12 @@ struct AcceptArgs {
   int forced_ld;
   int clamp_tail;                 // benchmark.py:104-105 effective block size at the tail
   unsigned long long* rng_step;
+  // multi-candidate verify (benchmark_candidate_solutions.py:590-625): K candidate blocks per request were verified
+  // in one target call; posterior rows are (r*K + k)*bs + i. K <= 1: the plain path.
+  int K;
+  const long long* cand_ids;      // [R][4][bs] candidate blocks (k = 0 is the greedy block)
+  const float* cand_scores;       // [R][4] draft score of each candidate
+  int* chosen;                    // [R] out: index of the committed candidate
 };
 
 // One warp per request.
@@ -170,26 +176,29 @@ __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
   if (r == 0 && lane == 0 && a.rng_step != nullptr) *a.rng_step += 1ull;
   if (a.done[r]) return;
   const int bs = a.bs;
+  const int K = a.K > 1 ? a.K : 1;
   long long* blk = a.block_ids + static_cast<long long>(r) * a.ids_ld;
-  __shared__ long long post[64];
-  __shared__ long long btok[64];
-  for (int i = lane; i < bs; i += 32) {
-    long long p;
-    if (a.posterior_in != nullptr) {
-      p = a.posterior_in[r * bs + i];
-    } else {
-      const int row = r * bs + i;
-      float bv = a.cand_val[row * a.nsplit];
-      int bi = a.cand_idx[row * a.nsplit];
-      for (int s = 1; s < a.nsplit; ++s) {
-        const float v = a.cand_val[row * a.nsplit + s];
-        const int ix = a.cand_idx[row * a.nsplit + s];
-        if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+  __shared__ long long s_post[4][64];
+  __shared__ long long s_btok[4][64];
+  for (int k = 0; k < K; ++k) {
+    for (int i = lane; i < bs; i += 32) {
+      long long p;
+      if (a.posterior_in != nullptr) {
+        p = a.posterior_in[(r * K + k) * bs + i];
+      } else {
+        const int row = (r * K + k) * bs + i;
+        float bv = a.cand_val[row * a.nsplit];
+        int bi = a.cand_idx[row * a.nsplit];
+        for (int s = 1; s < a.nsplit; ++s) {
+          const float v = a.cand_val[row * a.nsplit + s];
+          const int ix = a.cand_idx[row * a.nsplit + s];
+          if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+        }
+        p = bi;
       }
-      p = bi;
+      s_post[k][i] = p;
+      s_btok[k][i] = (a.K > 1) ? a.cand_ids[(static_cast<long long>(r) * 4 + k) * bs + i] : blk[i];
     }
-    post[i] = p;
-    btok[i] = blk[i];
   }
   __syncwarp();
   const int st = a.start[r];
@@ -197,12 +206,28 @@ __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
   if (a.forced_k != nullptr) {
     const int k = a.forced_k[r * a.forced_ld + (cyc % a.forced_ld)];
     for (int i = lane; i < bs - 1; i += 32)
-      if (i < k) post[i] = btok[i + 1];
+      if (i < k) s_post[0][i] = s_btok[0][i + 1];
     __syncwarp();
   }
+  const int eff = a.blk_len[r];  // == bs unless the tail clamp shortened this block
+  // candidate choice: maximise tau, then the draft score, then the lower index -- with the reference's own fp32
+  // composite  tau * 1e6 + score - idx * 1e-3  (benchmark_candidate_solutions.py:597-604), first maximum wins
+  int kc = 0;
+  if (K > 1) {
+    float best = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      int acc = 0;
+      while (acc < eff - 1 && s_btok[k][acc + 1] == s_post[k][acc]) ++acc;
+      const float comp = __fsub_rn(__fadd_rn(__fmul_rn(static_cast<float>(acc + 1), 1e6f), a.cand_scores[r * 4 + k]),
+                                   __fmul_rn(static_cast<float>(k), 1e-3f));
+      if (comp > best) { best = comp; kc = k; }
+    }
+    if (lane == 0 && a.chosen != nullptr) a.chosen[r] = kc;
+  }
+  const long long* post = s_post[kc];
+  const long long* btok = s_btok[kc];
   for (int i = lane; i < bs; i += 32) a.posterior[r * bs + i] = post[i];
   if (lane != 0) return;
-  const int eff = a.blk_len[r];  // == bs unless the tail clamp shortened this block
   int acc = 0;  // (blk[1:] == post[:-1]).cumprod().sum()
   while (acc < eff - 1 && btok[acc + 1] == post[acc]) ++acc;
   long long* out = a.output_ids + static_cast<long long>(r) * a.out_ld;
@@ -239,6 +264,8 @@ struct GatherArgs {
   const int* ctx_len;
   __nv_bfloat16* ctx_feat;  // [R*SL][n_sel*H]
   int pf_rows;       // > 0: prompt pass -- source rows [src_row0, src_row0 + pf_rows) -> ctx_feat rows [0, pf_rows)
+  const int* chosen; // multi-candidate verify: request rr's rows are those of candidate chosen[r] ([nreq][K][src_rows])
+  int K;
 };
 
 __global__ void __launch_bounds__(256) ctx_gather_kernel(const GatherArgs a) {
@@ -255,12 +282,99 @@ __global__ void __launch_bounds__(256) ctx_gather_kernel(const GatherArgs a) {
     const int r = a.r0 + rr;
     if (j >= a.ctx_len[r]) return;
     drow = static_cast<long long>(r) * a.SL + j;
+    if (a.chosen != nullptr) rr = rr * a.K + a.chosen[r];
   }
   const int sel = blockIdx.y;
   const uint4* s = reinterpret_cast<const uint4*>(
       a.src[sel] + (static_cast<long long>(rr) * a.src_rows + a.src_row0 + j) * a.H);
   uint4* d = reinterpret_cast<uint4*>(a.ctx_feat + drow * a.n_sel * a.H + static_cast<long long>(sel) * a.H);
   for (int i = threadIdx.x; i < a.H / 8; i += 256) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-candidate drafting, "fixed_prefix_rank" mode (benchmark_candidate_solutions.py:181-249): candidate 0 is the
+// greedy block; candidate k > 0 keeps the first `prefix_len` block positions and takes the rank-(k+1) token of the
+// draft logits at every later position. Input: the per-CTA top-4 lists of the lm_head GEMM (kModeTopK).
+struct CandArgs {
+  const float* cand_val;   // [n_cta][cand_ld][4], best first
+  const int* cand_idx;
+  int n_cta, cand_ld;
+  int R, SL, bs, prefix_len;
+  const int* blk_len;        // [R] effective block length of this cycle
+  long long* block_ids;      // [R][bs]: slots 1.. <- rank-1 tokens (as the plain draft step)
+  long long* draft_tokens;   // [R*SL]
+  int* topk_idx;             // [R*SL][4]
+  float* topk_val;           // [R*SL][4] bf16-rounded logits
+  long long* cand_ids;       // [R][4][bs]
+  float* cand_scores;        // [R][4]: sum of the rank-k logits over the varied positions (bf16-rounded sum)
+};
+
+__global__ void __launch_bounds__(256) candidates_kernel(const CandArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ int s_idx[32][4];
+  __shared__ float s_val[32][4];
+  for (int i = warp; i < a.SL; i += 8) {
+    const int row = r * a.SL + i;
+    // lane-local sorted top-4 over this lane's share of the n_cta * 4 per-CTA candidates
+    float lv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int li[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int g = lane; g < a.n_cta * 4; g += 32) {
+      const long long o = (static_cast<long long>(g >> 2) * a.cand_ld + row) * 4 + (g & 3);
+      float v = __ldcg(a.cand_val + o);
+      int ix = __ldcg(a.cand_idx + o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (v > lv[q] || (v == lv[q] && ix < li[q])) {
+          const float tv = lv[q]; lv[q] = v; v = tv;
+          const int ti = li[q]; li[q] = ix; ix = ti;
+        }
+      }
+    }
+    // four rounds of warp argmax over the lane heads (value desc, vocab index asc); the winner pops its head
+    for (int q = 0; q < 4; ++q) {
+      float bv = lv[0];
+      int bi = li[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lv[0] == bv && li[0] == bi) {  // vocab indices are unique: exactly one lane
+        lv[0] = lv[1]; li[0] = li[1]; lv[1] = lv[2]; li[1] = li[2]; lv[2] = lv[3]; li[2] = li[3];
+        lv[3] = -INFINITY; li[3] = 0x7fffffff;
+      }
+      if (lane == 0) {
+        s_idx[i][q] = bi; s_val[i][q] = bv;
+        a.topk_idx[row * 4 + q] = bi;
+        a.topk_val[row * 4 + q] = bv;
+      }
+    }
+    if (lane == 0) a.draft_tokens[row] = s_idx[i][0];
+  }
+  __syncthreads();
+  const int eff = a.blk_len[r];
+  int suffix_start = a.prefix_len < eff ? a.prefix_len : eff;
+  if (suffix_start < 1) suffix_start = 1;
+  long long* blk = a.block_ids + static_cast<long long>(r) * a.bs;
+  const long long tok0 = blk[0];
+  __syncthreads();
+  for (int t = threadIdx.x; t < a.bs; t += 256) {
+    for (int k = 0; k < 4; ++k) {
+      long long tok;
+      if (t == 0) tok = tok0;
+      else tok = (t < suffix_start || k == 0) ? s_idx[t][0] : s_idx[t][k];
+      a.cand_ids[(static_cast<long long>(r) * 4 + k) * a.bs + t] = tok;
+    }
+    if (t >= 1) blk[t] = s_idx[t][0];
+  }
+  if (threadIdx.x < 4) {
+    float sum = 0.f;
+    for (int t = suffix_start; t < eff; ++t) sum += s_val[t][threadIdx.x];
+    a.cand_scores[r * 4 + threadIdx.x] = bf16_round(sum);
+  }
 }
 
 struct SetStateArgs {

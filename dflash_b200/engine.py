@@ -23,7 +23,7 @@ class CConfig(Structure):
         ("max_requests", c_int), ("max_seq", c_int), ("out_len", c_int), ("hist_len", c_int),
         ("rms_eps", c_float), ("rope_scale", c_float), ("mask_token_id", c_longlong), ("attn_splits", c_int),
         ("post_splits", c_int), ("gemm_grid", c_int), ("use_pdl", c_int), ("keep_draft_logits", c_int),
-        ("prefetch_mb", c_int), ("use_mega", c_int),
+        ("prefetch_mb", c_int), ("use_mega", c_int), ("max_candidates", c_int),
     ]
 
 
@@ -47,6 +47,8 @@ BUFFERS = [
     ("n_cycles", torch.int32), ("blk_len", torch.int32), ("max_len", torch.int32), ("acc_hist", torch.int32),
     ("rng_step", torch.int64), ("draft_logits", torch.bfloat16), ("mega_gemms", torch.uint8),
     ("mega_phases", torch.uint8), ("mega_sync", torch.int64), ("pf_feat", torch.bfloat16), ("pf_a", torch.bfloat16),
+    ("topk_idx", torch.int32), ("topk_val", torch.float32), ("cand_ids", torch.int64), ("cand_scores", torch.float32),
+    ("chosen", torch.int32),
 ]
 
 
@@ -70,6 +72,11 @@ def _declare(lib):
     lib.dflash_verify_step.restype = c_int
     lib.dflash_verify_step.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, POINTER(c_void_p), c_float,
                                        c_void_p, c_ulonglong, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
+    lib.dflash_draft_step_candidates.restype = c_int
+    lib.dflash_draft_step_candidates.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    lib.dflash_verify_step_candidates.restype = c_int
+    lib.dflash_verify_step_candidates.argtypes = [c_void_p, c_int, c_void_p, c_longlong, POINTER(c_void_p), c_float,
+                                                  c_void_p, c_ulonglong, c_void_p, c_int, c_int, c_void_p]
     lib.dflash_sample.restype = c_int
     lib.dflash_sample.argtypes = [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_ulonglong, c_void_p,
                                   c_void_p, c_int, c_void_p, c_void_p]
@@ -129,7 +136,7 @@ class DraftEngine:
     def __init__(self, draft, embed_weight: torch.Tensor, lm_head_weight: torch.Tensor, *, max_seq: int,
                  out_len: int, max_requests: int = 1, block_size: Optional[int] = None, use_pdl: bool = True,
                  keep_draft_logits: bool = False, gemm_grid: int = 0, attn_splits: int = 0, hist_len: int = 4096,
-                 prefetch_mb: int = 0, use_mega: Optional[bool] = None, device=None):
+                 prefetch_mb: int = 0, use_mega: Optional[bool] = None, max_candidates: int = 0, device=None):
         self.lib = _lib.load()
         _declare(self.lib)
         if not torch.cuda.is_available():
@@ -159,7 +166,9 @@ class DraftEngine:
             rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id, attn_splits=attn_splits,
             post_splits=0, gemm_grid=gemm_grid, use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits),
             prefetch_mb=int(os.environ.get("DFLASH_PREFETCH_MB", prefetch_mb)),
-            use_mega=int(os.environ.get("DFLASH_MEGA", "0")) if use_mega is None else int(use_mega))
+            use_mega=int(os.environ.get("DFLASH_MEGA", "0")) if use_mega is None else int(use_mega),
+            max_candidates=int(max_candidates))
+        self.max_candidates = int(max_candidates)
         self.max_seq, self.out_len = int(max_seq), int(out_len)
         with torch.cuda.device(self.device):
             nbytes = self.lib.dflash_workspace_bytes(byref(self.ccfg))
@@ -192,6 +201,8 @@ class DraftEngine:
         self.posterior = self.buf["posterior"].view(R, bs)
         self.output_ids = self.buf["output_ids"].view(R, self.out_len)
         self.acc_hist = self.buf["acc_hist"].view(R, hist_len)
+        self.cand_ids = self.buf["cand_ids"].view(R, 4, bs)        # candidate blocks (multi-candidate drafting)
+        self.cand_scores = self.buf["cand_scores"].view(R, 4)
         self.SL = 16 if bs <= 16 else 32
         self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
         # launches per draft step of the schedule actually enqueued (engine.cuh): fc GEMM, one row kernel (context
@@ -265,6 +276,23 @@ class DraftEngine:
                                                float(temperature), _p(noise), int(seed) & (2**64 - 1), _p(stop_ids),
                                                n_stop, _p(forced_k), fld, int(clamp_tail), _stream()),
                    "dflash_verify_step")
+
+    def draft_step_candidates(self, n_candidates: int, fixed_prefix_len: int):
+        """Draft step with the top-4 lm_head epilogue; fills cand_ids[:, :n_candidates] / cand_scores
+        (fixed_prefix_rank candidates, benchmark_candidate_solutions.py:181-249)."""
+        _lib.check(self.lib.dflash_draft_step_candidates(self.handle, int(n_candidates), int(fixed_prefix_len), _stream()),
+                   "dflash_draft_step_candidates")
+
+    def verify_step_candidates(self, n_candidates: int, target_logits: torch.Tensor, hidden: Sequence[torch.Tensor], *,
+                               temperature: float = 0.0, noise: Optional[torch.Tensor] = None, seed: int = 0,
+                               stop_ids: Optional[torch.Tensor] = None, clamp_tail: bool = False):
+        """target_logits [R*K*bs, V] bf16, hidden[s] [R*K*bs, H] bf16 from ONE target forward over all candidates."""
+        arr = (c_void_p * self.n_sel)(*[h.data_ptr() for h in hidden])
+        n_stop = 0 if stop_ids is None else int(stop_ids.numel())
+        _lib.check(self.lib.dflash_verify_step_candidates(self.handle, int(n_candidates), _p(target_logits),
+                                                          target_logits.stride(-2), arr, float(temperature), _p(noise),
+                                                          int(seed) & (2**64 - 1), _p(stop_ids), n_stop, int(clamp_tail),
+                                                          _stream()), "dflash_verify_step_candidates")
 
     def sample(self, logits: torch.Tensor, temperature: float, seed: int = 0, noise: Optional[torch.Tensor] = None):
         """sample() of model/utils.py:27-34 on [rows, V] bf16 logits -> int64 [rows]."""

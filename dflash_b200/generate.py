@@ -184,3 +184,117 @@ def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, 
                            time_to_first_token=time_to_first_token, time_per_output_token=time_per_output_token,
                            acceptance_lengths=acceptance_lengths, cycle_trace=cycle_trace,
                            profile_summary=profile_summary)
+
+
+@torch.inference_mode()
+def dflash_generate_candidates(model, target, input_ids: torch.Tensor, mask_token_id: int, max_new_tokens: int,
+                               block_size: int, stop_token_ids: Optional[List[int]], *, fixed_prefix_len: int = 2,
+                               rank_top_k: int = 4, max_candidates: int = 4, temperature: float = 0.0,
+                               candidate_mode: str = "fixed_prefix_rank") -> SimpleNamespace:
+    """Multi-candidate speculative decoding, the reference's `dflash_generate_candidate_solutions`
+    (benchmark_candidate_solutions.py:417-741) in its `fixed_prefix_rank` mode -- the variant the reference's
+    results single out (`results.md:461-521`). Per cycle: the draft step keeps a top-4 per block row in the lm_head
+    epilogue and builds up to 4 candidate blocks on the device; ONE target forward verifies them all (batch = number
+    of candidates, the target's KV cache repeated per candidate exactly as the reference does, :574-577); one kernel
+    picks the candidate with the longest accepted prefix (ties: draft score, then index), commits it and gathers
+    the next context features from its rows; the caller keeps that branch of the target cache (:610-614).
+    Greedy only, like the reference (:441-442)."""
+    if candidate_mode != "fixed_prefix_rank":
+        raise NotImplementedError("only candidate_mode='fixed_prefix_rank' is on this path")
+    if temperature >= 1e-5:
+        raise ValueError("multi-candidate verification supports only temperature=0.0 (benchmark_candidate_solutions.py:441)")
+    if input_ids.shape[0] != 1:
+        raise RuntimeError("dflash_generate_candidates: batch size 1")
+    K = min(int(max_candidates), int(rank_top_k))
+    if not 2 <= K <= 4:
+        raise ValueError("2..4 candidates per cycle")
+    dev = target.device
+    P = input_ids.shape[1]
+    max_length = P + max_new_tokens
+    bs = int(block_size)
+    if int(mask_token_id) != int(model.mask_token_id):
+        raise ValueError("mask_token_id differs from the draft's config")
+    position_ids = torch.arange(max_length + bs, device=dev).unsqueeze(0)
+    cache_t = DynamicCache()
+    stop_t = None
+    if stop_token_ids is not None and len(stop_token_ids) > 0:
+        stop_t = torch.tensor(list(stop_token_ids), dtype=torch.int64, device=dev)
+    tap = ContextTap(target, model.target_layer_ids)
+    old_bs = model.block_size
+    prefill_start = cuda_time()
+    model.block_size = bs
+    try:
+        eng = model._get_engine(target.model.embed_tokens.weight, target.lm_head.weight, max_seq=max_length + 2 * bs + 1,
+                                out_len=max_length + bs + 1, max_candidates=4)
+        with tap:
+            out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
+                         logits_to_keep=1)
+        first = sample(out.logits, 0.0)
+        eng.reset_request(0, input_ids[0], first.view(-1)[0], max_new_tokens)
+        eng.buf["blk_len"][0] = min(bs, max_new_tokens)
+        eng.prefill_context(0, [h[0] for h in tap.states])
+        time_to_first_token = cuda_time() - prefill_start
+        decode_start = cuda_time()
+        start = P
+        acceptance_lengths: List[int] = []
+        cycle_trace = []
+        state = torch.empty(3, dtype=torch.int32).pin_memory()
+        state_dev = torch.empty(3, dtype=torch.int32, device=dev)
+        n_cand_sum = 0
+        while start < max_length:
+            eff = min(bs, max_length - start)
+            if eff > 1:
+                eng.draft_step_candidates(K, fixed_prefix_len)
+            else:  # a one-token tail block has nothing to draft: every candidate is the committed token
+                eng.cand_ids[0, :, 0] = eng.block_ids[0, 0]
+                eng.cand_scores.zero_()
+            cands = eng.cand_ids[0, :K, :eff]                       # [K, eff], the engine's buffer
+            cache_t.batch_repeat_interleave(K)                      # == clone + repeat of the reference (:574-577)
+            with tap:
+                out = target(cands, position_ids=position_ids[:, start:start + eff].expand(K, -1),
+                             past_key_values=cache_t, use_cache=True)
+            logits = out.logits
+            if logits.dtype != torch.bfloat16:
+                logits = logits.to(torch.bfloat16)
+            hidden = [h for h in tap.states]
+            if eff < bs:
+                logits = torch.nn.functional.pad(logits, (0, 0, 0, bs - eff))
+                hidden = [torch.nn.functional.pad(h, (0, 0, 0, bs - eff)) for h in hidden]
+            eng.verify_step_candidates(K, logits.reshape(K * bs, -1), [h.reshape(K * bs, -1).contiguous() for h in hidden],
+                                       stop_ids=stop_t, clamp_tail=True)
+            state_dev[0:1].copy_(eng.buf["start"][0:1])
+            state_dev[1:2].copy_(eng.buf["done"][0:1])
+            state_dev[2:3].copy_(eng.buf["chosen"][0:1])
+            state.copy_(state_dev, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            tau = int(state[0]) - start
+            chosen = int(state[2])
+            acceptance_lengths.append(tau)
+            n_cand_sum += K
+            cycle_trace.append({"cycle_idx": len(acceptance_lengths) - 1, "generated_tokens_before": start - P,
+                                "effective_block_size": int(eff), "tau": int(tau), "num_candidates": K,
+                                "chosen_candidate_idx": chosen})
+            start += tau
+            cache_t.batch_select_indices(torch.tensor([chosen], dtype=torch.long, device=dev))   # keep that branch
+            cache_t.crop(start)
+            if int(state[1]) and start < max_length:
+                break
+        output_ids = eng.output_ids[0:1, :max_length].clone()
+    finally:
+        model.block_size = old_bs
+    output_ids = output_ids[:, output_ids[0] != int(mask_token_id)]
+    if stop_t is not None:
+        idx = torch.isin(output_ids[0][P:], stop_t).nonzero(as_tuple=True)[0]
+        if idx.numel() > 0:
+            output_ids = output_ids[:, : P + idx[0] + 1]
+    num_output_tokens = output_ids.shape[1] - P
+    total_decode_time = cuda_time() - decode_start
+    return SimpleNamespace(output_ids=output_ids, num_input_tokens=P, num_output_tokens=num_output_tokens,
+                           time_to_first_token=time_to_first_token,
+                           time_per_output_token=total_decode_time / max(1, num_output_tokens),
+                           acceptance_lengths=acceptance_lengths, cycle_trace=cycle_trace,
+                           candidate_summary={"candidate_mode": candidate_mode, "fixed_prefix_len": int(fixed_prefix_len),
+                                              "avg_candidates_per_cycle": n_cand_sum / max(1, len(acceptance_lengths)),
+                                              "candidate_verify_calls": len(acceptance_lengths),
+                                              "candidate_count_sum": n_cand_sum},
+                           profile_summary=None)

@@ -93,9 +93,9 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
 
     # ------------------------------------------------------------------------------------------
     def _get_engine(self, embed_w: torch.Tensor, lm_head_w: torch.Tensor, max_seq: int, out_len: int,
-                    keep_draft_logits: bool = False) -> DraftEngine:
+                    keep_draft_logits: bool = False, max_candidates: int = 0) -> DraftEngine:
         key = (embed_w.data_ptr(), lm_head_w.data_ptr(), self.block_size, keep_draft_logits,
-               self.fc.weight.data_ptr())
+               self.fc.weight.data_ptr(), max_candidates)
         e = self._engine
         if e is not None and self._engine_key == key and e.max_seq >= max_seq and e.out_len >= out_len:
             return e
@@ -106,7 +106,7 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         cap_out = max(1024, 1 << (int(out_len) - 1).bit_length())
         self._engine = DraftEngine(self, embed_w, lm_head_w, max_seq=cap_seq, out_len=cap_out, max_requests=1,
                                    block_size=self.block_size, keep_draft_logits=keep_draft_logits,
-                                   device=embed_w.device)
+                                   max_candidates=max_candidates, device=embed_w.device)
         self._engine_key = key
         return self._engine
 

@@ -65,6 +65,8 @@ typedef struct dflash_config {
                            kernel in front of it (<= 0 = off, the default: it did not pay on B200) */
   int use_mega;         /* 1 = run the draft step as ONE persistent kernel (one CTA per SM, grid barriers between
                            phases, weights streamed continuously) when the shape allows it (R = 1, bs <= 16) */
+  int max_candidates;   /* candidate blocks per request for multi-candidate verify: 0/1 = off, up to 4 (needs
+                           max_requests * row slots <= 32: the lm_head epilogue then keeps a top-4 per row) */
 } dflash_config_t;
 
 /* Packed bf16 weights of one draft layer. wqkv = [q_proj; k_proj; v_proj] rows, wgu = [gate; up]. */
@@ -125,6 +127,11 @@ enum dflash_buffer_id {
   DFLASH_BUF_MEGA_SYNC,    /* uint64: [0] steps done, [1] error code, [8..] per-phase arrival counters */
   DFLASH_BUF_PF_FEAT,      /* bf16 [256, n_sel*hidden] prompt pass: gathered target features */
   DFLASH_BUF_PF_A,         /* bf16 [256, hidden] prompt pass: hidden_norm(fc(features)) */
+  DFLASH_BUF_TOPK_IDX,     /* int32 [R*SL, 4] top-4 vocab indices of every block row's draft logits */
+  DFLASH_BUF_TOPK_VAL,     /* fp32 [R*SL, 4] their bf16-rounded logits */
+  DFLASH_BUF_CAND_IDS,     /* int64 [R, 4, block_size] candidate blocks (feeds the target's batched verify forward) */
+  DFLASH_BUF_CAND_SCORES,  /* fp32 [R, 4] draft score per candidate */
+  DFLASH_BUF_CHOSEN,       /* int32 [R] candidate committed by the last verify step */
   DFLASH_BUF_COUNT
 };
 
@@ -183,6 +190,23 @@ int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long 
                        const long long* posterior_in, const void* const* hidden_host, float temperature,
                        const float* noise, unsigned long long seed, const long long* stop_ids, int n_stop,
                        const int* forced_k, int forced_ld, int clamp_tail, void* stream);
+
+/* Multi-candidate drafting ("fixed_prefix_rank", benchmark_candidate_solutions.py:181-249): the draft step with a
+ * top-4 lm_head epilogue; builds n_candidates (2..4) candidate blocks per request in DFLASH_BUF_CAND_IDS: candidate 0
+ * is the greedy block, candidate k keeps the first fixed_prefix_len positions and takes the rank-(k+1) token at every
+ * later position; DFLASH_BUF_CAND_SCORES holds their draft scores. block_ids[:, 1:] gets the greedy tokens as usual. */
+int dflash_draft_step_candidates(dflash_engine_t* e, int n_candidates, int fixed_prefix_len, void* stream);
+
+/* Verify after ONE target forward over all candidates (batch n_candidates per request):
+ * target_logits [R*n_candidates*block_size, vocab], hidden_host[s] [R*n_candidates*block_size, hidden]; rows of
+ * candidate k of request r start at (r*n_candidates + k)*block_size. Commits the candidate with the longest accepted
+ * prefix (ties: higher draft score, then lower index -- the reference's composite, :597-604), writes its index to
+ * DFLASH_BUF_CHOSEN (the caller keeps that branch of the target's KV cache, :610-614) and gathers the next context
+ * features from its rows. Greedy or sampled posterior as dflash_verify_step. */
+int dflash_verify_step_candidates(dflash_engine_t* e, int n_candidates, const void* target_logits, long long logits_ld,
+                                  const void* const* hidden_host, float temperature, const float* noise,
+                                  unsigned long long seed, const long long* stop_ids, int n_stop, int clamp_tail,
+                                  void* stream);
 
 /* tokens_out[row] = sample(logits[row, :], temperature) for standalone use (prefill's first token). */
 int dflash_sample(const void* logits, long long logits_ld, int rows, int vocab, float temperature,

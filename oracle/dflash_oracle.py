@@ -228,6 +228,39 @@ def acceptance_length(block_ids: Sequence[int], posterior: Sequence[int]) -> int
     return n
 
 
+def fixed_prefix_rank_candidates(base_block: torch.Tensor, draft_logits: torch.Tensor, fixed_prefix_len: int,
+                                 rank_top_k: int, max_candidates: int):
+    """benchmark_candidate_solutions.py:181-249 (`build_fixed_prefix_rank_candidates`), restated.
+    base_block [1, eff] (slot 0 committed, 1.. greedy draft tokens), draft_logits [1, eff-1, V] (row j -> block
+    position j+1). Returns (candidates [n, eff] int64, draft_scores list[float]): candidate 0 is the greedy block;
+    candidate r keeps positions < max(1, min(fixed_prefix_len, eff)) and takes the rank-(r+1) token at every later
+    position; the score of candidate r is the sum of its rank-(r+1) logits over those positions, summed in the logits'
+    own dtype as torch does (`.sum(dim=1)`). With no suffix position, or fewer than 2 candidates: the base block."""
+    eff = int(base_block.shape[1])
+    suffix_start = max(1, min(int(fixed_prefix_len), eff))
+    if suffix_start >= eff:
+        return base_block.clone(), [0.0]
+    n = min(int(max_candidates), int(rank_top_k), int(draft_logits.shape[-1]))
+    if n <= 1:
+        return base_block.clone(), [0.0]
+    vals, idx = torch.topk(draft_logits[:, suffix_start - 1:, :], k=n, dim=-1)  # [1, suffix, n]
+    cands = base_block.expand(n, -1).clone()
+    cands[:, suffix_start:] = idx[0].transpose(0, 1)
+    scores = vals[0].transpose(0, 1).sum(dim=1)
+    return cands, [float(x) for x in scores.tolist()]
+
+
+def choose_candidate(candidates: torch.Tensor, posterior_all: torch.Tensor, draft_scores: Sequence[float]):
+    """benchmark_candidate_solutions.py:590-607: acceptance length per candidate, then the reference's fp32 composite
+    `tau * 1e6 + draft_score - idx * 1e-3` and the first maximum. Returns (chosen index, acceptance lengths)."""
+    acc = (candidates[:, 1:] == posterior_all[:, :-1]).cumprod(dim=1).sum(dim=1)
+    tau = acc + 1
+    sc = torch.tensor([float(x) for x in draft_scores], dtype=torch.float32)
+    ids = torch.arange(candidates.shape[0], dtype=torch.float32)
+    comp = tau.float().cpu() * 1e6 + sc - ids * 1e-3
+    return int(torch.argmax(comp).item()), [int(x) for x in acc.tolist()]
+
+
 def verify_commit(output_ids: List[int], start: int, block_ids: Sequence[int], posterior: Sequence[int]):
     """model/dflash.py:258-261. Mutates output_ids; returns (new_start, tau)."""
     a = acceptance_length(block_ids, posterior)

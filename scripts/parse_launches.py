@@ -7,7 +7,7 @@ data = [(r[kn], float(r[mv].replace(',', ''))) for r in rows[hi + 1:] if len(r) 
 def short(n):
     n = re.sub(r'dfl::', '', n); n = re.sub(r'void ', '', n); return re.sub(r'\(.*', '', n)
 lm = [i for i, d in enumerate(data) if re.search(r'gemm_skinny_kernel<\d+, 1>', d[0])]  # lm_head GEMM (argmax mode)
-pairs = [(x + 1, y + 1) for x, y in zip(lm, lm[1:])]
+pairs = [(x + 1, y + 1) for x, y in zip(lm, lm[1:]) if y - x >= 20]  # (back-to-back lm_head launches = the roofline timing loop)
 a, b = min(pairs, key=lambda p: p[1] - p[0])   # kernels after one lm_head GEMM up to and including the next = one step (no request reset inside)
 step = data[a:b]
 agg = collections.OrderedDict()

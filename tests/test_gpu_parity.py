@@ -608,6 +608,139 @@ def test_dflash_generate_with_block_size_scheduler():
     draft.release_engine()
 
 
+# ------------------------------------------------------------------------------------------------
+# multi-candidate drafting / verify ("fixed_prefix_rank", benchmark_candidate_solutions.py)
+# ------------------------------------------------------------------------------------------------
+def _cand_engine(bs, K=4):
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY
+    dev = _cuda()
+    target, draft = _tiny(bs, rigged=False)
+    H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
+    g = torch.Generator(device=dev).manual_seed(31)
+    mk = lambda keep: DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=256,  # noqa: E731
+                                  out_len=256, max_requests=1, block_size=bs, keep_draft_logits=keep, max_candidates=K)
+    return dev, target, draft, H, V, nsel, g, mk
+
+
+@pytest.mark.parametrize("bs,prefix", [(16, 2), (16, 5), (8, 0), (32, 3)])
+def test_topk_epilogue_and_candidate_blocks_vs_oracle(bs, prefix):
+    from oracle import dflash_oracle as O
+    dev, target, draft, H, V, nsel, g, mk = _cand_engine(bs)
+    eng = mk(True)
+    hs = [(torch.randn(21, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+    eng.reset_request(0, torch.randint(0, V - 1, (21,), device=dev, generator=g), 5, 100)
+    eng.prefill_context(0, hs)
+    blk0 = eng.block_ids.clone()          # [committed token, mask, mask, ...]: the draft step's input
+    eng.draft_step()                      # argmax epilogue + bf16 logits dump
+    torch.cuda.synchronize()
+    logits = eng.buf["draft_logits"].view(eng.SL, V)[:bs].clone()
+    greedy = eng.block_ids.clone()
+    eng.block_ids.copy_(blk0)
+    eng.draft_step_candidates(4, prefix)  # same input state: top-4 epilogue + candidate blocks
+    torch.cuda.synchronize()
+    assert torch.equal(eng.block_ids, greedy)
+    tv = eng.buf["topk_val"].view(eng.SL, 4)[:bs]
+    ti = eng.buf["topk_idx"].view(eng.SL, 4)[:bs].long()
+    ref_v, ref_i = torch.topk(logits.float(), 5, dim=-1)
+    assert torch.equal(tv, ref_v[:, :4])                                   # the top-4 VALUES of the engine's own logits
+    assert torch.equal(torch.gather(logits.float(), 1, ti), tv)            # each index carries its value
+    assert all(len(set(row)) == 4 for row in ti.cpu().tolist())            # four distinct tokens per row
+    clean = [len(set(ref_v[i].tolist())) == 5 for i in range(bs)]          # rows without a tie among the top 5
+    for i in range(bs):
+        if clean[i]:
+            assert ti[i].cpu().tolist() == ref_i[i, :4].cpu().tolist()
+    # candidate blocks and scores against the reference's builder (restated in the oracle, pinned by goldens)
+    base = greedy.cpu()
+    cands, scores = O.fixed_prefix_rank_candidates(base, logits[1:].unsqueeze(0).cpu(), prefix, 4, 4)
+    got = eng.cand_ids[0].cpu()
+    assert got.shape == (4, bs)
+    suffix_start = max(1, min(prefix, bs))
+    for k in range(4):
+        for t in range(bs):
+            if t < suffix_start or clean[t]:  # (torch.topk's order among exactly tied logits is unspecified)
+                assert int(got[k, t]) == int(cands[k, t]), (k, t)
+            if k == 0:
+                assert int(got[0, t]) == int(base[0, t])  # candidate 0 is the greedy block (ties -> lowest index)
+    sc = eng.cand_scores[0].cpu().tolist()
+    for k in range(4):
+        assert abs(sc[k] - scores[k]) <= 2.0 ** -7 * max(1.0, abs(scores[k])), (k, sc, scores)
+    eng.close()
+
+
+def test_verify_candidates_choice_commit_and_gather():
+    """K candidates verified by one (synthetic) target forward: chosen index, commit, posterior, state and the context
+    rows gathered from the chosen candidate, against the oracle's restatement of the reference's choice rule."""
+    from oracle import dflash_oracle as O
+    bs, K = 16, 4
+    dev, target, draft, H, V, nsel, g, mk = _cand_engine(bs)
+    eng = mk(False)
+    hs = [(torch.randn(17, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+    eng.reset_request(0, torch.randint(0, V - 1, (17,), device=dev, generator=g), 5, 200)
+    eng.prefill_context(0, hs)
+    start = 17
+    for cyc, force in enumerate([[3, 9, 1, 9], [0, 0, 0, 0], [2, 5, 14, 7], [15, 15, 3, 3], [6, 2, 2, 11]]):
+        eng.draft_step_candidates(K, 2)
+        torch.cuda.synchronize()
+        cands = eng.cand_ids[0].clone().cpu()
+        scores = eng.cand_scores[0].cpu().tolist()
+        # target logits whose argmax agrees with candidate k on exactly force[k] positions
+        tl = torch.randn(K * bs, V, device=dev, generator=g)
+        for k in range(K):
+            for i in range(bs):
+                nxt = int(cands[k, i + 1]) if i + 1 < bs else 0
+                tok = nxt if i < force[k] else (nxt + 1 + i) % V
+                tl[k * bs + i, tok] += 20.0
+        tl = tl.to(torch.bfloat16)
+        hsel = [(torch.randn(K * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        eng.verify_step_candidates(K, tl, hsel)
+        torch.cuda.synchronize()
+        post_all = tl.float().argmax(-1).view(K, bs).cpu()
+        chosen, acc = O.choose_candidate(cands, post_all, scores)
+        assert acc == [min(f, bs - 1) for f in force]
+        assert int(eng.buf["chosen"][0]) == chosen, (cyc, acc, scores)
+        a = acc[chosen]
+        assert eng.posterior[0].cpu().tolist() == post_all[chosen].tolist()
+        out = eng.output_ids[0].cpu()
+        assert out[start:start + a + 1].tolist() == cands[chosen, :a + 1].tolist()
+        assert int(out[start + a + 1]) == int(post_all[chosen, a])
+        start += a + 1
+        assert int(eng.buf["start"][0]) == start and int(eng.buf["ctx_len"][0]) == a + 1
+        feat = eng.buf["ctx_feat"].view(eng.SL, -1)[:a + 1]
+        ref_feat = torch.cat([h[chosen * bs: chosen * bs + a + 1] for h in hsel], dim=-1)
+        assert torch.equal(feat, ref_feat)
+        assert eng.block_ids[0].cpu().tolist() == [int(post_all[chosen, a])] + [draft.mask_token_id] * (bs - 1)
+    eng.close()
+
+
+def test_dflash_generate_candidates_is_lossless():
+    """The whole multi-candidate loop with the HF target (one batched verify forward per cycle, the chosen branch of the
+    target cache kept): greedy output is still the target's own greedy continuation."""
+    dev = _cuda()
+    from dflash_b200 import dflash_generate, dflash_generate_candidates
+    from tests.tiny_models import TINY
+    bs = 16
+    target, draft = _tiny(bs, rigged=True)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 23), generator=torch.Generator().manual_seed(6)).to(dev)
+    res = dflash_generate_candidates(draft, target, prompt, draft.mask_token_id, 48, bs, None, fixed_prefix_len=2,
+                                     rank_top_k=4, max_candidates=4)
+    assert res.output_ids.shape == (1, 23 + 48) and sum(res.acceptance_lengths) >= 48
+    assert res.candidate_summary["avg_candidates_per_cycle"] == 4.0
+    with torch.inference_mode():
+        logits = target(res.output_ids).logits[0].float()
+    pred = logits.argmax(-1)
+    for t in range(22, res.output_ids.shape[1] - 1):
+        tok = res.output_ids[0, t + 1].item()
+        if pred[t].item() != tok:
+            assert _near_tie(logits[t], pred[t].item(), tok), (t, pred[t].item(), tok)
+    plain = dflash_generate(draft, target, prompt, draft.mask_token_id, 48, bs, None, 0.0)
+    # more candidates never commit fewer tokens per cycle on the same prefix: compare cycle counts loosely
+    assert len(res.acceptance_lengths) <= len(plain.acceptance_lengths) + 2
+    with pytest.raises(ValueError):
+        dflash_generate_candidates(draft, target, prompt, draft.mask_token_id, 8, bs, None, temperature=1.0)
+    draft.release_engine()
+
+
 def test_verify_with_given_posterior_and_stop_and_clamp():
     """Integer path only: posterior tokens supplied by the caller (e.g. sampled elsewhere at T>0), stop ids,
     tail clamp. Exhaustive over the acceptance length."""

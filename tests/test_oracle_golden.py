@@ -82,3 +82,19 @@ def test_acceptance_exhaustive():
         assert out[5:5 + a + 1] == blk[:a + 1] and out[5 + a + 1] == post[a]
         ref = (torch.tensor(blk[1:]) == torch.tensor(post[:-1])).cumprod(0).sum().item()
         assert ref == a
+
+
+def test_candidate_builder_and_choice_match_reference():
+    """the oracle's fixed_prefix_rank candidates / candidate choice against vectors generated from the
+    reference's own function and expressions (tests/golden/make_cand_golden.py)."""
+    import os
+    import torch
+    from oracle import dflash_oracle as O
+    cases = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "candidates.pt"))
+    assert len(cases) >= 10
+    for c in cases:
+        cands, scores = O.fixed_prefix_rank_candidates(c["base"], c["logits"], c["prefix"], c["topk"], c["maxc"])
+        assert torch.equal(cands, c["cands"])
+        assert scores == c["scores"]
+        chosen, acc = O.choose_candidate(cands, c["posterior"], scores)
+        assert acc == c["acc"] and chosen == c["chosen"]

@@ -203,7 +203,7 @@ def run_reference_arm(args):
                 cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 torch_threads=torch.get_num_threads())
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -560,13 +560,30 @@ def run_cuda_arm(args):
             gather_us=gather_us,
             full_cycle=full_cycle,
         )
-        print(json.dumps(line), flush=True)
+        emit(line)
     ddist.barrier()
     eng.close()
     if world > 1:
         import torch.distributed as tdist
         tdist.destroy_process_group()
     return 0
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the result JSON: everything else this process or its libraries write to
+    fd 1 (NCCL prints its version banner there on some hosts) is sent to stderr."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
 
 
 def main():
@@ -583,6 +600,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_cuda_arm(args)

@@ -984,6 +984,64 @@ def test_full_size_batched_configs_vs_oracle(name, R, temperature):
     eng.close()
 
 
+@pytest.mark.parametrize("P", [44, 256, 300, 1030])
+def test_prompt_pass_then_first_block_vs_oracle(P):
+    """Cycle 0 with c = P context rows (dflash.py:229,238-246): the prompt pass (256 rows per GEMM pass, UMMA width
+    picked per pass) followed by the first block, against one oracle forward over all P context rows."""
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY, draft_state_dict
+    bs = 16
+    target, draft = _tiny(bs)
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = draft_state_dict(draft)
+    H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
+    g = torch.Generator(device=dev).manual_seed(P)
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=P + 64, out_len=P + 64,
+                      max_requests=1, block_size=bs, keep_draft_logits=True)
+    hs = [(torch.randn(P, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+    eng.reset_request(0, torch.randint(0, V - 1, (P,), device=dev, generator=g), 9, 32)
+    eng.prefill_context(0, hs)
+    eng.draft_step()
+    torch.cuda.synchronize()
+    block = torch.tensor([[9] + [cfg.mask_token_id] * (bs - 1)], device=dev)
+    noise = target.model.embed_tokens(block)
+    hid = O.draft_forward(sd, cfg, torch.cat(hs, dim=-1).unsqueeze(0), noise,
+                          torch.arange(0, P + bs, device=dev).unsqueeze(0), O.DraftCache())
+    err = _rel_err(eng.hn[:bs], hid[0])
+    assert err < REL_TOL, err
+    eng.close()
+
+
+@pytest.mark.parametrize("P,n_new", [(1, 1), (1, 2), (5, 17), (300, 33), (1030, 20)])
+def test_spec_generate_edge_lengths_match_oracle(P, n_new):
+    """Shortest prompt, a single new token, a generation that ends inside the first / second block, a prompt longer
+    than one 256-row prompt pass and one that spans five of them: same tokens as the oracle's spec_generate (which is
+    pinned to the reference), near-ties excused by the lossless check against the target."""
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from tests.tiny_models import TINY, draft_state_dict
+    target, draft = _tiny(16, rigged=True)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, P), generator=torch.Generator().manual_seed(P)).to(dev)
+    out = draft.spec_generate(target, prompt, max_new_tokens=n_new, stop_token_ids=None, temperature=0.0)
+    assert out.shape == (1, P + n_new) and torch.equal(out[:, :P], prompt)
+    ref, taus = O.spec_generate(draft_state_dict(draft), O.DraftConfig.from_hf(draft), target, prompt, n_new, None, 0.0)
+    assert ref.shape == out.shape
+    if not torch.equal(out, ref):  # a near-tie somewhere: every token must still be the target's greedy choice
+        with torch.inference_mode():
+            logits = target(out).logits[0].float()
+        pred = logits.argmax(-1)
+        for t in range(P - 1, out.shape[1] - 1):
+            tok = out[0, t + 1].item()
+            if pred[t].item() != tok:
+                assert _near_tie(logits[t], pred[t].item(), tok), (t, pred[t].item(), tok)
+    # (acceptance lengths may differ from the oracle's where the DRAFT's own logits are near-tied: with equal
+    #  committed tokens that only moves tokens between cycles)
+    assert sum(draft.last_acceptance_lengths) >= n_new
+    draft.release_engine()
+
+
 @pytest.mark.parametrize("bs", [8, 32])
 def test_spec_generate_block_size_override_is_lossless(bs):
     """benchmark.py --block-size: the number of mask slots is overridden at inference (benchmark.py:104-108,419);

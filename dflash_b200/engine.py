@@ -128,6 +128,29 @@ class PackedDraftWeights:
         self.final_norm = draft.norm.weight.detach().to(device=device, dtype=bf).contiguous()
         self.inv_freq = draft.rotary_emb.inv_freq.detach().to(device=device, dtype=torch.float32).contiguous()
         self.rope_scale = float(getattr(draft.rotary_emb, "attention_scaling", 1.0))
+        self.device = torch.device(device)
+        self._fc_src = draft.fc.weight.data_ptr()
+
+    def still_matches(self, draft, device) -> bool:
+        """True while the module's parameters are the views this packing created (or, for un-aliased packings, the
+        same storage it was copied from): several engines of one draft then share ONE packed copy."""
+        if torch.device(device) != self.device or draft.fc.weight.data_ptr() != self._fc_src:
+            return False
+        if len(draft.layers) != len(self.layers):
+            return False
+        at = draft.layers[0].self_attn
+        return at.q_proj.weight.data_ptr() == self.layers[0]["wqkv"].data_ptr()
+
+    @classmethod
+    def for_draft(cls, draft, device):
+        cached = getattr(draft, "_dflash_packed", None)
+        if cached is not None and cached.still_matches(draft, device):
+            return cached
+        packed = cls(draft, device)
+        at = draft.layers[0].self_attn
+        if at.q_proj.weight.data_ptr() == packed.layers[0]["wqkv"].data_ptr():  # aliased: safe to share
+            draft._dflash_packed = packed
+        return packed
 
 
 class DraftEngine:
@@ -156,7 +179,7 @@ class DraftEngine:
             raise _lib.DFlashNativeError("the CUDA path computes in bf16: load the target with dtype=torch.bfloat16")
         self.embed = embed_weight.detach().contiguous()
         self.lm_head = lm_head_weight.detach().contiguous()
-        self.weights = PackedDraftWeights(draft, self.device)
+        self.weights = PackedDraftWeights.for_draft(draft, self.device)
         head_dim = getattr(cfg, "head_dim", cfg.hidden_size // cfg.num_attention_heads)
         self.ccfg = CConfig(
             hidden=cfg.hidden_size, intermediate=cfg.intermediate_size, n_layers=cfg.num_hidden_layers,

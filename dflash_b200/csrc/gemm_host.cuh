@@ -170,7 +170,7 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   p->args.w_ld = K;
   p->args.w_rows = static_cast<int>(w_rows_total);
   p->args.pf_units = 0;
-  p->args.late_w = getenv("DFLASH_LATE_W") ? 1 : 0;
+  p->args.late_w = getenv("DFLASH_LATE_W") ? atoi(getenv("DFLASH_LATE_W")) : 0;  // 1: late W issue, 2: no X reloads (timing experiments)
   p->mb = mb;
   p->mode = mode;
   p->groups = groups;

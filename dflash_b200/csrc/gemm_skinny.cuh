@@ -97,6 +97,9 @@ __host__ __device__ inline int tile_num_slots(int t, int k_blocks, long long T, 
 #ifndef DFLASH_GEMM_SMEM_KB_ARGMAX
 #define DFLASH_GEMM_SMEM_KB_ARGMAX 215
 #endif
+#ifndef DFLASH_GEMM_SMEM_KB_WIDE   // partials GEMMs with >= 64 activation rows per group
+#define DFLASH_GEMM_SMEM_KB_WIDE 215
+#endif
 
 template <int MB, int MODE = 0>
 struct GemmCfg {
@@ -105,7 +108,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kWBytes + kXBytes;
   // wide activation tiles (batched engines) need the whole SM to keep >= 4 stages in flight
   static constexpr int kBudget =
-      ((MODE != 0 || MB >= 64) ? DFLASH_GEMM_SMEM_KB_ARGMAX : DFLASH_GEMM_SMEM_KB_PARTIALS) * 1024;
+      (MODE != 0 ? DFLASH_GEMM_SMEM_KB_ARGMAX : (MB >= 64 ? DFLASH_GEMM_SMEM_KB_WIDE : DFLASH_GEMM_SMEM_KB_PARTIALS)) * 1024;
   static constexpr int kStages = kBudget / kStageBytes < 3 ? 3 : kBudget / kStageBytes;
   static constexpr int kTmemCols = (2 * MB < 32) ? 32 : 2 * MB;
   // epilogue warps: warp w drains TMEM lane quarter w % 4. The 256-wide argmax epilogue keeps one packed running
@@ -199,7 +202,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const long long n_units = u1 - u0;
       const int npre = n_units < S ? static_cast<int>(n_units) : S;
       // weight tiles first: they do not depend on the predecessor kernel
-      if (a.late_w) pdl_wait();
+      if (a.late_w == 1) pdl_wait();
       for (int i = 0; i < npre; ++i) {
         const long long u = u0 + i;
         const int tile = static_cast<int>(u / a.k_blocks);
@@ -219,6 +222,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int tile = static_cast<int>(u / a.k_blocks);
         const int kb = static_cast<int>(u % a.k_blocks);
         mbar_wait(&empty[stage], phase ^ 1u);
+        if (a.late_w == 2) {  // timing experiment only (wrong results): no activation tile after the first S units
+          mbar_expect_tx(&full[stage], Cfg::kWBytes);
+          tma_load_2d(sW + stage * Cfg::kWBytes, &tmW, &full[stage], kb * kTileK, a.w_row0 + tile * kTileN, polW);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+          continue;
+        }
         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
         tma_load_2d(sW + stage * Cfg::kWBytes, &tmW, &full[stage], kb * kTileK,
                     a.w_row0 + tile * kTileN, polW);
@@ -314,12 +323,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         dst = a.ws + (static_cast<long long>(slot) * a.ws_rows + m0) * a.ws_ld + n;
       }
       const uint32_t tile_tag = 0xFFFFu - static_cast<uint32_t>(tile);
+      // kChunk columns per TMEM round trip: the loads of a chunk are all issued before the one wait, so a wide
+      // accumulator (128-256 columns at 8+ request streams) is not drained 16 columns at a time -- the last
+      // tile's epilogue is exposed at the end of every GEMM
+      constexpr int kChunk = (MODE == kModePartials) ? (kCols >= 64 ? 64 : kCols)
+                                                      : ((kCols >= 32 && kCols < 128) ? 32 : 16);  // (register budget)
 #pragma unroll
-      for (int c = 0; c < kCols / 16; ++c) {
-        float v[16];
-        tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + col0 + c * 16), v);
+      for (int c = 0; c < kCols / kChunk; ++c) {
+        float v[kChunk];
+#pragma unroll
+        for (int q = 0; q < kChunk / 16; ++q)
+          tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + col0 + c * kChunk + q * 16), v + q * 16);
         tmem_ld_wait();
-        if (c == kCols / 16 - 1) {
+        if (c == kCols / kChunk - 1) {
           // all of this thread's share of the accumulator is in registers: hand the TMEM stage back
           tc_fence_before();
           mbar_arrive(&tempty[acc]);
@@ -327,30 +343,30 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (MODE == kModePartials) {
           if (n < a.N) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int m = col0 + c * 16 + j;
+            for (int j = 0; j < kChunk; ++j) {
+              const int m = col0 + c * kChunk + j;
               if (m < mv) dst[static_cast<long long>(m) * a.ws_ld] = v[j];
             }
           }
         } else if (n < a.N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < kChunk; ++j) {
             uint32_t key = (bf16_order_key(v[j]) << 16) | tile_tag;
             if (MODE == kModeTopK) {
               // insertion into the sorted 4-entry list: a compare-exchange per entry
 #pragma unroll
               for (int q = 0; q < kKeep; ++q) {
-                uint32_t& b = best[kArgmax ? (c * 16 + j) * kKeep + q : 0];
+                uint32_t& b = best[kArgmax ? (c * kChunk + j) * kKeep + q : 0];
                 const uint32_t hi = key > b ? key : b;
                 key = key > b ? b : key;
                 b = hi;
               }
             } else {
-              uint32_t& b = best[kArgmax ? c * 16 + j : 0];
+              uint32_t& b = best[kArgmax ? c * kChunk + j : 0];
               b = key > b ? key : b;
             }
             if (MODE == kModeArgmaxDump) {
-              const int m = col0 + c * 16 + j;
+              const int m = col0 + c * kChunk + j;
               if (m < mv) a.logits[static_cast<long long>(m0 + m) * a.logits_ld + n] = __float2bfloat16_rn(v[j]);
             }
           }

@@ -249,6 +249,21 @@ int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K
   return DFLASH_OK;
 }
 
+// Debug: dflash_gemm_skinny with per-CTA phase timestamps (not part of the reference-facing surface; scripts/gemm_trace.py)
+int dflash_gemm_trace(const void* W, int N, int K, const void* X, int x_rows_total, int mb, int m_valid, float* ws,
+                      int ws_rows, unsigned long long* trace, int grid, void* stream) {
+  GemmPlan p;
+  int rc = make_gemm_plan(&p, W, N, 0, N, K, X, x_rows_total, 0, mb, m_valid, kModePartials, grid);
+  if (rc) return DFLASH_ERR_ARG;
+  p.args.ws = ws;
+  p.args.ws_rows = ws_rows;
+  p.args.ws_ld = N;
+  p.args.trace = trace;
+  cudaError_t e = launch_gemm(p, static_cast<cudaStream_t>(stream), false);
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_trace launch");
+  return p.grid;
+}
+
 int dflash_gemm_argmax(const void* W, int w_rows_total, int N, int K, const void* X, int x_rows_total,
                        int x_row0, int mb, int m_valid, float* cand_val, int* cand_idx, void* logits,
                        long long logits_ld, long long* tokens_out, int grid, int use_pdl,

@@ -62,6 +62,10 @@ struct GemmArgs {
   int w_rows;          // rows of the weight matrix (prefetch bound)
   int pf_units;        // 0 = off
   int late_w;          // experiment: issue the first weight tiles only after griddepcontrol.wait
+  // optional per-CTA phase timestamps (globaltimer ns), [ranges * groups][8]: 0 kernel entry, 1 prologue done,
+  // 2 producer past griddepcontrol.wait, 3 first stage landed (MMA warp), 4 last MMA issued, 5 last accumulator
+  // complete (epilogue), 6 epilogue stores issued (scripts/gemm_trace.py)
+  unsigned long long* trace;
   // Column groups (wide batches): the activation rows are cut into `groups` slabs of MB rows; the grid is
   // (groups, ranges) with the group index fastest, so the `groups` CTAs that stream one weight range are
   // launched side by side and share it through L2 (HBM sees every weight byte once per step).
@@ -97,8 +101,8 @@ __host__ __device__ inline int tile_num_slots(int t, int k_blocks, long long T, 
 #ifndef DFLASH_GEMM_SMEM_KB_ARGMAX
 #define DFLASH_GEMM_SMEM_KB_ARGMAX 215
 #endif
-#ifndef DFLASH_GEMM_SMEM_KB_WIDE   // partials GEMMs with >= 64 activation rows per group
-#define DFLASH_GEMM_SMEM_KB_WIDE 215
+#ifndef DFLASH_GEMM_SMEM_KB_WIDE   // partials GEMMs with >= 64 activation rows per group (+ 16 KB store staging)
+#define DFLASH_GEMM_SMEM_KB_WIDE 196
 #endif
 
 template <int MB, int MODE = 0>
@@ -130,6 +134,12 @@ __device__ __forceinline__ float bf16_from_order_key(uint32_t k) {
   return __uint_as_float(u << 16);
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int MB, int MODE>
 __global__ void __launch_bounds__(GemmCfg<MB, MODE>::kThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
@@ -150,6 +160,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  unsigned long long* tr = a.trace ? a.trace + (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = global_ns();
   const long long T = static_cast<long long>(a.n_tiles) * a.k_blocks;
   const long long G = gridDim.y;           // weight ranges
   const int cta = blockIdx.y;              // this CTA's weight range
@@ -190,6 +202,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (tr && threadIdx.x == 0) tr[1] = global_ns();
   // Let the next kernel in the stream start its own prologue / weight prefetch right away.
   pdl_trigger();
 
@@ -212,6 +225,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                     polW);
       }
       pdl_wait();
+      if (tr) tr[2] = global_ns();
       for (int i = 0; i < npre; ++i) {
         const int kb = static_cast<int>((u0 + i) % a.k_blocks);
         tma_load_2d(sX + i * Cfg::kXBytes, &tmX, &full[i], kb * kTileK, a.x_row0 + m0, polX);
@@ -253,6 +267,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         uint32_t accumulate = 0;
         for (; u < seg_end; ++u) {
           mbar_wait(&full[stage], phase);
+          if (tr && u == u0) tr[3] = global_ns();
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(sW + stage * Cfg::kWBytes));
           const uint64_t db = umma_desc_sw128(smem_u32(sX + stage * Cfg::kXBytes));
@@ -267,6 +282,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull[acc]);  // accumulator complete
+        if (tr && u >= u1) tr[4] = global_ns();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -316,6 +332,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           static_cast<long long>(tile + 1) * a.k_blocks < u1 ? static_cast<long long>(tile + 1) * a.k_blocks : u1;
       const int n = tile * kTileN + row_in_tile;
       mbar_wait(&tfull[acc], acc_phase);
+      if (tr && seg_end >= u1 && threadIdx.x == 0) tr[5] = global_ns();
       tc_fence_after();
       float* dst = nullptr;
       if (MODE == kModePartials) {
@@ -323,11 +340,16 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         dst = a.ws + (static_cast<long long>(slot) * a.ws_rows + m0) * a.ws_ld + n;
       }
       const uint32_t tile_tag = 0xFFFFu - static_cast<uint32_t>(tile);
-      // kChunk columns per TMEM round trip: the loads of a chunk are all issued before the one wait, so a wide
-      // accumulator (128-256 columns at 8+ request streams) is not drained 16 columns at a time -- the last
-      // tile's epilogue is exposed at the end of every GEMM
-      constexpr int kChunk = (MODE == kModePartials) ? (kCols >= 64 ? 64 : kCols)
+      // kChunk columns per TMEM round trip: the loads of a chunk are all issued before the one wait
+      constexpr bool kStageOut = (MODE == kModePartials) && (MB >= 64);
+      constexpr int kChunk = (MODE == kModePartials) ? (kStageOut ? 32 : kCols)
                                                       : ((kCols >= 32 && kCols < 128) ? 32 : 16);  // (register budget)
+      // Wide partial tiles go out through a 16 KB transpose buffer: a thread owns one weight row (column n of the
+      // output) and would store its 128-256 values 4 bytes at a time, one 128-byte warp store per activation row
+      // -- measured 4.4 / 8.5 us per tile at 128 / 256 rows (scripts/gemm_trace.py), exposed at the end of every
+      // GEMM. Transposed, a warp writes one 512-byte output row per store.
+      __shared__ __align__(16) float s_out[kStageOut ? 32 * kTileN : 4];
+      const bool vec_ok = kStageOut && ((a.ws_ld & 3) == 0);
 #pragma unroll
       for (int c = 0; c < kCols / kChunk; ++c) {
         float v[kChunk];
@@ -339,6 +361,30 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           // all of this thread's share of the accumulator is in registers: hand the TMEM stage back
           tc_fence_before();
           mbar_arrive(&tempty[acc]);
+        }
+        if (kStageOut) {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) s_out[j * kTileN + row_in_tile] = v[j];
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          const int nn = tile * kTileN + lane * 4;
+          float* row0 = a.ws + (static_cast<long long>(cta - tile_first_cta(tile, a.k_blocks, T, G)) * a.ws_rows + m0) *
+                                   a.ws_ld + nn;
+          for (int j = quarter; j < kChunk; j += 4) {
+            const int m = col0 + c * kChunk + j;
+            if (m >= mv) continue;
+            const float4 x = *reinterpret_cast<const float4*>(&s_out[j * kTileN + lane * 4]);
+            float* o = row0 + static_cast<long long>(m) * a.ws_ld;
+            if (vec_ok && nn + 3 < a.N) {
+              *reinterpret_cast<float4*>(o) = x;
+            } else {
+              if (nn < a.N) o[0] = x.x;
+              if (nn + 1 < a.N) o[1] = x.y;
+              if (nn + 2 < a.N) o[2] = x.z;
+              if (nn + 3 < a.N) o[3] = x.w;
+            }
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          continue;
         }
         if (MODE == kModePartials) {
           if (n < a.N) {
@@ -376,6 +422,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (tr && threadIdx.x == 0) tr[6] = global_ns();
 
     if (kArgmax) {
       // Reduce over the 128 weight rows of the tile shape through shared memory (the pipeline stages are idle by

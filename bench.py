@@ -30,6 +30,9 @@ LLAMA31_8B = dict(hidden=4096, intermediate=14336, draft_layers=5, heads=32, kv_
                   target_layers=32, eps=1e-5, rope_theta=500000.0, mask_token_id=128255, block_size=16,
                   rope_parameters={"rope_type": "llama3", "rope_theta": 500000.0, "factor": 8.0, "low_freq_factor": 1.0,
                                    "high_freq_factor": 4.0, "original_max_position_embeddings": 8192})
+# BASELINE.json configs[0]: Qwen3-4B target shape (hidden 2560 != heads * head_dim = 4096, tied lm_head / embeddings)
+QWEN3_4B = dict(hidden=2560, intermediate=9728, draft_layers=5, heads=32, kv_heads=8, head_dim=128, vocab=151936,
+                target_layers=36, eps=1e-6, rope_theta=1_000_000.0, mask_token_id=151669, block_size=16)
 QWEN3_CODER_30B_A3B = dict(hidden=2048, intermediate=6144, draft_layers=8, heads=32, kv_heads=4, head_dim=128,
                            vocab=151936, target_layers=48, eps=1e-6, rope_theta=10_000_000.0, mask_token_id=151669,
                            block_size=16)

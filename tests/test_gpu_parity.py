@@ -903,16 +903,16 @@ def test_full_size_qwen3_8b_step_vs_oracle():
 
 
 # ------------------------------------------------------------------------------------------------
-# BASELINE configs[2] and configs[3] at their full draft dimensions, several request streams per engine:
+# BASELINE configs[0], [2] and [3] at their full draft dimensions (configs[0]: Qwen3-4B shape, hidden 2560, batch 1):
 #   LLaMA-3.1-8B shape (I = 14336, V = 128256, llama3 rope table) with the posterior sampled at temperature 1.0;
 #   Qwen3-Coder-30B-A3B shape (H = 2048, 8 draft layers / 8 selected target layers, GQA 8:1), greedy.
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,R,temperature", [("llama31", 16, 1.0), ("coder30b", 4, 0.0)])
+@pytest.mark.parametrize("name,R,temperature", [("llama31", 16, 1.0), ("coder30b", 4, 0.0), ("qwen3_4b", 1, 0.0)])
 def test_full_size_batched_configs_vs_oracle(name, R, temperature):
     dev = _cuda()
     import bench
     from oracle import dflash_oracle as O
-    dims = bench.LLAMA31_8B if name == "llama31" else bench.QWEN3_CODER_30B_A3B
+    dims = {"llama31": bench.LLAMA31_8B, "coder30b": bench.QWEN3_CODER_30B_A3B, "qwen3_4b": bench.QWEN3_4B}[name]
     H, V, L, bs = dims["hidden"], dims["vocab"], dims["draft_layers"], dims["block_size"]
     draft, eng, embed, lm_head = bench.build_engine(dims, dev, seed=5, R=R, max_new=128)
     assert len(draft.target_layer_ids) == L
@@ -959,7 +959,7 @@ def test_full_size_batched_configs_vs_oracle(name, R, temperature):
         blk = eng.block_ids.clone().cpu()
         tl = torch.randn(R * bs, V, device=dev, generator=g)
         for r in range(R):
-            for i in range((3 * r + cyc) % bs):
+            for i in range((3 * r + cyc + 5) % bs):
                 tl[r * bs + i, int(blk[r, i + 1])] += 16.0  # the target agrees with the first drafted tokens
         tl = tl.to(torch.bfloat16)
         hsel = [(torch.randn(R * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(L)]

@@ -30,13 +30,16 @@ def _pow2_at_least(n: int) -> int:
 def spec_generate_batch(draft, target, prompts: Sequence[torch.Tensor], max_new_tokens: int,
                         stop_token_ids: Optional[List[int]], temperature: float, *, max_requests: Optional[int] = None,
                         clamp_tail: bool = False, forced_k: Optional[Sequence[Sequence[int]]] = None,
-                        seed: Optional[int] = None,
-                        noise_fn: Optional[Callable[[int], torch.Tensor]] = None) -> List[torch.Tensor]:
+                        seed: Optional[int] = None, noise_fn: Optional[Callable[[int], torch.Tensor]] = None,
+                        graph_target: bool = False, sync_every: int = 1) -> List[torch.Tensor]:
     """prompts: LongTensor[1, P_i] each (ragged). Returns one LongTensor[1, P_i + n_i] per prompt, in order.
 
     max_requests: request streams resident in the engine (power of two <= 64; default: enough for all prompts).
     forced_k[i]: harness hook, per-prompt forced-acceptance schedule. noise_fn(cycle) -> fp32
     [R * block_size, V] Exp(1) draws for the posterior race at temperature > 0 (tests); otherwise Philox(seed).
+    graph_target: every slot replays the (unmodified) target's verify forward from its own CUDA graph over a static
+    KV cache whose length is the engine's device-side `start[r]` (`target_graph.py`); the host
+    then only polls `start` / `done` every `sync_every` cycles (finished streams are frozen on the device meanwhile).
     Side effect: `draft.last_batch_acceptance_lengths[i]` = tau per cycle of prompt i."""
     draft.eval()
     n = len(prompts)
@@ -57,13 +60,13 @@ def spec_generate_batch(draft, target, prompts: Sequence[torch.Tensor], max_new_
                       device=dev)
     try:
         return _run(draft, target, eng, list(prompts), max_new_tokens, stop_token_ids, temperature, clamp_tail,
-                    forced_k, seed, noise_fn)
+                    forced_k, seed, noise_fn, graph_target, max(1, int(sync_every)), max_len_all + bs)
     finally:
         eng.close()
 
 
 def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_ids, temperature, clamp_tail, forced_k,
-         seed, noise_fn):
+         seed, noise_fn, graph_target=False, sync_every=1, cache_len=0):
     dev, bs, R, n = eng.device, eng.block_size, eng.R, len(prompts)
     H, V, nsel = eng.hidden, eng.vocab, eng.n_sel
     layer_ids = draft.target_layer_ids
@@ -89,19 +92,30 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
     state = torch.empty(2, R, dtype=torch.int32).pin_memory()
     state_dev = torch.empty(2, R, dtype=torch.int32, device=dev)
     next_req = 0
+    gts = [None] * R          # graph_target: one graphed target + static cache per slot
+    if graph_target:
+        from .target_graph import GraphedVerifyTarget
+        cap = max(1024, 1 << (int(cache_len) - 1).bit_length())
+        for r in range(R):
+            gts[r] = GraphedVerifyTarget(target, bs, cap, layer_ids, eng.buf["start"][r:r + 1], eng.block_ids[r:r + 1])
 
     def admit(r: int, i: int):
         ids = prompts[i].to(dev)
         P = ids.shape[1]
-        cache = DynamicCache()
-        with tap:
-            out = target(ids, position_ids=torch.arange(P, device=dev).unsqueeze(0), past_key_values=cache,
-                         use_cache=True, logits_to_keep=1)
-        first = sample(out.logits, temperature, seed=(seed ^ 0x5DEECE66D) + i)
+        cache = None
+        if graph_target:
+            logits0, hidden0 = gts[r].prefill(ids)
+        else:
+            cache = DynamicCache()
+            with tap:
+                out = target(ids, position_ids=torch.arange(P, device=dev).unsqueeze(0), past_key_values=cache,
+                             use_cache=True, logits_to_keep=1)
+            logits0, hidden0 = out.logits, list(tap.states)
+        first = sample(logits0, temperature, seed=(seed ^ 0x5DEECE66D) + i)
         eng.reset_request(r, ids[0], first.view(-1)[0], max_new_tokens)
         if clamp_tail:
             eng.buf["blk_len"][r] = min(bs, max_new_tokens)
-        eng.prefill_context(r, [h[0] for h in tap.states])
+        eng.prefill_context(r, [h[0] for h in hidden0])
         if forced_t is not None:
             f = list(forced_k[i]) or [0]
             forced_t[r] = torch.tensor([f[c % len(f)] for c in range(forced_t.shape[1])], dtype=torch.int32)
@@ -130,8 +144,13 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
         live = [r for r in range(R) if slot_req[r] >= 0]
         if not live:
             break
-        eng.draft_step()
-        for r in live:  # the caller's target, per request, exactly as the reference calls it
+        eng.draft_step_graphed()
+        for r in live if graph_target else ():  # static graphs: positions / cache length come from start[r] on the device
+            logits, hidden = gts[r].verify_forward()
+            tl[r * bs: (r + 1) * bs] = logits
+            for s in range(nsel):
+                hs[s][r * bs: (r + 1) * bs] = hidden[s]
+        for r in () if graph_target else live:  # the caller's target, per request, exactly as the reference calls it
             start = slot_start[r]
             eff = min(bs, slot_P[r] + max_new_tokens - start) if clamp_tail else bs
             with tap:
@@ -144,6 +163,9 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
         noise = noise_fn(cycle) if (noise_fn is not None and temperature >= 1e-5) else None
         eng.verify_step(tl, hs, temperature=temperature, noise=noise, seed=seed, stop_ids=stop_t, forced_k=forced_t,
                         clamp_tail=clamp_tail)
+        cycle += 1
+        if graph_target and cycle % sync_every != 0:
+            continue  # nothing on the host depends on this cycle's outcome
         # the one host sync of the cycle: the HF target caches need every stream's new length
         state_dev[0].copy_(eng.buf["start"])
         state_dev[1].copy_(eng.buf["done"])
@@ -151,9 +173,9 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
         torch.cuda.current_stream(dev).synchronize()
         for r in live:
             slot_start[r] = int(state[0, r])
-            slot_cache[r].crop(slot_start[r])
+            if not graph_target:
+                slot_cache[r].crop(slot_start[r])
             if int(state[1, r]):
                 harvest(r)
-        cycle += 1
     draft.last_batch_acceptance_lengths = taus
     return results

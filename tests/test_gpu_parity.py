@@ -537,6 +537,31 @@ def test_spec_generate_batch_lossless_with_refill(n_prompts, R, temperature, rig
     draft.release_engine()
 
 
+@pytest.mark.parametrize("sync_every", [1, 3])
+def test_spec_generate_batch_with_graphed_targets(sync_every):
+    """Batched loop with every slot's target verify forward replayed from a CUDA graph over a static cache (device-side
+    positions / cache length), host polling every `sync_every` cycles, slots refilled: still lossless per prompt."""
+    dev = _cuda()
+    from tests.tiny_models import TINY
+    target, draft = _tiny(16, rigged=True)
+    g = torch.Generator().manual_seed(17)
+    lens = [12, 31, 9, 22, 17, 40]
+    prompts = [torch.randint(0, TINY["vocab"] - 1, (1, n), generator=g).to(dev) for n in lens]
+    n_new = 20
+    outs = draft.spec_generate_batch(target, prompts, n_new, None, 0.0, max_requests=4, graph_target=True,
+                                     sync_every=sync_every)
+    for i, (p, o) in enumerate(zip(prompts, outs)):
+        assert o.shape == (1, lens[i] + n_new) and torch.equal(o[:, :lens[i]], p)
+        with torch.inference_mode():
+            logits = target(o).logits[0].float()
+        pred = logits.argmax(-1)
+        for t in range(lens[i] - 1, o.shape[1] - 1):
+            tok = o[0, t + 1].item()
+            if pred[t].item() != tok:
+                assert _near_tie(logits[t], pred[t].item(), tok), (i, t, pred[t].item(), tok)
+    draft.release_engine()
+
+
 def test_dflash_generate_twin_of_benchmark_loop():
     """benchmark.py:44-272 twin: same record, tail clamp, block_size == 1 baseline, --collect-profile spans."""
     dev = _cuda()

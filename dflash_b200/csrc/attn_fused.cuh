@@ -22,6 +22,7 @@ constexpr int kFusedSplits = 8;  // cluster size (portable maximum)
 struct AttnFusedArgs {
   QkvPostArgs post;
   AttnArgs attn;  // nsplit must be kFusedSplits; part_o / part_ml unused
+  int fuse_post;  // 0: qkv_post ran as its own kernel before this one (steps B + C only)
 };
 
 __host__ __device__ inline int attn_fused_smem(int group) {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(384, 1) attn_fused_kernel(const AttnFusedArgs 
   float* s_ml = s_o + 16 * group * kAttnD;                                    // [16*group][2]
 
   // ---- A: post-processing items of this (request, kv head, query tile)
-  {
+  if (fa.fuse_post) {
     const int n_q = group * 16, n_kv = 2 * a.SL;  // q rows of the tile; ctx + block rows of the request
     const int total = n_q + 2 * n_kv;
     const int wpc = static_cast<int>(blockDim.x >> 5);  // warps per CTA taking part in step A
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(384, 1) attn_fused_kernel(const AttnFusedArgs 
       qkv_post_rowhead(pa, row, hh, lane);
     }
     __threadfence();
+    cluster_sync_all();
   }
-  cluster_sync_all();
 
   // ---- B: flash-decoding over this CTA's key range; partial stays in shared memory
   {

@@ -43,7 +43,7 @@ struct Engine {
   int max_cand = 1;
   // persistent draft-step kernel (step_mega.cuh): tables live in the workspace
   bool mega = false;
-  bool fused_attn = false;  // cluster-fused qkv_post + attention + combine (attn_fused.cuh)
+  int fused_attn = 0;  // 1: cluster-fused qkv_post + attention + combine, 2: attention + combine only (attn_fused.cuh)
   bool want_mega = false;
   int mega_phases = 0;
 
@@ -384,7 +384,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   {
     const char* fe = getenv("DFLASH_FUSED_ATTN");
     const int group = e->Hq / e->Hkv;
-    e->fused_attn = fe != nullptr && atoi(fe) != 0;  // opt-in: measured 758 vs 750 us/step, no gain
+    e->fused_attn = fe != nullptr ? atoi(fe) : 0;  // opt-in: measured 758 vs 750 us/step, no gain
     if (e->fused_attn) {
       ce = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_fused_smem(group));
       if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "fused attention smem attribute"); }
@@ -507,9 +507,12 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     aa.k_cache = qa.k_cache;
     aa.v_cache = qa.v_cache;
     if (e->fused_attn && !dbg_skip()) {
+      if (e->fused_attn == 2)
+        DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
       AttnFusedArgs fa;
       fa.post = qa;
       fa.attn = aa;
+      fa.fuse_post = e->fused_attn == 1;
       fa.attn.nsplit = kFusedSplits;
       DFL_CUDA(launch_cluster_pdl(attn_fused_kernel, dim3(kFusedSplits, e->Hkv, e->R * (e->SL / 16)),
                                   dim3(32 * (group + kFusedPostWarps)), dim3(kFusedSplits, 1, 1), attn_fused_smem(group), st, e->pdl, fa),

@@ -79,12 +79,12 @@ __host__ __device__ inline int attn_chunk(int L, int nsplit) {
 // cluster-fused kernel) -- instead of the global [split][row][head] layout.
 template <int NSTG, bool LOCAL = false>
 __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt, int h, int split, int tid,
-                                                int nthreads, uint32_t smem0, int bar_id) {
+                                                int nthreads, uint32_t smem0, int bar_id, int L_in = -1) {
   const int warp = tid >> 5, lane = tid & 31;
   const int group = a.Hq / a.Hkv;
   const int hq = h * group + warp;
   const int RS = a.R * a.SL;
-  const int L = a.start[r] + a.blk_len[r];
+  const int L = L_in >= 0 ? L_in : a.start[r] + a.blk_len[r];
   const int chunk = attn_chunk(L, a.nsplit);
   const int k0 = split * chunk;
   const int k1 = min(L, k0 + chunk);
@@ -260,32 +260,37 @@ __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt
 
 __global__ void attn_split_kernel(const AttnArgs a) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ __align__(128) uint8_t attn_smem[];
   const int tiles_per_req = a.SL / 16;
-  attn_split_body<2>(a, blockIdx.z / tiles_per_req, blockIdx.z % tiles_per_req, blockIdx.y, blockIdx.x, threadIdx.x,
-                     blockDim.x, smem_u32(attn_smem), 0);
+  const int r = blockIdx.z / tiles_per_req;
+  // the key range comes from request state that only the previous step's accept kernel writes: read it while the
+  // kernel in front of this one (qkv_post) is still running
+  const int L = a.start[r] + a.blk_len[r];
+  pdl_wait();
+  attn_split_body<2>(a, r, blockIdx.z % tiles_per_req, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x,
+                     smem_u32(attn_smem), 0, L);
 }
 
 // Merge the splits of one (row, q head) item: one warp.
 __device__ __forceinline__ void attn_combine_item(const AttnArgs& a, int item, int lane) {
   const int RS = a.R * a.SL;
   // all (max, sum) pairs first (one L2 round trip), then the partial outputs of the live splits
+  // (max, sum) pairs AND the partial outputs of every split are requested together: one L2 round trip instead of two
+  // (a dead split's output rows were never written; they are loaded but only used under the `!= -inf` test below)
   float2 ml[16];
+  float4 ov[16];
 #pragma unroll
   for (int s = 0; s < 16; ++s)
-    if (s < a.nsplit) ml[s] = __ldcg(reinterpret_cast<const float2*>(a.part_ml + (static_cast<long long>(s) * RS * a.Hq + item) * 2));
+    if (s < a.nsplit) {
+      ml[s] = __ldcg(reinterpret_cast<const float2*>(a.part_ml + (static_cast<long long>(s) * RS * a.Hq + item) * 2));
+      ov[s] = __ldcg(reinterpret_cast<const float4*>(a.part_o + (static_cast<long long>(s) * RS * a.Hq + item) * kAttnD + lane * 4));
+    }
   float M = -INFINITY;
 #pragma unroll
   for (int s = 0; s < 16; ++s)
     if (s < a.nsplit) M = fmaxf(M, ml[s].x);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float den = 0.f;
-  float4 ov[16];
-#pragma unroll
-  for (int s = 0; s < 16; ++s)
-    if (s < a.nsplit && ml[s].x != -INFINITY)
-      ov[s] = __ldcg(reinterpret_cast<const float4*>(a.part_o + (static_cast<long long>(s) * RS * a.Hq + item) * kAttnD + lane * 4));
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
     if (s < a.nsplit && ml[s].x != -INFINITY) {

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) posterior_kernel(const PosteriorArgs a) {
   const int c1 = min(a.V, c0 + seg);
   const __nv_bfloat16* lp = a.logits + static_cast<long long>(row) * a.ld;
   const bool greedy = a.inv_temp == 0.f;
-  const unsigned long long step = (a.rng_step != nullptr) ? *a.rng_step : 0ull;
+  const unsigned long long step = (a.rng_step != nullptr && !greedy && a.noise == nullptr) ? *a.rng_step : 0ull;
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(lp) & 15) == 0);
@@ -174,7 +174,14 @@ __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
   pdl_wait();
   const int r = blockIdx.x, lane = threadIdx.x;
   if (r == 0 && lane == 0 && a.rng_step != nullptr) *a.rng_step += 1ull;
-  if (a.done[r]) return;
+  // every scalar of the request's state is requested up front: one L2 round trip instead of one per use
+  const int done = a.done[r];
+  const int st = a.start[r];
+  const int cyc = a.n_cycles[r];
+  const int eff = a.blk_len[r];  // == bs unless the tail clamp shortened this block
+  const int max_len = a.max_len[r];
+  const int fk = a.forced_k != nullptr ? a.forced_k[r * a.forced_ld + (cyc % a.forced_ld)] : 0;
+  if (done) return;
   const int bs = a.bs;
   const int K = a.K > 1 ? a.K : 1;
   long long* blk = a.block_ids + static_cast<long long>(r) * a.ids_ld;
@@ -187,12 +194,19 @@ __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
         p = a.posterior_in[(r * K + k) * bs + i];
       } else {
         const int row = (r * K + k) * bs + i;
-        float bv = a.cand_val[row * a.nsplit];
-        int bi = a.cand_idx[row * a.nsplit];
-        for (int s = 1; s < a.nsplit; ++s) {
-          const float v = a.cand_val[row * a.nsplit + s];
-          const int ix = a.cand_idx[row * a.nsplit + s];
-          if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+        const float* cv = a.cand_val + static_cast<long long>(row) * a.nsplit;
+        const int* ci = a.cand_idx + static_cast<long long>(row) * a.nsplit;
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int s0 = 0; s0 < a.nsplit; s0 += 8) {  // eight candidates in flight per round trip
+          float v[8];
+          int ix[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (s0 + q < a.nsplit) { v[q] = cv[s0 + q]; ix[q] = ci[s0 + q]; }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (s0 + q < a.nsplit && (v[q] > bv || (v[q] == bv && ix[q] < bi))) { bv = v[q]; bi = ix[q]; }
         }
         p = bi;
       }
@@ -201,15 +215,11 @@ __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
     }
   }
   __syncwarp();
-  const int st = a.start[r];
-  const int cyc = a.n_cycles[r];
   if (a.forced_k != nullptr) {
-    const int k = a.forced_k[r * a.forced_ld + (cyc % a.forced_ld)];
     for (int i = lane; i < bs - 1; i += 32)
-      if (i < k) s_post[0][i] = s_btok[0][i + 1];
+      if (i < fk) s_post[0][i] = s_btok[0][i + 1];
     __syncwarp();
   }
-  const int eff = a.blk_len[r];  // == bs unless the tail clamp shortened this block
   // candidate choice: maximise tau, then the draft score, then the lower index -- with the reference's own fp32
   // composite  tau * 1e6 + score - idx * 1e-3  (benchmark_candidate_solutions.py:597-604), first maximum wins
   int kc = 0;
@@ -244,9 +254,9 @@ __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
   a.ctx_len[r] = acc + 1;
   if (cyc < a.hist_ld) a.acc_hist[r * a.hist_ld + cyc] = acc + 1;
   a.n_cycles[r] = cyc + 1;
-  if (stop || nst >= a.max_len[r]) a.done[r] = 1;
+  if (stop || nst >= max_len) a.done[r] = 1;
   if (a.clamp_tail) {
-    const int remaining = a.max_len[r] - nst;
+    const int remaining = max_len - nst;
     a.blk_len[r] = remaining < bs ? (remaining < 1 ? 1 : remaining) : bs;
   }
   blk[0] = bonus;

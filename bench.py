@@ -195,8 +195,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     import torch
-    steps = min(args.steps, 12)
-    warmup = min(max(args.warmup, 1), 2)
+    steps = min(args.steps, 60)   # bounded sample: ~10 s of CPU work at ~0.17 s per step
+    warmup = min(max(args.warmup, 1), 3)
     tps, ms, cores, sample = cpu_step_bench(Q8, steps, warmup)
     line = dict(metric="draft_verify_tokens_per_s", value=tps, unit="tokens/s", n_gpus=args.gpus, steps=steps,
                 warmup=warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -531,7 +531,7 @@ def run_cuda_arm(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                tps, ms, cores, sample = cpu_step_bench(dims, steps=8, warmup=1)
+                tps, ms, cores, sample = cpu_step_bench(dims, steps=48, warmup=2)  # ~10 s of CPU work
                 cpu = dict(value=tps, unit="tokens/s", cores=cores, kind="port", sample=sample, ms_per_step=ms)
             except Exception as ex:  # e.g. not enough host RAM
                 cpu = dict(value=None, unit="tokens/s", cores=os.cpu_count(), kind="port", sample=f"failed: {ex}")

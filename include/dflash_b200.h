@@ -236,6 +236,13 @@ int dflash_gemm_argmax(const void* W, int w_rows_total, int N, int K, const void
                        int x_row0, int mb, int m_valid, float* cand_val, int* cand_idx, void* logits,
                        long long logits_ld, long long* tokens_out, int grid, int use_pdl, void* stream);
 
+/* Debug only (scripts/gemm_trace.py): dflash_gemm_skinny without the slot sum, recording per-CTA phase timestamps
+ * (globaltimer ns) into trace[ranges * groups][8]: kernel entry, prologue done, producer past griddepcontrol.wait,
+ * first stage landed, last MMA issued, last accumulator complete, epilogue stores issued. Returns the number of weight
+ * ranges (> 0) or a negative error. */
+int dflash_gemm_trace(const void* W, int N, int K, const void* X, int x_rows_total, int mb, int m_valid, float* ws,
+                      int ws_rows, unsigned long long* trace, int grid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

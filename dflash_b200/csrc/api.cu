@@ -151,6 +151,39 @@ int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long 
   return enqueue_verify_step(e->impl, v, static_cast<cudaStream_t>(stream));
 }
 
+int dflash_draft_step_sampled(dflash_engine_t* e, float temperature, unsigned long long seed, void* stream) {
+  if (!e) { set_error("draft_step_sampled: null engine"); return DFLASH_ERR_ARG; }
+  if (temperature >= 1e-5f && !e->impl->has_sample) {
+    set_error("draft_step_sampled: the sampling epilogue needs max_requests * row slots <= 32");
+    return DFLASH_ERR_ARG;
+  }
+  return enqueue_draft_step(e->impl, nullptr, true, static_cast<cudaStream_t>(stream), 1, 0, temperature, seed);
+}
+
+int dflash_gemm_sample(const void* W, int w_rows_total, int N, int K, const void* X, int x_rows_total, int x_row0,
+                       int mb, int m_valid, float temperature, unsigned long long seed, unsigned long long step,
+                       float* cand_val, int* cand_idx, long long* tokens_out, int grid, int use_pdl, void* stream) {
+  if (!W || !X || !cand_val || !cand_idx || !tokens_out || temperature < 1e-5f || m_valid > mb || mb > 32) {
+    set_error("gemm_sample: bad argument (needs temperature > 0, m_valid <= mb <= 32)");
+    return DFLASH_ERR_ARG;
+  }
+  GemmPlan p;
+  int rc = make_gemm_plan(&p, W, w_rows_total, 0, N, K, X, x_rows_total, x_row0, mb, m_valid, kModeSample, grid);
+  if (rc) return DFLASH_ERR_ARG;
+  p.args.cand_val = cand_val;
+  p.args.cand_idx = cand_idx;
+  p.args.inv_temp = 1.0f / temperature;
+  p.args.seed = seed;
+  p.args.step_base = step;
+  p.args.rng_step = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = launch_gemm(p, st, use_pdl != 0);
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_sample launch");
+  e = launch_reduce_candidates(cand_val, cand_idx, p.grid, p.args.cand_ld, m_valid, tokens_out, st);
+  if (e != cudaSuccess) return cuda_fail(e, "reduce_candidates launch");
+  return DFLASH_OK;
+}
+
 int dflash_draft_step_candidates(dflash_engine_t* e, int n_candidates, int fixed_prefix_len, void* stream) {
   if (!e) { set_error("draft_step_candidates: null engine"); return DFLASH_ERR_ARG; }
   if (n_candidates < 2 || n_candidates > e->impl->max_cand || fixed_prefix_len < 0) {

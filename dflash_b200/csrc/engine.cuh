@@ -40,6 +40,8 @@ struct Engine {
   std::vector<GemmPlan> o, gu, d;
   GemmPlan lm;
   GemmPlan lm_topk;             // same GEMM with the top-4 epilogue (multi-candidate drafting)
+  GemmPlan lm_sample;           // same GEMM with the Gumbel-max epilogue (draft tokens sampled at temperature > 0)
+  bool has_sample = false;
   int max_cand = 1;
   // persistent draft-step kernel (step_mega.cuh): tables live in the workspace
   bool mega = false;
@@ -325,6 +327,14 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->lm.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
   e->lm.args.logits = c.keep_draft_logits ? e->buf<__nv_bfloat16>(DFLASH_BUF_DRAFT_LOGITS) : nullptr;
   e->lm.args.logits_ld = e->V;
+  if (mb_blk <= 32) {
+    DFL_PLAN(make_gemm_plan(&e->lm_sample, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
+                            kModeSample, e->grid));
+    e->lm_sample.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
+    e->lm_sample.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
+    e->lm_sample.args.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
+    e->has_sample = true;
+  }
   e->max_cand = c.max_candidates > 1 ? c.max_candidates : 1;
   if (e->max_cand > 1) {
     DFL_PLAN(make_gemm_plan(&e->lm_topk, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
@@ -449,8 +459,10 @@ inline int enqueue_draft_step_mega(Engine* e, cudaStream_t st);
 
 // n_candidates > 1: top-4 lm_head epilogue + candidate blocks (fixed_prefix_rank) instead of the plain argmax tail
 inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st,
-                              int n_candidates = 1, int fixed_prefix_len = 0) {
-  if (e->mega && noise_embedding == nullptr && run_lm_head && n_candidates <= 1) return enqueue_draft_step_mega(e, st);
+                              int n_candidates = 1, int fixed_prefix_len = 0, float draft_temperature = 0.f,
+                              unsigned long long draft_seed = 0) {
+  if (e->mega && noise_embedding == nullptr && run_lm_head && n_candidates <= 1 && draft_temperature < 1e-5f)
+    return enqueue_draft_step_mega(e, st);
   const int RS = e->RS;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
@@ -581,7 +593,16 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     DFL_CUDA(launch_pdl(candidates_kernel, dim3(e->R), dim3(256), 0, st, e->pdl, ca), "candidate blocks");
     return DFLASH_OK;
   }
-  if (!(dbg_skip() & 64)) DFL_CUDA(launch_gemm(e->lm, st, e->pdl), "lm_head gemm");
+  const bool sampled = draft_temperature >= 1e-5f;
+  if (sampled) {
+    GemmPlan p = e->lm_sample;
+    p.args.inv_temp = 1.0f / draft_temperature;
+    p.args.seed = draft_seed;
+    p.args.step_base = 0;
+    DFL_CUDA(launch_gemm(p, st, e->pdl), "lm_head sampling gemm");
+  } else if (!(dbg_skip() & 64)) {
+    DFL_CUDA(launch_gemm(e->lm, st, e->pdl), "lm_head gemm");
+  }
   DraftTokArgs ta;
   ta.cand_val = e->lm.args.cand_val;
   ta.cand_idx = e->lm.args.cand_idx;

@@ -98,6 +98,13 @@ inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pd
 }
 
 inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl) {
+  if (p.mode == kModeSample) {
+    switch (p.mb) {
+      case 16: return launch_gemm_t<16, kModeSample>(p, stream, pdl);
+      case 32: return launch_gemm_t<32, kModeSample>(p, stream, pdl);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (p.mode == kModeTopK) {
     switch (p.mb) {
       case 16: return launch_gemm_t<16, kModeTopK>(p, stream, pdl);

@@ -35,6 +35,8 @@ enum GemmMode : int {
                         // out of the hot instantiation's registers)
   kModeTopK = 3,      // whole tiles per CTA; per-CTA top-4 of the bf16-rounded logits per activation row
                       // (multi-candidate drafting: benchmark_candidate_solutions.py:181-249)
+  kModeSample = 4,    // whole tiles per CTA; per-CTA argmax of  logit / T + Gumbel noise  per activation row = a draw
+                      // from softmax(logits / T) (Gumbel-max, the construction the posterior sampler uses too)
 };
 constexpr int kTopK = 4;
 
@@ -71,6 +73,11 @@ struct GemmArgs {
   // launched side by side and share it through L2 (HBM sees every weight byte once per step).
   int groups;          // >= 1
   int cand_ld;         // kModeArgmax: row pitch of cand_val/cand_idx (= groups * MB)
+  // kModeSample
+  float inv_temp;                        // 1 / temperature
+  unsigned long long seed;               // Philox key
+  unsigned long long step_base;          // Philox counter words 2-3 = step_base + *rng_step
+  const unsigned long long* rng_step;    // optional device counter (bumped once per cycle by the accept kernel)
 };
 
 // The CTA that owns flat unit x when T units are cut into G ranges [floor(g*T/G), floor((g+1)*T/G)).
@@ -319,11 +326,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     // so that keeping the best is ONE integer max per logit, and a tie keeps the lower tile = the lower vocab
     // index (this thread's weight row inside the tile is fixed). Decoded and reduced over threads at the end.
     constexpr int kKeep = MODE == kModeTopK ? kTopK : 1;  // running bests per activation row (sorted, descending)
+    constexpr bool kSample = MODE == kModeSample;
     uint32_t best[kArgmax ? kCols * kKeep : 1];
+    float bestf[kSample ? kCols : 1];  // kModeSample: fp32 perturbed key per row (best[] then holds its tile)
     if (kArgmax) {
 #pragma unroll
       for (int j = 0; j < kCols * kKeep; ++j) best[j] = 0u;
     }
+    if (kSample) {
+#pragma unroll
+      for (int j = 0; j < kCols; ++j) bestf[j] = -INFINITY;
+    }
+    unsigned long long rstep = 0;
+    if (kSample) rstep = a.step_base + (a.rng_step != nullptr ? *a.rng_step : 0ull);
 
     long long u = u0;
     while (u < u1) {
@@ -394,6 +409,27 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
               if (m < mv) dst[static_cast<long long>(m) * a.ws_ld] = v[j];
             }
           }
+        } else if (kSample) {
+          if (n < a.N) {
+#pragma unroll
+            for (int j4 = 0; j4 < kChunk; j4 += 4) {
+              // one Philox call per (vocab row n, group of four activation rows): four uniforms in (0, 1]
+              uint32_t rnd[4];
+              philox4x32(static_cast<uint32_t>(n), static_cast<uint32_t>((m0 + col0 + c * kChunk + j4) >> 2),
+                         static_cast<uint32_t>(rstep), static_cast<uint32_t>(rstep >> 32) ^ 0x40000000u,
+                         static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32), rnd);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int j = j4 + q;
+                const float e = -__logf(u32_to_unit(rnd[q]));                       // Exp(1)
+                const float key = bf16_round(v[j]) * a.inv_temp - logf(fmaxf(e, 1e-30f));  // = logit/T + Gumbel
+                if (key > bestf[kSample ? c * kChunk + j : 0]) {
+                  bestf[kSample ? c * kChunk + j : 0] = key;
+                  best[kSample ? c * kChunk + j : 0] = static_cast<uint32_t>(tile);
+                }
+              }
+            }
+          }
         } else if (n < a.N) {
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) {
@@ -424,7 +460,28 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
     if (tr && threadIdx.x == 0) tr[6] = global_ns();
 
-    if (kArgmax) {
+    if (kSample) {
+      // reduce (perturbed key, tile) over the 128 weight rows through the idle pipeline smem
+      constexpr int kPitchS = MB + 1;
+      float* skey = reinterpret_cast<float*>(smem);
+      uint32_t* stile = reinterpret_cast<uint32_t*>(smem) + kTileN * kPitchS;
+#pragma unroll
+      for (int j = 0; j < (kSample ? kCols : 1); ++j) {
+        skey[row_in_tile * kPitchS + col0 + j] = bestf[j];
+        stile[row_in_tile * kPitchS + col0 + j] = best[j];
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kEpiWarps * 32) : "memory");
+      for (int j = epi_tid; j < MB; j += Cfg::kEpiWarps * 32) {
+        float bk = -INFINITY;
+        int bn = 0x7fffffff;
+        for (int r = 0; r < kTileN; ++r) {
+          const float k = skey[r * kPitchS + j];
+          if (k > bk) { bk = k; bn = static_cast<int>(stile[r * kPitchS + j]) * kTileN + r; }
+        }
+        a.cand_val[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bk;
+        a.cand_idx[static_cast<long long>(cta) * a.cand_ld + m0 + j] = bn;
+      }
+    } else if (kArgmax) {
       // Reduce over the 128 weight rows of the tile shape through shared memory (the pipeline stages are idle by
       // now): keys[row][col], padded pitch so that both the row-wise writes and the column-wise reads are
       // conflict-free. Rows are visited in ascending order with a strict compare, so among equal keys (same value,

@@ -10,24 +10,6 @@
 
 namespace dfl {
 
-// ------------------------------------------------------------------------------------ Philox4x32-10
-__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                           uint32_t k1, uint32_t* out) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1]
-  return (static_cast<float>(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
-}
-
 struct PosteriorArgs {
   const __nv_bfloat16* logits;  // [rows][ld]
   long long ld;

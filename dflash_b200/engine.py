@@ -72,6 +72,11 @@ def _declare(lib):
     lib.dflash_verify_step.restype = c_int
     lib.dflash_verify_step.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, POINTER(c_void_p), c_float,
                                        c_void_p, c_ulonglong, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
+    lib.dflash_draft_step_sampled.restype = c_int
+    lib.dflash_draft_step_sampled.argtypes = [c_void_p, c_float, c_ulonglong, c_void_p]
+    lib.dflash_gemm_sample.restype = c_int
+    lib.dflash_gemm_sample.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                       c_ulonglong, c_ulonglong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.dflash_draft_step_candidates.restype = c_int
     lib.dflash_draft_step_candidates.argtypes = [c_void_p, c_int, c_int, c_void_p]
     lib.dflash_verify_step_candidates.restype = c_int
@@ -299,6 +304,12 @@ class DraftEngine:
                                                float(temperature), _p(noise), int(seed) & (2**64 - 1), _p(stop_ids),
                                                n_stop, _p(forced_k), fld, int(clamp_tail), _stream()),
                    "dflash_verify_step")
+
+    def draft_step_sampled(self, temperature: float, seed: int = 0):
+        """Draft step whose tokens are drawn from softmax(draft_logits / temperature) in the lm_head epilogue
+        (benchmark_dynamic_schedule.py:342); temperature 0 = the greedy step."""
+        _lib.check(self.lib.dflash_draft_step_sampled(self.handle, float(temperature), int(seed) & (2**64 - 1),
+                                                      _stream()), "dflash_draft_step_sampled")
 
     def draft_step_candidates(self, n_candidates: int, fixed_prefix_len: int):
         """Draft step with the top-4 lm_head epilogue; fills cand_ids[:, :n_candidates] / cand_scores

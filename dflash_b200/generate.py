@@ -28,10 +28,13 @@ def cuda_time() -> float:
 @torch.inference_mode()
 def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, max_new_tokens: int, block_size: int,
                     stop_token_ids: Optional[List[int]], temperature: float = 0.0, collect_profile: bool = False,
-                    draft_steps: int = 1, seed: Optional[int] = None, scheduler=None) -> SimpleNamespace:
+                    draft_steps: int = 1, seed: Optional[int] = None, scheduler=None,
+                    draft_temperature: float = 0.0) -> SimpleNamespace:
     """`scheduler` (optional, `dflash_b200.schedule.EwmaBlockScheduler`): per-cycle block-size policy, the
     reference's `dflash_generate_policy` (benchmark_dynamic_schedule.py:260-434). `block_size` must then be the
-    largest candidate: the engine is built for it and a smaller block is a shorter device-side `blk_len`."""
+    largest candidate: the engine is built for it and a smaller block is a shorter device-side `blk_len`.
+    `draft_temperature` > 0 samples the DRAFTED tokens from softmax(draft_logits / T) in the lm_head epilogue, as that
+    policy loop does (benchmark_dynamic_schedule.py:342); `spec_generate` / `benchmark.py` always draft greedily."""
     if draft_steps != 1:
         raise NotImplementedError("draft_steps > 1 (cache-less block refinement, benchmark.py:114-142) is a research "
                                   "variant outside the draft-and-verify hot path")
@@ -98,7 +101,10 @@ def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, 
                 if collect_profile:
                     draft_ev = (ev(), ev())
                     draft_ev[0].record()
-                eng.draft_step_graphed()  # embed -> ctx injection -> layers -> lm_head + argmax (benchmark.py:110-140)
+                if draft_temperature >= 1e-5:
+                    eng.draft_step_sampled(draft_temperature, seed ^ 0x2545F491)
+                else:
+                    eng.draft_step_graphed()  # embed -> ctx injection -> layers -> lm_head + argmax (benchmark.py:110-140)
                 if collect_profile:
                     draft_ev[1].record()
                 if draft_prefill:

@@ -191,6 +191,12 @@ int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long 
                        const float* noise, unsigned long long seed, const long long* stop_ids, int n_stop,
                        const int* forced_k, int forced_ld, int clamp_tail, void* stream);
 
+/* dflash_draft_step with the drafted tokens SAMPLED from softmax(draft_logits / temperature) instead of argmax-ed
+ * (the reference's policy loop does that: benchmark_dynamic_schedule.py:342; spec_generate itself always drafts
+ * greedily). Gumbel-max inside the lm_head epilogue -- key = bf16(logit) / T + Gumbel(Philox(seed, cycle, row, vocab))
+ * -- so the logits still never reach HBM. temperature < 1e-5 is the plain greedy step. */
+int dflash_draft_step_sampled(dflash_engine_t* e, float temperature, unsigned long long seed, void* stream);
+
 /* Multi-candidate drafting ("fixed_prefix_rank", benchmark_candidate_solutions.py:181-249): the draft step with a
  * top-4 lm_head epilogue; builds n_candidates (2..4) candidate blocks per request in DFLASH_BUF_CAND_IDS: candidate 0
  * is the greedy block, candidate k keeps the first fixed_prefix_len positions and takes the rank-(k+1) token at every
@@ -235,6 +241,12 @@ int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K
 int dflash_gemm_argmax(const void* W, int w_rows_total, int N, int K, const void* X, int x_rows_total,
                        int x_row0, int mb, int m_valid, float* cand_val, int* cand_idx, void* logits,
                        long long logits_ld, long long* tokens_out, int grid, int use_pdl, void* stream);
+
+/* tokens_out[m] ~ softmax(bf16(X[m] . W^T) / temperature): the Gumbel-max epilogue as a raw operator (mb <= 32);
+ * `step` selects the noise stream (the engine uses its cycle counter). */
+int dflash_gemm_sample(const void* W, int w_rows_total, int N, int K, const void* X, int x_rows_total, int x_row0,
+                       int mb, int m_valid, float temperature, unsigned long long seed, unsigned long long step,
+                       float* cand_val, int* cand_idx, long long* tokens_out, int grid, int use_pdl, void* stream);
 
 /* Debug only (scripts/gemm_trace.py): dflash_gemm_skinny without the slot sum, recording per-CTA phase timestamps
  * (globaltimer ns) into trace[ranges * groups][8]: kernel entry, prologue done, producer past griddepcontrol.wait,

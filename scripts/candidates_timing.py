@@ -46,4 +46,10 @@ def cands():
     eng.draft_step_candidates(4, 2)
 
 
+def sampled():
+    eng.block_ids.copy_(mask)
+    eng.draft_step_sampled(1.0, 7)
+
+
+print(f"draft step, Gumbel-max sampling epilogue (T = 1): {timed(sampled):.1f} us")
 print(f"draft step, argmax epilogue: {timed(plain):.1f} us; top-4 epilogue + 4 candidate blocks: {timed(cands):.1f} us")

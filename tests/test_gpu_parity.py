@@ -100,6 +100,58 @@ def test_gemm_argmax_column_groups(mb, rows):
     assert toks.cpu().tolist() == logits.float().cpu().argmax(-1).tolist()
 
 
+def test_gemm_sample_epilogue_distribution_and_greedy_limit():
+    """Gumbel-max in the lm_head epilogue: tokens ~ softmax(bf16 logits / T) (chi-square over 6400 draws), a different
+    draw per step / seed, and the argmax in the T -> 0 limit."""
+    dev = _cuda()
+    from dflash_b200 import _lib
+    from dflash_b200.engine import _declare
+    lib = _lib.load()
+    _declare(lib)
+    torch.manual_seed(3)
+    V, K, mb = 300, 128, 16  # three tiles, the last one partial
+    W = (torch.randn(V, K, device=dev) * 0.25).to(torch.bfloat16)
+    x = torch.randn(1, K, device=dev).to(torch.bfloat16)
+    X = x.repeat(mb, 1).contiguous()  # sixteen identical rows: sixteen draws from one distribution per launch
+    logits = (x.float() @ W.float().t()).to(torch.bfloat16).float()[0]
+    T = 0.8
+    p = torch.softmax(logits / T, -1).cpu()
+    grid = 148
+    cv = torch.empty(grid, mb, dtype=torch.float32, device=dev)
+    ci = torch.empty(grid, mb, dtype=torch.int32, device=dev)
+    toks = torch.empty(mb, dtype=torch.int64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    counts = torch.zeros(V)
+    draws = []
+    for step in range(400):
+        _lib.check(lib.dflash_gemm_sample(_ptr(W), V, V, K, _ptr(X), mb, 0, mb, mb, T, 1234, step, _ptr(cv), _ptr(ci),
+                                          _ptr(toks), grid, 0, st))
+        t = toks.cpu()
+        draws.append(t.tolist())
+        counts += torch.bincount(t, minlength=V).float()
+    assert int(counts.sum()) == 6400 and counts[V:].sum() == 0
+    assert len({tuple(d) for d in draws}) > 350          # fresh noise per step
+    assert len(set(draws[0])) > 1                          # and per activation row
+    # chi-square with the tail merged so that every expected count is >= 8
+    order = torch.argsort(p, descending=True)
+    exp, obs, k = [], [], 0
+    while k < V and p[order[k]] * 6400 >= 8:
+        exp.append(float(p[order[k]] * 6400)); obs.append(float(counts[order[k]])); k += 1
+    exp.append(float(p[order[k:]].sum() * 6400)); obs.append(float(counts[order[k:]].sum()))
+    chi2 = sum((o - e) ** 2 / e for o, e in zip(obs, exp))
+    dof = len(exp) - 1
+    assert dof >= 10 and chi2 < dof + 5 * (2 * dof) ** 0.5, (chi2, dof)
+    # another seed: a different stream; T -> 0: the argmax
+    _lib.check(lib.dflash_gemm_sample(_ptr(W), V, V, K, _ptr(X), mb, 0, mb, mb, T, 99, 0, _ptr(cv), _ptr(ci), _ptr(toks),
+                                      grid, 0, st))
+    assert toks.cpu().tolist() != draws[0]
+    _lib.check(lib.dflash_gemm_sample(_ptr(W), V, V, K, _ptr(X), mb, 0, mb, mb, 1e-3, 1, 0, _ptr(cv), _ptr(ci),
+                                      _ptr(toks), grid, 0, st))
+    top2 = torch.topk(logits, 2).values
+    if (top2[0] - top2[1]).item() > 0.05:
+        assert toks.cpu().tolist() == [int(logits.argmax())] * mb
+
+
 def test_gemm_argmax_matches_own_logits():
     dev = _cuda()
     from dflash_b200 import _lib
@@ -603,6 +655,39 @@ def test_dflash_generate_twin_of_benchmark_loop():
     draft.release_engine()
 
 
+def test_draft_step_sampled_in_engine():
+    """dflash_draft_step_sampled: temperature 0 is the greedy step; at temperature 1 the drafted tokens are valid vocab
+    ids that change from cycle to cycle (the noise is keyed by the device-side cycle counter)."""
+    dev = _cuda()
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY
+    bs = 16
+    target, draft = _tiny(bs)
+    H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
+    g = torch.Generator(device=dev).manual_seed(2)
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=256, out_len=256,
+                      max_requests=1, block_size=bs)
+    hs = [(torch.randn(20, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+    eng.reset_request(0, torch.randint(0, V - 1, (20,), device=dev, generator=g), 4, 100)
+    eng.prefill_context(0, hs)
+    blk0 = eng.block_ids.clone()
+    eng.draft_step()
+    greedy = eng.block_ids.clone()
+    eng.block_ids.copy_(blk0)
+    eng.draft_step_sampled(0.0)
+    assert torch.equal(eng.block_ids, greedy)
+    seen = set()
+    for cyc in range(6):
+        eng.block_ids.copy_(blk0)
+        eng.draft_step_sampled(1.0, seed=5)
+        toks = eng.block_ids[0].cpu().tolist()
+        assert toks[0] == 4 and all(0 <= t < V for t in toks[1:])
+        seen.add(tuple(toks))
+        eng.buf["rng_step"] += 1  # what the accept kernel does once per cycle
+    assert len(seen) == 6 and tuple(greedy[0].cpu().tolist()) not in seen
+    eng.close()
+
+
 def test_dflash_generate_with_block_size_scheduler():
     """the block size is chosen per cycle by a host policy; every choice is a device-side blk_len.
     Output stays the target's greedy continuation for any schedule (verification is lossless)."""
@@ -630,6 +715,14 @@ def test_dflash_generate_with_block_size_scheduler():
             assert _near_tie(logits[t], pred[t].item(), tok), (t, pred[t].item(), tok)
     with pytest.raises(ValueError):
         dflash_generate(draft, target, prompt, draft.mask_token_id, 8, 16, None, 0.0, scheduler=sched)
+    # sampled drafts (the policy loop's `sample(draft_logits, temperature)`): verification keeps the output the target's
+    res2 = dflash_generate(draft, target, prompt, draft.mask_token_id, 40, 16, None, 0.0, draft_temperature=1.0, seed=3)
+    assert res2.num_output_tokens == 40
+    n = min(res2.output_ids.shape[1], res.output_ids.shape[1])
+    diff = (res2.output_ids[0, :n] != res.output_ids[0, :n]).nonzero()
+    if diff.numel():
+        t = int(diff[0]) - 1
+        assert _near_tie(logits[t], res2.output_ids[0, t + 1].item(), res.output_ids[0, t + 1].item())
     draft.release_engine()
 
 

@@ -786,48 +786,57 @@ def test_topk_epilogue_and_candidate_blocks_vs_oracle(bs, prefix):
     eng.close()
 
 
-def test_verify_candidates_choice_commit_and_gather():
-    """K candidates verified by one (synthetic) target forward: chosen index, commit, posterior, state and the context
-    rows gathered from the chosen candidate, against the oracle's restatement of the reference's choice rule."""
+@pytest.mark.parametrize("R", [1, 2])
+def test_verify_candidates_choice_commit_and_gather(R):
+    """K candidates per request verified by one (synthetic) target forward: chosen index, commit, posterior, state and
+    the context rows gathered from the chosen candidate, against the oracle's restatement of the reference's choice
+    rule. R = 2: two request streams, rows ordered [request][candidate][slot]."""
     from oracle import dflash_oracle as O
+    from dflash_b200.engine import DraftEngine
     bs, K = 16, 4
     dev, target, draft, H, V, nsel, g, mk = _cand_engine(bs)
-    eng = mk(False)
-    hs = [(torch.randn(17, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
-    eng.reset_request(0, torch.randint(0, V - 1, (17,), device=dev, generator=g), 5, 200)
-    eng.prefill_context(0, hs)
-    start = 17
-    for cyc, force in enumerate([[3, 9, 1, 9], [0, 0, 0, 0], [2, 5, 14, 7], [15, 15, 3, 3], [6, 2, 2, 11]]):
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=256, out_len=256,
+                      max_requests=R, block_size=bs, max_candidates=K)
+    starts = [17 + 6 * r for r in range(R)]
+    for r in range(R):
+        hs = [(torch.randn(starts[r], H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        eng.reset_request(r, torch.randint(0, V - 1, (starts[r],), device=dev, generator=g), 5 + r, 200)
+        eng.prefill_context(r, hs)
+    plans = [[3, 9, 1, 9], [0, 0, 0, 0], [2, 5, 14, 7], [15, 15, 3, 3], [6, 2, 2, 11]]
+    for cyc in range(len(plans)):
         eng.draft_step_candidates(K, 2)
         torch.cuda.synchronize()
-        cands = eng.cand_ids[0].clone().cpu()
-        scores = eng.cand_scores[0].cpu().tolist()
-        # target logits whose argmax agrees with candidate k on exactly force[k] positions
-        tl = torch.randn(K * bs, V, device=dev, generator=g)
-        for k in range(K):
-            for i in range(bs):
-                nxt = int(cands[k, i + 1]) if i + 1 < bs else 0
-                tok = nxt if i < force[k] else (nxt + 1 + i) % V
-                tl[k * bs + i, tok] += 20.0
+        cands = eng.cand_ids.clone().cpu()          # [R, 4, bs]
+        scores = eng.cand_scores.cpu().tolist()
+        force = [plans[(cyc + r) % len(plans)] for r in range(R)]
+        # target logits whose argmax agrees with candidate k of request r on exactly force[r][k] positions
+        tl = torch.randn(R * K * bs, V, device=dev, generator=g)
+        for r in range(R):
+            for k in range(K):
+                for i in range(bs):
+                    nxt = int(cands[r, k, i + 1]) if i + 1 < bs else 0
+                    tok = nxt if i < force[r][k] else (nxt + 1 + i) % V
+                    tl[(r * K + k) * bs + i, tok] += 20.0
         tl = tl.to(torch.bfloat16)
-        hsel = [(torch.randn(K * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        hsel = [(torch.randn(R * K * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
         eng.verify_step_candidates(K, tl, hsel)
         torch.cuda.synchronize()
-        post_all = tl.float().argmax(-1).view(K, bs).cpu()
-        chosen, acc = O.choose_candidate(cands, post_all, scores)
-        assert acc == [min(f, bs - 1) for f in force]
-        assert int(eng.buf["chosen"][0]) == chosen, (cyc, acc, scores)
-        a = acc[chosen]
-        assert eng.posterior[0].cpu().tolist() == post_all[chosen].tolist()
-        out = eng.output_ids[0].cpu()
-        assert out[start:start + a + 1].tolist() == cands[chosen, :a + 1].tolist()
-        assert int(out[start + a + 1]) == int(post_all[chosen, a])
-        start += a + 1
-        assert int(eng.buf["start"][0]) == start and int(eng.buf["ctx_len"][0]) == a + 1
-        feat = eng.buf["ctx_feat"].view(eng.SL, -1)[:a + 1]
-        ref_feat = torch.cat([h[chosen * bs: chosen * bs + a + 1] for h in hsel], dim=-1)
-        assert torch.equal(feat, ref_feat)
-        assert eng.block_ids[0].cpu().tolist() == [int(post_all[chosen, a])] + [draft.mask_token_id] * (bs - 1)
+        post_all = tl.float().argmax(-1).view(R, K, bs).cpu()
+        for r in range(R):
+            chosen, acc = O.choose_candidate(cands[r], post_all[r], scores[r])
+            assert acc == [min(f, bs - 1) for f in force[r]]
+            assert int(eng.buf["chosen"][r]) == chosen, (cyc, r, acc, scores[r])
+            a = acc[chosen]
+            assert eng.posterior[r].cpu().tolist() == post_all[r, chosen].tolist()
+            out = eng.output_ids[r].cpu()
+            assert out[starts[r]:starts[r] + a + 1].tolist() == cands[r, chosen, :a + 1].tolist()
+            assert int(out[starts[r] + a + 1]) == int(post_all[r, chosen, a])
+            starts[r] += a + 1
+            assert int(eng.buf["start"][r]) == starts[r] and int(eng.buf["ctx_len"][r]) == a + 1
+            feat = eng.buf["ctx_feat"].view(R * eng.SL, -1)[r * eng.SL: r * eng.SL + a + 1]
+            row0 = (r * K + chosen) * bs
+            assert torch.equal(feat, torch.cat([h[row0: row0 + a + 1] for h in hsel], dim=-1))
+            assert eng.block_ids[r].cpu().tolist() == [int(post_all[r, chosen, a])] + [draft.mask_token_id] * (bs - 1)
     eng.close()
 
 

@@ -26,7 +26,6 @@ namespace dfl {
 constexpr int kTileN = 128;   // weight rows per tile (UMMA M)
 constexpr int kTileK = 64;    // bf16 elements per k-block (= one 128-byte swizzle row)
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;  // default role layout: warps 0-3 epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc
 
 enum GemmMode : int {
   kModePartials = 0,  // write fp32 partial sums to ws[slot][m][n]

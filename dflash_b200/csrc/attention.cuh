@@ -306,8 +306,7 @@ __device__ __forceinline__ void attn_combine_item(const AttnArgs& a, int item, i
 }
 
 __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnArgs a) {
-  pdl_wait();
-  pdl_trigger();
+  DFL_WAIT_THEN_TRIGGER();
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (item >= a.R * a.SL * a.Hq) return;
   attn_combine_item(a, item, threadIdx.x & 31);

@@ -305,8 +305,7 @@ __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsA
   __syncthreads();
   // wait first, trigger second: the GEMM behind this kernel then becomes resident exactly when this
   // kernel starts its real work
-  pdl_wait();
-  pdl_trigger();
+  DFL_WAIT_THEN_TRIGGER();
   finalize_row_body<kRowsThreads, true>(a, blockIdx.x, threadIdx.x, rowbuf, red, ns_tab, 0);
 }
 
@@ -324,8 +323,7 @@ __global__ void __launch_bounds__(kRowsThreads) finalize_rows2_kernel(const Rows
     for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
   }
   __syncthreads();
-  pdl_wait();
-  pdl_trigger();
+  DFL_WAIT_THEN_TRIGGER();
   finalize_row_body<kRowsThreads, true>(a, first ? blockIdx.x : blockIdx.x - rows0, threadIdx.x, rowbuf, red, ns_tab, 0);
 }
 
@@ -388,8 +386,7 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const SwigluArgs a) {
     ns_g = tile_slots32(n / kTileN, a.sm);
     ns_u = tile_slots32((a.I + n) / kTileN, a.sm);
   }
-  pdl_wait();
-  pdl_trigger();
+  DFL_WAIT_THEN_TRIGGER();
   if (n >= a.I) return;
   const float4 g = sum_slots_4(a.ws, a.sm, m, n, ns_g);
   const float4 u = sum_slots_4(a.ws, a.sm, m, a.I + n, ns_u);

@@ -162,6 +162,14 @@ __device__ __forceinline__ void pdl_trigger() {
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 }
 
+// Small kernels in front of a GEMM: wait for the producer first, release the dependent GEMM second, so that the GEMM
+// becomes resident exactly when this kernel starts its real work (measured against trigger-first: DESIGN.md §7).
+#ifdef DFLASH_TRIGGER_FIRST
+#define DFL_WAIT_THEN_TRIGGER() do { pdl_trigger(); pdl_wait(); } while (0)
+#else
+#define DFL_WAIT_THEN_TRIGGER() do { pdl_wait(); pdl_trigger(); } while (0)
+#endif
+
 // named barrier over `nthreads` threads of the CTA (id 0 with blockDim.x threads == __syncthreads)
 __device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");

@@ -259,14 +259,13 @@ __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt
 }
 
 __global__ void attn_split_kernel(const AttnArgs a) {
-  pdl_trigger();
   extern __shared__ __align__(128) uint8_t attn_smem[];
   const int tiles_per_req = a.SL / 16;
   const int r = blockIdx.z / tiles_per_req;
   // the key range comes from request state that only the previous step's accept kernel writes: read it while the
   // kernel in front of this one (qkv_post) is still running
   const int L = a.start[r] + a.blk_len[r];
-  pdl_wait();
+  DFL_WAIT_THEN_TRIGGER();
   attn_split_body<2>(a, r, blockIdx.z % tiles_per_req, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x,
                      smem_u32(attn_smem), 0, L);
 }

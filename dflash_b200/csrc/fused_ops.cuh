@@ -166,8 +166,7 @@ __device__ __forceinline__ void draft_tokens_row(const DraftTokArgs& a, int row,
 }
 
 __global__ void __launch_bounds__(32) draft_tokens_kernel(const DraftTokArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  DFL_VERIFY_SYNC();
   draft_tokens_row(a, blockIdx.x, threadIdx.x);
 }
 
@@ -521,7 +520,6 @@ __device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, in
 }
 
 __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
-  pdl_trigger();
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int heads_per_row = a.q_cols / 128 + 2 * a.Hkv;
   const int lane = threadIdx.x & 31;
@@ -529,7 +527,7 @@ __global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
   it.kind = -1;
   // positions, rope table and norm weights while the QKV GEMM in front of this kernel is still running
   if (item < a.rows * heads_per_row) it = qkv_post_prepare(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
-  pdl_wait();
+  DFL_WAIT_THEN_TRIGGER();
   qkv_post_apply(a, it, lane);
 }
 

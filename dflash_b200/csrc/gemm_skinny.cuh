@@ -210,7 +210,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   if (tr && threadIdx.x == 0) tr[1] = global_ns();
   // Let the next kernel in the stream start its own prologue / weight prefetch right away.
+#ifndef DFLASH_GEMM_LATE_TRIGGER
   pdl_trigger();
+#endif
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -231,6 +233,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                     polW);
       }
       pdl_wait();
+#ifdef DFLASH_GEMM_LATE_TRIGGER
+      pdl_trigger();  // (experiment) the dependent small kernel becomes resident only once this GEMM really starts
+#endif
       if (tr) tr[2] = global_ns();
       for (int i = 0; i < npre; ++i) {
         const int kb = static_cast<int>((u0 + i) % a.k_blocks);

@@ -170,6 +170,13 @@ __device__ __forceinline__ void pdl_trigger() {
 #define DFL_WAIT_THEN_TRIGGER() do { pdl_wait(); pdl_trigger(); } while (0)
 #endif
 
+// the verify-side kernels and the token reduce (experiment switch: same ordering question)
+#ifdef DFLASH_VERIFY_WAIT_FIRST
+#define DFL_VERIFY_SYNC() do { pdl_wait(); pdl_trigger(); } while (0)
+#else
+#define DFL_VERIFY_SYNC() do { pdl_trigger(); pdl_wait(); } while (0)
+#endif
+
 // named barrier over `nthreads` threads of the CTA (id 0 with blockDim.x threads == __syncthreads)
 __device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");

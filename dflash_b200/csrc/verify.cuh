@@ -25,8 +25,7 @@ struct PosteriorArgs {
 // key_i = logit_i (greedy) or logit_i / T - log(e_i), e_i ~ Exp(1): argmax_i key_i is a draw from
 // softmax(logits / T) -- the same exponential race torch.multinomial runs (argmax(p / q)).
 __global__ void __launch_bounds__(256) posterior_kernel(const PosteriorArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  DFL_VERIFY_SYNC();
   const int row = blockIdx.y, split = blockIdx.x;
   int seg = (a.V + a.nsplit - 1) / a.nsplit;
   seg = (seg + 7) & ~7;
@@ -152,8 +151,7 @@ struct AcceptArgs {
 
 // One warp per request.
 __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  DFL_VERIFY_SYNC();
   const int r = blockIdx.x, lane = threadIdx.x;
   if (r == 0 && lane == 0 && a.rng_step != nullptr) *a.rng_step += 1ull;
   // every scalar of the request's state is requested up front: one L2 round trip instead of one per use
@@ -261,8 +259,7 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) ctx_gather_kernel(const GatherArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  DFL_VERIFY_SYNC();
   int rr = blockIdx.x / a.SL, j = blockIdx.x % a.SL;
   long long drow;
   if (a.pf_rows > 0) {
@@ -302,8 +299,7 @@ struct CandArgs {
 };
 
 __global__ void __launch_bounds__(256) candidates_kernel(const CandArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  DFL_VERIFY_SYNC();
   const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ int s_idx[32][4];
   __shared__ float s_val[32][4];

@@ -168,6 +168,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   unsigned long long* tr = a.trace ? a.trace + (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = global_ns();
+#ifdef DFLASH_GEMM_TOP_TRIGGER
+  pdl_trigger();  // (experiment) release the dependent before this kernel's own prologue
+#endif
   const long long T = static_cast<long long>(a.n_tiles) * a.k_blocks;
   const long long G = gridDim.y;           // weight ranges
   const int cta = blockIdx.y;              // this CTA's weight range
@@ -210,7 +213,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   if (tr && threadIdx.x == 0) tr[1] = global_ns();
   // Let the next kernel in the stream start its own prologue / weight prefetch right away.
-#ifndef DFLASH_GEMM_LATE_TRIGGER
+#if !defined(DFLASH_GEMM_LATE_TRIGGER) && !defined(DFLASH_GEMM_TOP_TRIGGER)
   pdl_trigger();
 #endif
 
@@ -224,15 +227,22 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const int npre = n_units < S ? static_cast<int>(n_units) : S;
       // weight tiles first: they do not depend on the predecessor kernel
       if (a.late_w == 1) pdl_wait();
-      for (int i = 0; i < npre; ++i) {
+#ifdef DFLASH_PREWAIT_STAGES   // (experiment) only this many weight tiles before griddepcontrol.wait, the rest after
+      const int n_early = npre < DFLASH_PREWAIT_STAGES ? npre : DFLASH_PREWAIT_STAGES;
+#else
+      const int n_early = npre;
+#endif
+      auto issue_w = [&](int i) {
         const long long u = u0 + i;
         const int tile = static_cast<int>(u / a.k_blocks);
         const int kb = static_cast<int>(u % a.k_blocks);
         mbar_expect_tx(&full[i], Cfg::kStageBytes);
         tma_load_2d(sW + i * Cfg::kWBytes, &tmW, &full[i], kb * kTileK, a.w_row0 + tile * kTileN,
                     polW);
-      }
+      };
+      for (int i = 0; i < n_early; ++i) issue_w(i);
       pdl_wait();
+      for (int i = n_early; i < npre; ++i) issue_w(i);
 #ifdef DFLASH_GEMM_LATE_TRIGGER
       pdl_trigger();  // (experiment) the dependent small kernel becomes resident only once this GEMM really starts
 #endif

@@ -192,7 +192,7 @@ class DraftEngine:
             vocab=self.vocab, n_sel=self.n_sel, block_size=self.block_size, max_requests=self.R,
             max_seq=int(max_seq), out_len=int(out_len), hist_len=int(hist_len), rms_eps=float(cfg.rms_norm_eps),
             rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id, attn_splits=attn_splits,
-            post_splits=0, gemm_grid=gemm_grid, use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits),
+            post_splits=0, gemm_grid=int(os.environ.get("DFLASH_GEMM_GRID", gemm_grid)), use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits),
             prefetch_mb=int(os.environ.get("DFLASH_PREFETCH_MB", prefetch_mb)),
             use_mega=int(os.environ.get("DFLASH_MEGA", "0")) if use_mega is None else int(use_mega),
             max_candidates=int(max_candidates))

@@ -200,7 +200,10 @@ struct RowsArgs {
   float eps;
 };
 
-constexpr int kRowsThreads = 512;
+#ifndef DFLASH_ROWS_THREADS
+#define DFLASH_ROWS_THREADS 512
+#endif
+constexpr int kRowsThreads = DFLASH_ROWS_THREADS;
 constexpr int kRowsMaxTiles = 64;  // H <= 8192
 
 // One CTA per row:  v = bf16(sum of partials)           (nn.Linear output dtype)

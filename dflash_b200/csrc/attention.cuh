@@ -304,9 +304,9 @@ __device__ __forceinline__ void attn_combine_item(const AttnArgs& a, int item, i
       make_uint2(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv));
 }
 
-__global__ void __launch_bounds__(256) attn_combine_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(32 * kItemWarps) attn_combine_kernel(const AttnArgs a) {
   DFL_WAIT_THEN_TRIGGER();
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int item = blockIdx.x * kItemWarps + (threadIdx.x >> 5);
   if (item >= a.R * a.SL * a.Hq) return;
   attn_combine_item(a, item, threadIdx.x & 31);
 }

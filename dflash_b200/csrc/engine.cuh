@@ -520,7 +520,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     aa.v_cache = qa.v_cache;
     if (e->fused_attn && !dbg_skip()) {
       if (e->fused_attn == 2)
-        DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
+        DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, qa), "qkv post");
       AttnFusedArgs fa;
       fa.post = qa;
       fa.attn = aa;
@@ -530,11 +530,11 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
                                   dim3(32 * (group + kFusedPostWarps)), dim3(kFusedSplits, 1, 1), attn_fused_smem(group), st, e->pdl, fa),
                "fused attention");
     } else {
-    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "qkv post");
+    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, qa), "qkv post");
     if (!(dbg_skip() & 16)) DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
                         kAttnSmem, st, e->pdl, aa),
              "attention");
-    if (!(dbg_skip() & 4)) DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + 7) / 8), dim3(256), 0, st, e->pdl, aa),
+    if (!(dbg_skip() & 4)) DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, aa),
              "attention combine");
     }
     if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
@@ -555,7 +555,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
       sa.rows = RS;
       sa.I = e->I;
       sa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
-      if (!(dbg_skip() & 2)) DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I / 4 + 255) / 256, RS), dim3(256), 0, st, e->pdl, sa), "swiglu");
+      if (!(dbg_skip() & 2)) DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I / 4 + kSwigluThreads - 1) / kSwigluThreads, RS), dim3(kSwigluThreads), 0, st, e->pdl, sa), "swiglu");
     }
     if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
     {
@@ -908,7 +908,7 @@ inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int n_ro
       qa.pf_req = r;
       qa.pf_pos0 = pos0 + c0;
       const int items = n * (2 * e->Hkv);
-      DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + 7) / 8), dim3(256), 0, st, e->pdl, qa), "prefill kv post");
+      DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, qa), "prefill kv post");
     }
   }
   SetStateArgs sa;

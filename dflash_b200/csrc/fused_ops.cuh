@@ -380,8 +380,8 @@ __device__ __forceinline__ void swiglu_items3(const SwigluArgs& a, int it0, int 
   }
 }
 
-__global__ void __launch_bounds__(256) swiglu_kernel(const SwigluArgs a) {
-  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+__global__ void __launch_bounds__(kSwigluThreads) swiglu_kernel(const SwigluArgs a) {
+  const int n = (blockIdx.x * kSwigluThreads + threadIdx.x) * 4;
   const int m = blockIdx.y;
   int ns_g = 1, ns_u = 1;  // slot counts do not depend on the GEMM's data: computed while waiting for it
   if (n < a.I) {
@@ -522,8 +522,8 @@ __device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, in
   qkv_post_rowhead(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
 }
 
-__global__ void __launch_bounds__(256) qkv_post_kernel(const QkvPostArgs a) {
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(32 * kItemWarps) qkv_post_kernel(const QkvPostArgs a) {
+  const int item = blockIdx.x * kItemWarps + (threadIdx.x >> 5);
   const int heads_per_row = a.q_cols / 128 + 2 * a.Hkv;
   const int lane = threadIdx.x & 31;
   QkvItem it;

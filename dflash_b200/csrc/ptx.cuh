@@ -177,6 +177,16 @@ __device__ __forceinline__ void pdl_trigger() {
 #define DFL_VERIFY_SYNC() do { pdl_trigger(); pdl_wait(); } while (0)
 #endif
 
+// block sizes of the small kernels (tuning switches; measured defaults)
+#ifndef DFLASH_SWIGLU_THREADS
+#define DFLASH_SWIGLU_THREADS 256
+#endif
+#ifndef DFLASH_WARPITEM_WARPS   // warps (= items) per CTA of the warp-per-item kernels qkv_post / attn_combine
+#define DFLASH_WARPITEM_WARPS 8
+#endif
+constexpr int kSwigluThreads = DFLASH_SWIGLU_THREADS;
+constexpr int kItemWarps = DFLASH_WARPITEM_WARPS;
+
 // named barrier over `nthreads` threads of the CTA (id 0 with blockDim.x threads == __syncthreads)
 __device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");

@@ -191,7 +191,8 @@ class DraftEngine:
             n_q_heads=cfg.num_attention_heads, n_kv_heads=cfg.num_key_value_heads, head_dim=head_dim,
             vocab=self.vocab, n_sel=self.n_sel, block_size=self.block_size, max_requests=self.R,
             max_seq=int(max_seq), out_len=int(out_len), hist_len=int(hist_len), rms_eps=float(cfg.rms_norm_eps),
-            rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id, attn_splits=attn_splits,
+            rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id,
+            attn_splits=int(os.environ.get("DFLASH_ATTN_SPLITS", attn_splits)),
             post_splits=0, gemm_grid=int(os.environ.get("DFLASH_GEMM_GRID", gemm_grid)), use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits),
             prefetch_mb=int(os.environ.get("DFLASH_PREFETCH_MB", prefetch_mb)),
             use_mega=int(os.environ.get("DFLASH_MEGA", "0")) if use_mega is None else int(use_mega),

@@ -196,7 +196,8 @@ def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, 
 def dflash_generate_candidates(model, target, input_ids: torch.Tensor, mask_token_id: int, max_new_tokens: int,
                                block_size: int, stop_token_ids: Optional[List[int]], *, fixed_prefix_len: int = 2,
                                rank_top_k: int = 4, max_candidates: int = 4, temperature: float = 0.0,
-                               candidate_mode: str = "fixed_prefix_rank") -> SimpleNamespace:
+                               candidate_mode: str = "fixed_prefix_rank", graph_target: bool = False,
+                               sync_every: int = 1) -> SimpleNamespace:
     """Multi-candidate speculative decoding, the reference's `dflash_generate_candidate_solutions`
     (benchmark_candidate_solutions.py:417-741) in its `fixed_prefix_rank` mode -- the variant the reference's
     results single out (`results.md:461-521`). Per cycle: the draft step keeps a top-4 per block row in the lm_head
@@ -204,7 +205,9 @@ def dflash_generate_candidates(model, target, input_ids: torch.Tensor, mask_toke
     of candidates, the target's KV cache repeated per candidate exactly as the reference does, :574-577); one kernel
     picks the candidate with the longest accepted prefix (ties: draft score, then index), commits it and gathers
     the next context features from its rows; the caller keeps that branch of the target cache (:610-614).
-    Greedy only, like the reference (:441-442)."""
+    Greedy only, like the reference (:441-442). graph_target=True: the batch-K verify forward replays from a CUDA graph
+    over a batch-K static cache (`GraphedCandidateTarget`): no per-cycle cache clone, the winning branch is kept by a
+    <= block_size-row copy on the device, and the host polls only every `sync_every` cycles."""
     if candidate_mode != "fixed_prefix_rank":
         raise NotImplementedError("only candidate_mode='fixed_prefix_rank' is on this path")
     if temperature >= 1e-5:
@@ -229,16 +232,25 @@ def dflash_generate_candidates(model, target, input_ids: torch.Tensor, mask_toke
     old_bs = model.block_size
     prefill_start = cuda_time()
     model.block_size = bs
+    gt = None
     try:
         eng = model._get_engine(target.model.embed_tokens.weight, target.lm_head.weight, max_seq=max_length + 2 * bs + 1,
                                 out_len=max_length + bs + 1, max_candidates=4)
-        with tap:
-            out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
-                         logits_to_keep=1)
-        first = sample(out.logits, 0.0)
+        if graph_target:
+            from .target_graph import GraphedCandidateTarget
+            cap = max(1024, 1 << (max_length + bs - 1).bit_length())
+            gt = GraphedCandidateTarget(target, bs, K, cap, model.target_layer_ids, eng.buf["start"][0:1],
+                                        eng.cand_ids[0, :K], eng.buf["chosen"][0:1])
+            logits0, hidden0 = gt.prefill(input_ids)
+        else:
+            with tap:
+                out = target(input_ids, position_ids=position_ids[:, :P], past_key_values=cache_t, use_cache=True,
+                             logits_to_keep=1)
+            logits0, hidden0 = out.logits, list(tap.states)
+        first = sample(logits0, 0.0)
         eng.reset_request(0, input_ids[0], first.view(-1)[0], max_new_tokens)
         eng.buf["blk_len"][0] = min(bs, max_new_tokens)
-        eng.prefill_context(0, [h[0] for h in tap.states])
+        eng.prefill_context(0, [h[0] for h in hidden0])
         time_to_first_token = cuda_time() - prefill_start
         decode_start = cuda_time()
         start = P
@@ -247,6 +259,29 @@ def dflash_generate_candidates(model, target, input_ids: torch.Tensor, mask_toke
         state = torch.empty(3, dtype=torch.int32).pin_memory()
         state_dev = torch.empty(3, dtype=torch.int32, device=dev)
         n_cand_sum = 0
+        cyc = 0
+        while gt is not None and start < max_length:
+            # device-driven cycle: draft (top-4 epilogue + candidate blocks) -> batch-K target graph -> verify kernels
+            eng.draft_step_candidates(K, fixed_prefix_len)
+            logits, hidden = gt.verify_forward()
+            if logits.dtype != torch.bfloat16:
+                logits = logits.to(torch.bfloat16)
+            eng.verify_step_candidates(K, logits, hidden, stop_ids=stop_t, clamp_tail=True)
+            cyc += 1
+            if cyc % max(1, sync_every):
+                continue  # blind cycles past the end are frozen on the device (`done`)
+            state_dev[0:1].copy_(eng.buf["start"][0:1])
+            state_dev[1:2].copy_(eng.buf["done"][0:1])
+            state.copy_(state_dev, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            start = int(state[0])
+            if int(state[1]):
+                break
+        if gt is not None:
+            n_cyc = int(eng.buf["n_cycles"][0])
+            acceptance_lengths = eng.acc_hist[0, :n_cyc].tolist()
+            n_cand_sum = K * n_cyc
+            start = max_length  # skip the eager loop below
         while start < max_length:
             eff = min(bs, max_length - start)
             if eff > 1:

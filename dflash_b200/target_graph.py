@@ -82,3 +82,65 @@ class GraphedVerifyTarget:
             self.capture()
         self.graph.replay()
         return self.logits, self.hidden
+
+
+class GraphedCandidateTarget(GraphedVerifyTarget):
+    """Multi-candidate verify on the graphed target: the K candidate blocks of a cycle are the K
+    rows of ONE batch-K forward over a batch-K static cache. The reference clones and repeats its whole `DynamicCache`
+    per cycle and selects the winning branch afterwards (`benchmark_candidate_solutions.py:574-577,610-614`); here all
+    K rows share the committed prefix by construction and only the last block differs, so keeping the winner is a
+    copy of <= block_size cache rows per layer -- done at the START of the next replay, from the engine's device-side
+    `chosen` / `start`, so the cycle still has no host round trip.
+
+    start_buf: device int32 [1]; cand_ids: device int64 [K, block_size] (engine buffer); chosen_buf: device int32 [1]."""
+
+    def __init__(self, target, block_size: int, n_candidates: int, max_cache_len: int, layer_ids: Sequence[int],
+                 start_buf: torch.Tensor, cand_ids: torch.Tensor, chosen_buf: torch.Tensor):
+        super().__init__(target, block_size, max_cache_len, layer_ids, start_buf, cand_ids)
+        self.K = int(n_candidates)
+        self.chosen_buf = chosen_buf
+        self.pos = torch.zeros(self.K, self.bs, dtype=torch.long, device=self.device)
+
+    def prefill(self, input_ids: torch.Tensor):
+        """The prompt goes through all K cache rows (identical rows: K x the prompt's compute, once)."""
+        logits, hidden = super().prefill(input_ids.expand(self.K, -1))
+        self.chosen_buf.zero_()
+        return logits[0:1], [h[0:1] for h in hidden]
+
+    def _forward(self):
+        start = self.start_buf[0:1].to(torch.long)
+        chosen = self.chosen_buf[0:1].to(torch.long)
+        # keep the previous cycle's winner: rows [start - bs, start) of batch row `chosen` -> every batch row. (The
+        # accepted tokens sit at [previous start, start) inside that window; older rows are equal already.)
+        idx = (self._arange[0] + start - self.bs).clamp_min(0)
+        for layer in self.cache.layers:
+            for t in (layer.keys, layer.values):
+                win = t.index_select(0, chosen).index_select(2, idx)        # [1, H, bs, D]
+                t.index_copy_(2, idx, win.expand(t.shape[0], -1, -1, -1))
+            layer.cumulative_length.copy_(start.view(layer.cumulative_length.shape).to(layer.cumulative_length.dtype))
+        self.pos.copy_((self._arange + start).expand(self.K, -1))
+        with ContextTap(self.target, self.layer_ids) as tap:
+            out = self.target(self.block_ids, position_ids=self.pos, past_key_values=self.cache, use_cache=True)
+        return out.logits, list(tap.states)
+
+    def verify_forward(self):
+        if self.graph is None:
+            self._capture_all()
+        self.graph.replay()
+        return self.logits, self.hidden
+
+    def _capture_all(self):
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._forward()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            logits, hidden = self._forward()
+        self.graph = g
+        self.logits = logits.reshape(self.K * self.bs, -1)
+        self.hidden = [h.reshape(self.K * self.bs, -1) for h in hidden]

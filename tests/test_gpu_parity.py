@@ -840,9 +840,11 @@ def test_verify_candidates_choice_commit_and_gather(R):
     eng.close()
 
 
-def test_dflash_generate_candidates_is_lossless():
+@pytest.mark.parametrize("graph_target", [False, True])
+def test_dflash_generate_candidates_is_lossless(graph_target):
     """The whole multi-candidate loop with the HF target (one batched verify forward per cycle, the chosen branch of the
-    target cache kept): greedy output is still the target's own greedy continuation."""
+    target cache kept): greedy output is still the target's own greedy continuation. graph_target: the batch-K forward
+    replays from a CUDA graph over a batch-K static cache; the winning branch is kept by a device-side row copy."""
     dev = _cuda()
     from dflash_b200 import dflash_generate, dflash_generate_candidates
     from tests.tiny_models import TINY
@@ -850,7 +852,8 @@ def test_dflash_generate_candidates_is_lossless():
     target, draft = _tiny(bs, rigged=True)
     prompt = torch.randint(0, TINY["vocab"] - 1, (1, 23), generator=torch.Generator().manual_seed(6)).to(dev)
     res = dflash_generate_candidates(draft, target, prompt, draft.mask_token_id, 48, bs, None, fixed_prefix_len=2,
-                                     rank_top_k=4, max_candidates=4)
+                                     rank_top_k=4, max_candidates=4, graph_target=graph_target,
+                                     sync_every=2 if graph_target else 1)
     assert res.output_ids.shape == (1, 23 + 48) and sum(res.acceptance_lengths) >= 48
     assert res.candidate_summary["avg_candidates_per_cycle"] == 4.0
     with torch.inference_mode():

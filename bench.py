@@ -36,15 +36,18 @@ QWEN3_4B = dict(hidden=2560, intermediate=9728, draft_layers=5, heads=32, kv_hea
 QWEN3_CODER_30B_A3B = dict(hidden=2048, intermediate=6144, draft_layers=8, heads=32, kv_heads=4, head_dim=128,
                            vocab=151936, target_layers=48, eps=1e-6, rope_theta=10_000_000.0, mask_token_id=151669,
                            block_size=16)
+if os.environ.get("DFLASH_BENCH_BS"):  # block-size sweep (BASELINE configs[4] shape): 8 / 16 / 32 slots per block
+    Q8 = dict(Q8, block_size=int(os.environ["DFLASH_BENCH_BS"]))
 PROMPT_LEN = 128
 MAX_NEW = 2048
 TAU_SCHEDULE_LEN = 64
 MEAN_TAU_TARGET = 7.3  # published Qwen3-8B-DFlash-b16 math-average acceptance length
 
 
-def forced_schedule(seed=0, n=TAU_SCHEDULE_LEN, bs=16):
+def forced_schedule(seed=0, n=TAU_SCHEDULE_LEN, bs=None):
     """Seeded per-cycle forced-acceptance counts k (tau = k + 1) with mean tau ~= 7.3."""
     import random
+    bs = Q8["block_size"] if bs is None else bs
     rng = random.Random(seed)
     ks = []
     for _ in range(n):
@@ -540,7 +543,7 @@ def run_cuda_arm(args):
             warmup=args.warmup, ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak",
             vs_baseline=None, dtype="bf16", data="synthetic",
             config=dict(workload="Qwen3-8B + DFlash-b16 draft+verify step (target forward excluded, SURVEY 8d), "
-                                 f"batch {R} per GPU, bs 16, prompt 128, up to 2048 new tokens, forced-tau schedule "
+                                 f"batch {R} per GPU, bs {bs}, prompt 128, up to 2048 new tokens, forced-tau schedule "
                                  f"mean {mean_tau:.2f} (BASELINE.json configs[1])",
                         l2="inputs larger than L2: 3.34 GB of weights streamed per step vs 126 MB L2",
                         parallelism=f"dp{world} (independent request stream per GPU, no data-path collective)",

@@ -297,6 +297,17 @@ int dflash_gemm_trace(const void* W, int N, int K, const void* X, int x_rows_tot
   return p.grid;
 }
 
+#ifdef DFLASH_STEP_TRACE
+// Debug build only: device buffer for the in-step timeline (ptx.cuh). cap = number of (tag, time) records.
+int dflash_step_trace_set(unsigned long long* buf, unsigned int cap) {
+  unsigned int zero = 0;
+  cudaError_t e = cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+  return e == cudaSuccess ? DFLASH_OK : cuda_fail(e, "step_trace_set");
+}
+#endif
+
 int dflash_gemm_argmax(const void* W, int w_rows_total, int N, int K, const void* X, int x_rows_total,
                        int x_row0, int mb, int m_valid, float* cand_val, int* cand_idx, void* logits,
                        long long logits_ld, long long* tokens_out, int grid, int use_pdl,

@@ -268,6 +268,7 @@ __global__ void attn_split_kernel(const AttnArgs a) {
   DFL_WAIT_THEN_TRIGGER();
   attn_split_body<2>(a, r, blockIdx.z % tiles_per_req, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x,
                      smem_u32(attn_smem), 0, L);
+  DFL_TRACE(2);
 }
 
 // Merge the splits of one (row, q head) item: one warp.
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(32 * kItemWarps) attn_combine_kernel(const Att
   const int item = blockIdx.x * kItemWarps + (threadIdx.x >> 5);
   if (item >= a.R * a.SL * a.Hq) return;
   attn_combine_item(a, item, threadIdx.x & 31);
+  DFL_TRACE(2);
 }
 
 }  // namespace dfl

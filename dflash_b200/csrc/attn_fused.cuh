@@ -29,33 +29,6 @@ __host__ __device__ inline int attn_fused_smem(int group) {
   return 2 * 2 * kAttnTileBytes + 16 * group * kAttnD * 4 + 16 * group * 2 * 4;
 }
 
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_cta_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t dsmem_map(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ float4 dsmem_ld_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float2 dsmem_ld_f2(uint32_t addr) {
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-  return v;
-}
-
 constexpr int kFusedPostWarps = 8;  // extra warps that only help with step A (latency-bound, one item per warp)
 
 // grid (kFusedSplits, Hkv, R * SL/16), cluster (kFusedSplits, 1, 1), block 32 * (group + kFusedPostWarps)

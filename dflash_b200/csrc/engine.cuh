@@ -379,6 +379,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     cudaFuncSetAttribute(gemm_skinny_kernel<256, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(finalize_rows_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(swiglu_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
@@ -415,6 +416,17 @@ inline RowsArgs rows_args_base(const Engine* e) {
   a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
   a.valid_mode = kRowsAll;
   return a;
+}
+
+// Per-layer row pass (partials + residual + RMSNorm): four CTAs per row when the width allows it
+inline cudaError_t launch_finalize(Engine* e, const RowsArgs& a, int rows, cudaStream_t st) {
+  static const bool no_cluster = getenv("DFLASH_NO_ROW_CLUSTER") != nullptr;
+  const bool ok = !no_cluster && a.ws != nullptr && a.embed == nullptr && a.norm_w != nullptr &&
+                  e->H % (4 * kRowCtas) == 0 && e->H / kRowCtas <= kRowClThreads * 4 * kRowClGroups;
+  if (ok)
+    return launch_cluster_pdl(finalize_rows_cluster_kernel, dim3(kRowCtas, rows), dim3(kRowClThreads),
+                              dim3(kRowCtas, 1, 1), 0, st, e->pdl, a);
+  return launch_pdl(finalize_rows_kernel, dim3(rows), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a);
 }
 
 // fc GEMM + hidden_norm over the pending context rows -> a_in rows [0, RS)   (dflash.py:177)
@@ -545,7 +557,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
       a.resid = x;
       a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
       a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
-      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "o finalize");
+      if (!(dbg_skip() & 1)) DFL_CUDA(launch_finalize(e, a, RS, st), "o finalize");
     }
     if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
     {
@@ -570,7 +582,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
         a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
         a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
       }
-      if (!(dbg_skip() & 1)) DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a), "down finalize");
+      if (!(dbg_skip() & 1)) DFL_CUDA(launch_finalize(e, a, RS, st), "down finalize");
     }
   }
   if (!run_lm_head) return DFLASH_OK;

@@ -168,6 +168,7 @@ __device__ __forceinline__ void draft_tokens_row(const DraftTokArgs& a, int row,
 __global__ void __launch_bounds__(32) draft_tokens_kernel(const DraftTokArgs a) {
   DFL_VERIFY_SYNC();
   draft_tokens_row(a, blockIdx.x, threadIdx.x);
+  DFL_TRACE(2);
 }
 
 // =============================================================================================
@@ -279,9 +280,11 @@ __device__ __forceinline__ void finalize_row_body(const RowsArgs& a, int row, in
     }
   }
   if (a.norm_w == nullptr) return;
+  DFL_TRACE(4);
   ss = warp_sum(ss);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
   group_sync(bar_id, NT);
+  DFL_TRACE(5);
   float tot = 0.f;
 #pragma unroll
   for (int w = 0; w < NT / 32; ++w) tot += red[w];
@@ -309,6 +312,91 @@ __global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsA
   // kernel starts its real work
   DFL_WAIT_THEN_TRIGGER();
   finalize_row_body<kRowsThreads, true>(a, blockIdx.x, threadIdx.x, rowbuf, red, ns_tab, 0);
+  DFL_TRACE(2);
+}
+
+// The same row pass with kRowCtas CTAs per row (one thread-block cluster): a lone CTA has to pull ~110 KB of partials
+// through one SM's load path (3-4 us in the step timeline, scripts/step_trace.py); four SMs share it here. Each CTA
+// owns a quarter of the columns, keeps its values in registers, and the row's sum of squares is exchanged through
+// distributed shared memory (every CTA pushes its partial sum into all peers, one cluster barrier, fixed summation
+// order). Partials + optional residual + RMSNorm only (what the per-layer launches need).
+#ifndef DFLASH_ROW_CTAS
+#define DFLASH_ROW_CTAS 4
+#endif
+constexpr int kRowCtas = DFLASH_ROW_CTAS;
+constexpr int kRowClThreads = 256;
+constexpr int kRowClGroups = 2;  // float4 groups per thread: H / kRowCtas <= 256 * 4 * 2 (H <= 8192)
+
+__global__ void __launch_bounds__(kRowClThreads) finalize_rows_cluster_kernel(const RowsArgs a) {
+  __shared__ int ns_tab[kRowsMaxTiles];
+  __shared__ float red[kRowClThreads / 32];
+  __shared__ float peer_ss[kRowCtas];
+  const int rank = static_cast<int>(cluster_cta_rank());
+  const int row = blockIdx.y, tid = threadIdx.x;
+  const int cols = a.H / kRowCtas, c0 = rank * cols;
+  {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = tid; t < nt; t += kRowClThreads) ns_tab[t] = tile_slots32(t, a.sm);
+  }
+  __syncthreads();
+  DFL_WAIT_THEN_TRIGGER();
+  if (a.valid_mode == kRowsCtx) {  // the whole cluster takes the same branch (no barrier is left half-entered)
+    const int r = row / a.SL, j = row % a.SL;
+    if (j >= a.ctx_len[r]) return;
+  }
+  const long long roff = static_cast<long long>(row) * a.H;
+  float4 v[kRowClGroups];
+  uint2 rs[kRowClGroups], wv[kRowClGroups];
+#pragma unroll
+  for (int g = 0; g < kRowClGroups; ++g) {
+    const int n = c0 + tid * 4 + g * kRowClThreads * 4;
+    if (n < c0 + cols) {
+      wv[g] = *reinterpret_cast<const uint2*>(a.norm_w + n);
+      v[g] = sum_slots_4(a.ws, a.sm, row, n, ns_tab[n / kTileN]);
+      if (a.resid != nullptr) rs[g] = __ldcg(reinterpret_cast<const uint2*>(a.resid + roff + n));
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int g = 0; g < kRowClGroups; ++g) {
+    const int n = c0 + tid * 4 + g * kRowClThreads * 4;
+    if (n >= c0 + cols) continue;
+    float4& x = v[g];
+    x.x = bf16_round(x.x); x.y = bf16_round(x.y); x.z = bf16_round(x.z); x.w = bf16_round(x.w);
+    if (a.resid != nullptr) {
+      const float4 rsd = unpack4_bf16(rs[g]);
+      x.x = bf16_round(rsd.x + x.x); x.y = bf16_round(rsd.y + x.y);
+      x.z = bf16_round(rsd.z + x.z); x.w = bf16_round(rsd.w + x.w);
+      *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
+    }
+    ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+  }
+  DFL_TRACE(4);
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid < kRowCtas) {  // thread p pushes this CTA's partial sum into CTA p's peer_ss[rank]
+    float part = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowClThreads / 32; ++w) part += red[w];
+    dsmem_st_f32(dsmem_map(smem_u32(&peer_ss[rank]), static_cast<uint32_t>(tid)), part);
+  }
+  cluster_sync_all();
+  DFL_TRACE(5);
+  float tot = 0.f;
+#pragma unroll
+  for (int p = 0; p < kRowCtas; ++p) tot += peer_ss[p];
+  const float rstd = 1.0f / sqrtf(tot / static_cast<float>(a.H) + a.eps);
+#pragma unroll
+  for (int g = 0; g < kRowClGroups; ++g) {
+    const int n = c0 + tid * 4 + g * kRowClThreads * 4;
+    if (n >= c0 + cols) continue;
+    const float4 w = unpack4_bf16(wv[g]);
+    *reinterpret_cast<uint2*>(a.out + roff + n) =
+        pack4_bf16(w.x * bf16_round(v[g].x * rstd), w.y * bf16_round(v[g].y * rstd), w.z * bf16_round(v[g].z * rstd),
+                   w.w * bf16_round(v[g].w * rstd));
+  }
+  DFL_TRACE(2);
 }
 
 // Two independent row passes in one launch (CTAs [0, rows0) run a0, the rest run a1): the step's first small
@@ -327,6 +415,7 @@ __global__ void __launch_bounds__(kRowsThreads) finalize_rows2_kernel(const Rows
   __syncthreads();
   DFL_WAIT_THEN_TRIGGER();
   finalize_row_body<kRowsThreads, true>(a, first ? blockIdx.x : blockIdx.x - rows0, threadIdx.x, rowbuf, red, ns_tab, 0);
+  DFL_TRACE(2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -394,6 +483,7 @@ __global__ void __launch_bounds__(kSwigluThreads) swiglu_kernel(const SwigluArgs
   const float4 u = sum_slots_4(a.ws, a.sm, m, a.I + n, ns_u);
   *reinterpret_cast<uint2*>(a.out + static_cast<long long>(m) * a.I + n) =
       pack4_bf16(silu_mul_bf16(g.x, u.x), silu_mul_bf16(g.y, u.y), silu_mul_bf16(g.z, u.z), silu_mul_bf16(g.w, u.w));
+  DFL_TRACE(2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -514,6 +604,7 @@ __device__ __forceinline__ void qkv_post_apply(const QkvPostArgs& a, const QkvIt
 __device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, int hh, int lane) {
   const QkvItem it = qkv_post_prepare(a, row, hh, lane);
   qkv_post_apply(a, it, lane);
+  DFL_TRACE(2);
 }
 
 // item in [0, rows * (q_cols/128 + 2*Hkv))
@@ -532,6 +623,7 @@ __global__ void __launch_bounds__(32 * kItemWarps) qkv_post_kernel(const QkvPost
   if (item < a.rows * heads_per_row) it = qkv_post_prepare(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
   DFL_WAIT_THEN_TRIGGER();
   qkv_post_apply(a, it, lane);
+  DFL_TRACE(2);
 }
 
 }  // namespace dfl

@@ -168,6 +168,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   unsigned long long* tr = a.trace ? a.trace + (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = global_ns();
+  DFL_TRACE(0);
 #ifdef DFLASH_GEMM_TOP_TRIGGER
   pdl_trigger();  // (experiment) release the dependent before this kernel's own prologue
 #endif
@@ -247,6 +248,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       pdl_trigger();  // (experiment) the dependent small kernel becomes resident only once this GEMM really starts
 #endif
       if (tr) tr[2] = global_ns();
+      DFL_TRACE_ANY(1);
       for (int i = 0; i < npre; ++i) {
         const int kb = static_cast<int>((u0 + i) % a.k_blocks);
         tma_load_2d(sX + i * Cfg::kXBytes, &tmX, &full[i], kb * kTileK, a.x_row0 + m0, polX);
@@ -289,6 +291,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         for (; u < seg_end; ++u) {
           mbar_wait(&full[stage], phase);
           if (tr && u == u0) tr[3] = global_ns();
+          if (u == u0) DFL_TRACE_ANY(3);
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(sW + stage * Cfg::kWBytes));
           const uint64_t db = umma_desc_sw128(smem_u32(sX + stage * Cfg::kXBytes));
@@ -473,6 +476,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       if (acc == 0) acc_phase ^= 1u;
     }
     if (tr && threadIdx.x == 0) tr[6] = global_ns();
+    DFL_TRACE(2);
 
     if (kSample) {
       // reduce (perturbed key, tile) over the 128 weight rows through the idle pipeline smem

@@ -162,19 +162,46 @@ __device__ __forceinline__ void pdl_trigger() {
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 }
 
+// ----------------------------------------------------------------------------- in-step timeline (debug build only)
+// -DDFLASH_STEP_TRACE: thread 0 of block (0,0,0) of every kernel appends (tag, globaltimer) records to a device
+// buffer set by dflash_step_trace_set(); tag = phase | blockDim.x << 4 | gridDim.x << 16 | gridDim.y << 40 identifies
+// the kernel by its launch shape (scripts/step_trace.py). Compiled out of the product build.
+#ifdef DFLASH_STEP_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_n = 0;
+__device__ __forceinline__ void dfl_trace_any(int phase) {  // call from ONE thread of the block
+  if (g_trace_buf == nullptr || blockIdx.x != 0 || blockIdx.y != 0 || blockIdx.z != 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  const unsigned int i = atomicAdd(&g_trace_n, 1u);
+  if (i < g_trace_cap) {
+    g_trace_buf[2 * i] = static_cast<unsigned long long>(phase) | (static_cast<unsigned long long>(blockDim.x) << 4) |
+                         (static_cast<unsigned long long>(gridDim.x) << 16) |
+                         (static_cast<unsigned long long>(gridDim.y) << 40);
+    g_trace_buf[2 * i + 1] = t;
+  }
+}
+#define DFL_TRACE(phase) do { if (threadIdx.x == 0) dfl_trace_any(phase); } while (0)
+#define DFL_TRACE_ANY(phase) dfl_trace_any(phase)
+#else
+#define DFL_TRACE(phase) do { } while (0)
+#define DFL_TRACE_ANY(phase) do { } while (0)
+#endif
+
 // Small kernels in front of a GEMM: wait for the producer first, release the dependent GEMM second, so that the GEMM
 // becomes resident exactly when this kernel starts its real work (measured against trigger-first: DESIGN.md §7).
 #ifdef DFLASH_TRIGGER_FIRST
-#define DFL_WAIT_THEN_TRIGGER() do { pdl_trigger(); pdl_wait(); } while (0)
+#define DFL_WAIT_THEN_TRIGGER() do { DFL_TRACE(0); pdl_trigger(); pdl_wait(); DFL_TRACE(1); } while (0)
 #else
-#define DFL_WAIT_THEN_TRIGGER() do { pdl_wait(); pdl_trigger(); } while (0)
+#define DFL_WAIT_THEN_TRIGGER() do { DFL_TRACE(0); pdl_wait(); pdl_trigger(); DFL_TRACE(1); } while (0)
 #endif
 
 // the verify-side kernels and the token reduce (experiment switch: same ordering question)
 #ifdef DFLASH_VERIFY_WAIT_FIRST
-#define DFL_VERIFY_SYNC() do { pdl_wait(); pdl_trigger(); } while (0)
+#define DFL_VERIFY_SYNC() do { DFL_TRACE(0); pdl_wait(); pdl_trigger(); DFL_TRACE(1); } while (0)
 #else
-#define DFL_VERIFY_SYNC() do { pdl_trigger(); pdl_wait(); } while (0)
+#define DFL_VERIFY_SYNC() do { DFL_TRACE(0); pdl_trigger(); pdl_wait(); DFL_TRACE(1); } while (0)
 #endif
 
 // block sizes of the small kernels (tuning switches; measured defaults)
@@ -190,6 +217,38 @@ constexpr int kItemWarps = DFLASH_WARPITEM_WARPS;
 // named barrier over `nthreads` threads of the CTA (id 0 with blockDim.x threads == __syncthreads)
 __device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");
+}
+
+// ----------------------------------------------------------------------------- thread-block clusters / DSMEM
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t dsmem_map(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 dsmem_ld_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 dsmem_ld_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ void dsmem_st_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
 }
 
 // ----------------------------------------------------------------------------- small helpers

@@ -26,6 +26,7 @@ struct AttnArgs {
   int nsplit;
   const int* start;
   const int* blk_len;
+  const int* ctx_len;            // optional: keys below start - ctx_len were cached by earlier steps
   const __nv_bfloat16* q;        // [R*SL][Hq][128]
   const __nv_bfloat16* k_cache;  // [R][Hkv][S_max][128]
   const __nv_bfloat16* v_cache;
@@ -77,9 +78,13 @@ __host__ __device__ inline int attn_chunk(int L, int nsplit) {
 // (tid in [0, 32*group)). NSTG = K/V smem stages (1 or 2) at smem0; bar_id = named barrier of the group.
 // LOCAL: partials are indexed (row_in_tile * group + head_in_group) -- a per-CTA buffer (shared memory of the
 // cluster-fused kernel) -- instead of the global [split][row][head] layout.
-template <int NSTG, bool LOCAL = false>
+// PDLIN (stand-alone kernel): griddepcontrol.wait happens INSIDE, after the first K/V tile has been requested when
+// that tile only holds keys cached by earlier steps (old_end = start - ctx_len): its HBM latency then overlaps the
+// wait for qkv_post instead of following it.
+template <int NSTG, bool LOCAL = false, bool PDLIN = false>
 __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt, int h, int split, int tid,
-                                                int nthreads, uint32_t smem0, int bar_id, int L_in = -1) {
+                                                int nthreads, uint32_t smem0, int bar_id, int L_in = -1,
+                                                int old_end = -1) {
   const int warp = tid >> 5, lane = tid & 31;
   const int group = a.Hq / a.Hkv;
   const int hq = h * group + warp;
@@ -105,22 +110,6 @@ __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt
     return;
   }
 
-  // Q fragments (A operand, 8 k-steps of 16 over D=128), straight from global (L2)
-  uint32_t qf[8][4];
-  {
-    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(a.q + (static_cast<long long>(row_lo) * a.Hq + hq) * kAttnD);
-    const uint32_t* q1 =
-        reinterpret_cast<const uint32_t*>(a.q + (static_cast<long long>(row_lo + 8) * a.Hq + hq) * kAttnD);
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const int c = (ks * 16 + tq * 2) >> 1;  // in 32-bit words
-      qf[ks][0] = __ldcg(q0 + c);
-      qf[ks][1] = __ldcg(q1 + c);
-      qf[ks][2] = __ldcg(q0 + c + 4);
-      qf[ks][3] = __ldcg(q1 + c + 4);
-    }
-  }
-
   const __nv_bfloat16* kbase = a.k_cache + (static_cast<long long>(r) * a.Hkv + h) * a.S_max * kAttnD;
   const __nv_bfloat16* vbase = a.v_cache + (static_cast<long long>(r) * a.Hkv + h) * a.S_max * kAttnD;
 
@@ -138,13 +127,39 @@ __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt
     }
   };
 
+  bool pre0 = false;
+  if (PDLIN) {
+    pre0 = NSTG == 2 && old_end >= 0 && k0 + kAttnKeys <= old_end;
+    if (pre0) {
+      load_tile(0, 0);
+      cp_async_commit();
+    }
+    DFL_WAIT_THEN_TRIGGER();
+  }
+
+  // Q fragments (A operand, 8 k-steps of 16 over D=128), straight from global (L2)
+  uint32_t qf[8][4];
+  {
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(a.q + (static_cast<long long>(row_lo) * a.Hq + hq) * kAttnD);
+    const uint32_t* q1 =
+        reinterpret_cast<const uint32_t*>(a.q + (static_cast<long long>(row_lo + 8) * a.Hq + hq) * kAttnD);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int c = (ks * 16 + tq * 2) >> 1;  // in 32-bit words
+      qf[ks][0] = __ldcg(q0 + c);
+      qf[ks][1] = __ldcg(q1 + c);
+      qf[ks][2] = __ldcg(q0 + c + 4);
+      qf[ks][3] = __ldcg(q1 + c + 4);
+    }
+  }
+
   float o[16][4];
 #pragma unroll
   for (int nt = 0; nt < 16; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
   const int ntiles = (k1 - k0 + kAttnKeys - 1) / kAttnKeys;
-  if (NSTG == 2) {
+  if (NSTG == 2 && !pre0) {
     load_tile(0, 0);
     cp_async_commit();
   }
@@ -264,10 +279,11 @@ __global__ void attn_split_kernel(const AttnArgs a) {
   const int r = blockIdx.z / tiles_per_req;
   // the key range comes from request state that only the previous step's accept kernel writes: read it while the
   // kernel in front of this one (qkv_post) is still running
-  const int L = a.start[r] + a.blk_len[r];
-  DFL_WAIT_THEN_TRIGGER();
-  attn_split_body<2>(a, r, blockIdx.z % tiles_per_req, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x,
-                     smem_u32(attn_smem), 0, L);
+  const int st = a.start[r];
+  const int L = st + a.blk_len[r];
+  const int old_end = a.ctx_len != nullptr ? st - a.ctx_len[r] : -1;
+  attn_split_body<2, false, true>(a, r, blockIdx.z % tiles_per_req, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x,
+                                  smem_u32(attn_smem), 0, L, old_end);
   DFL_TRACE(2);
 }
 

@@ -518,6 +518,9 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   aa.nsplit = e->nsplit_attn;
   aa.start = e->buf<int>(DFLASH_BUF_START);
   aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+#ifndef DFLASH_NO_KV_PREFETCH
+  aa.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+#endif
   aa.q = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
   aa.part_o = e->buf<float>(DFLASH_BUF_ATTN_PO);
   aa.part_ml = e->buf<float>(DFLASH_BUF_ATTN_ML);
@@ -685,6 +688,9 @@ inline int build_mega(Engine* e) {
   aa.nsplit = e->nsplit_attn;
   aa.start = e->buf<int>(DFLASH_BUF_START);
   aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+#ifndef DFLASH_NO_KV_PREFETCH
+  aa.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+#endif
   aa.q = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
   aa.part_o = e->buf<float>(DFLASH_BUF_ATTN_PO);
   aa.part_ml = e->buf<float>(DFLASH_BUF_ATTN_ML);
@@ -847,6 +853,9 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
   aa.done = e->buf<int>(DFLASH_BUF_DONE);
   aa.n_cycles = e->buf<int>(DFLASH_BUF_N_CYCLES);
   aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+#ifndef DFLASH_NO_KV_PREFETCH
+  aa.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+#endif
   aa.acc_hist = e->buf<int>(DFLASH_BUF_ACC_HIST);
   aa.hist_ld = e->cfg.hist_len;
   aa.max_len = e->buf<int>(DFLASH_BUF_MAX_LEN);

@@ -321,15 +321,16 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
                             kModePartials, e->grid));
     finish(e->d[l], mb_blk);
   }
+  const int lm_grid = getenv("DFLASH_LM_GRID") ? atoi(getenv("DFLASH_LM_GRID")) : e->grid;  // (make_gemm_plan balances it)
   DFL_PLAN(make_gemm_plan(&e->lm, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
-                          c.keep_draft_logits ? kModeArgmaxDump : kModeArgmax, e->grid));
+                          c.keep_draft_logits ? kModeArgmaxDump : kModeArgmax, lm_grid));
   e->lm.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
   e->lm.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
   e->lm.args.logits = c.keep_draft_logits ? e->buf<__nv_bfloat16>(DFLASH_BUF_DRAFT_LOGITS) : nullptr;
   e->lm.args.logits_ld = e->V;
   if (mb_blk <= 32) {
     DFL_PLAN(make_gemm_plan(&e->lm_sample, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
-                            kModeSample, e->grid));
+                            kModeSample, lm_grid));
     e->lm_sample.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
     e->lm_sample.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
     e->lm_sample.args.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
@@ -338,7 +339,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->max_cand = c.max_candidates > 1 ? c.max_candidates : 1;
   if (e->max_cand > 1) {
     DFL_PLAN(make_gemm_plan(&e->lm_topk, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
-                            kModeTopK, e->grid));
+                            kModeTopK, lm_grid));
     e->lm_topk.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
     e->lm_topk.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
   }

@@ -553,7 +553,7 @@ def run_cuda_arm(args):
             step_roofline=dict(bound="hbm", achieved=step_gbs, peak=peak_gbs, unit="GB/s", frac=step_gbs / peak_gbs,
                                algorithmic_bytes=ab["total"], note=f"all {launches_per_step} kernels of the step, median step time"),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
-                          traffic=1244.856e6 + 3.737e6,  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one
+                          traffic=1244.860e6 + 4.830e6,  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one
                           # `ncu --set full` capture of this command (profiles/ncu_gemm_r1_table.md); not re-measured per run
                           kernel="gemm_skinny_kernel<16,argmax> (lm_head 151936x4096 + fused argmax)",
                           launch_us=lm_us, algorithmic_bytes=lm_bytes, peak_source=peak_src),

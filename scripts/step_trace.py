@@ -56,7 +56,7 @@ for _ in range(6):
 torch.cuda.synchronize()
 rec = buf.view(cap, 2).cpu()
 rec = rec[rec[:, 1] != 0]
-names = {(512, 32, 1): "finalize2", (512, 16, 1): "finalize", (256, 192, 1): "qkv_post", (128, 16, 8): "attn_split",
+names = {(512, 32, 1): "finalize2", (512, 16, 1): "finalize", (256, 4, 16): "finalize_cl", (256, 192, 1): "qkv_post", (128, 16, 8): "attn_split",
          (256, 64, 1): "attn_combine", (256, 12, 16): "swiglu", (32, 16, 1): "draft_tokens", (256, 32, 16): "posterior",
          (32, 1, 1): "accept", (256, 16, 5): "ctx_gather", (192, 1, 148): "gemm"}
 ev = []

@@ -45,7 +45,9 @@ MEAN_TAU_TARGET = 7.3  # published Qwen3-8B-DFlash-b16 math-average acceptance l
 
 
 def forced_schedule(seed=0, n=TAU_SCHEDULE_LEN, bs=None):
-    """Seeded per-cycle forced-acceptance counts k (tau = k + 1) with mean tau ~= 7.3."""
+    """Seeded per-cycle forced-acceptance counts k (tau = k + 1) with mean tau ~= 7.3. The draws are
+    arranged so that every window of the schedule has about the same mean (alternating from both ends of the sorted
+    draws), which keeps tokens/s comparable between short and long runs."""
     import random
     bs = Q8["block_size"] if bs is None else bs
     rng = random.Random(seed)
@@ -54,7 +56,15 @@ def forced_schedule(seed=0, n=TAU_SCHEDULE_LEN, bs=None):
         # geometric-like mixture clipped to [0, bs-1]
         k = min(bs - 1, int(rng.expovariate(1.0 / 6.2)))  # seed 0, n 64 -> mean tau 7.28
         ks.append(k)
-    return ks
+    mean = sum(ks) / len(ks)
+    rest, out, tot = sorted(ks), [], 0
+    while rest:
+        want = mean * (len(out) + 1) - tot
+        k = min(rest, key=lambda v: (abs(v - want), v))
+        rest.remove(k)
+        out.append(k)
+        tot += k
+    return out
 
 
 def algorithmic_bytes(dims, S, c, R=1):

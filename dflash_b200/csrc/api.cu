@@ -252,6 +252,11 @@ int dflash_sample(const void* logits, long long logits_ld, int rows, int vocab, 
   return DFLASH_OK;
 }
 
+int dflash_gemm_argmax_grid(int N, int grid) {
+  if (N <= 0 || grid <= 0) return DFLASH_ERR_ARG;
+  return balanced_tile_grid((N + kTileN - 1) / kTileN, grid);
+}
+
 int dflash_gemm_max_slots(int N, int K, int grid) {
   if (N <= 0 || K <= 0 || K % kTileK != 0 || grid <= 0) return DFLASH_ERR_ARG;
   const int n_tiles = (N + kTileN - 1) / kTileN;

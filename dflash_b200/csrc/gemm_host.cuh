@@ -154,6 +154,14 @@ inline void set_gemm_prefetch(GemmPlan* p, long long bytes) {
 // so ranges * groups ~ one wave of CTAs.
 inline int ranges_for(int grid, int groups) { return grid / groups > 0 ? grid / groups : 1; }
 
+// CTAs for a whole-tile GEMM: the smallest grid whose busiest CTA has as many tiles as with `grid` CTAs.
+inline int balanced_tile_grid(int n_tiles, int grid) {
+  int g = grid < n_tiles ? grid : n_tiles;
+  if (g < 1) g = 1;
+  const int per = (n_tiles + g - 1) / g;
+  return (n_tiles + per - 1) / per;
+}
+
 // Fill a plan. W: [w_rows_total, K] bf16 (pitch K); the GEMM covers weight rows [w_row0, w_row0+N).
 // X: [x_rows_total, K] bf16 (pitch K); activation rows [x_row0, x_row0+groups*mb) feed the MMA in `groups`
 // slabs of mb rows (groups = ceil(m_valid / mb)).
@@ -199,10 +207,7 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
     // with 8, and the kernel would last 9 tiles' time at 8/9 of the bandwidth (in-graph timeline: block 0 done 31 us
     // before the kernel). Take the smallest grid with the same maximum -- ceil(1187 / 9) = 132 CTAs of 9 tiles; the
     // stream stays HBM-bound with 132 SMs pulling (measured 694 -> 685 us per step).
-    int g = grid < p->args.n_tiles ? grid : p->args.n_tiles;
-    const int per = (p->args.n_tiles + g - 1) / g;
-    g = (p->args.n_tiles + per - 1) / per;
-    p->grid = g;
+    p->grid = balanced_tile_grid(p->args.n_tiles, grid);
     p->max_slots = 1;
   } else {
     p->grid = static_cast<long long>(grid) < T ? grid : static_cast<int>(T);

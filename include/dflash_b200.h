@@ -229,6 +229,9 @@ int dflash_sample(const void* logits, long long logits_ld, int rows, int vocab, 
  * runs ceil(m_valid/mb) column groups in one launch over grid/groups weight ranges (X must hold groups*mb rows).
  * ws: fp32 scratch [dflash_gemm_max_slots(N,K,grid/groups)][ws_rows >= groups*mb][ws_ld] for the split-K partials. */
 int dflash_gemm_max_slots(int N, int K, int grid);
+/* CTAs dflash_gemm_argmax actually launches for N weight rows when offered `grid`: whole 128-row tiles per CTA, the
+ * smallest grid with the same busiest CTA (151936 rows, 148 -> 132 CTAs of 9 tiles). */
+int dflash_gemm_argmax_grid(int N, int grid);
 int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K, const void* X,
                        int x_rows_total, int x_row0, int mb, int m_valid, float* ws, int ws_rows,
                        long long ws_ld, float* out, long long out_ld, int grid, int use_pdl,

@@ -162,3 +162,30 @@ def test_context_tap_equals_output_hidden_states():
     assert [len(m._forward_hooks) for m in target.model.layers] == n_hooks  # our hooks are removed on exit
     with pytest.raises(ValueError):
         ContextTap(target, [TINY["target_layers"] - 1])  # the last entry of hidden_states is post-norm, not a layer output
+
+
+def test_whole_tile_grid_is_balanced(lib):
+    """lm_head-style GEMMs run on the smallest grid with the same busiest CTA (host arithmetic, no GPU)."""
+    lib.dflash_gemm_argmax_grid.restype = ctypes.c_int
+    f = lib.dflash_gemm_argmax_grid
+    assert f(151936, 148) == 132          # 1187 tiles: 9 per CTA either way, 132 CTAs all busy
+    assert f(128256, 148) == 144          # 1002 tiles: 7 per CTA
+    assert f(1000, 148) == 8              # fewer tiles than CTAs: one tile each
+    assert f(151936, 37) == 36            # wide batches: 37 ranges -> 36 of 33 tiles
+    for n_rows in (128, 129, 5000, 151936, 262144):
+        for grid in (1, 7, 37, 148):
+            g = f(n_rows, grid)
+            nt = (n_rows + 127) // 128
+            assert 1 <= g <= min(grid, nt)
+            assert -(-nt // g) == -(-nt // min(grid, nt))   # same maximum tiles per CTA
+    assert f(0, 148) < 0
+
+
+def test_forced_tau_schedule_is_window_balanced():
+    import bench
+    ks = bench.forced_schedule(seed=0)
+    mean = sum(k + 1 for k in ks) / len(ks)
+    assert abs(mean - 7.28) < 0.01 and sorted(ks) == sorted(bench.forced_schedule(seed=0)) and max(ks) <= 15
+    for w in (8, 16, 32):
+        for i in range(0, len(ks) - w + 1, w):
+            assert abs(sum(k + 1 for k in ks[i:i + w]) / w - mean) < 0.75

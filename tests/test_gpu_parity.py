@@ -152,6 +152,40 @@ def test_gemm_sample_epilogue_distribution_and_greedy_limit():
         assert toks.cpu().tolist() == [int(logits.argmax())] * mb
 
 
+def test_gemm_sample_epilogue_two_streams_width():
+    """The 32-row instantiation (two request streams): 20 valid rows, each row its own distribution; T -> 0 gives
+    every row's argmax, T = 1 gives tokens that vary with the step and stay inside the vocabulary."""
+    dev = _cuda()
+    from dflash_b200 import _lib
+    from dflash_b200.engine import _declare
+    lib = _lib.load()
+    _declare(lib)
+    torch.manual_seed(5)
+    V, K, mb, rows = 1000, 256, 32, 20
+    W = (torch.randn(V, K, device=dev) * 0.3).to(torch.bfloat16)
+    X = torch.randn(mb, K, device=dev).to(torch.bfloat16)
+    logits = (X[:rows].float() @ W.float().t()).to(torch.bfloat16).float()
+    cv = torch.empty(148, mb, dtype=torch.float32, device=dev)
+    ci = torch.empty(148, mb, dtype=torch.int32, device=dev)
+    toks = torch.full((mb,), -1, dtype=torch.int64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.dflash_gemm_sample(_ptr(W), V, V, K, _ptr(X), mb, 0, mb, rows, 1e-3, 1, 0, _ptr(cv), _ptr(ci),
+                                      _ptr(toks), 148, 0, st))
+    got = toks[:rows].cpu()
+    ref = logits.argmax(-1).cpu()
+    top2 = torch.topk(logits, 2, dim=-1).values.cpu()
+    clear = (top2[:, 0] - top2[:, 1]) > 0.05
+    assert torch.equal(got[clear], ref[clear]) and int(clear.sum()) >= rows // 2
+    seen = set()
+    for step in range(8):
+        _lib.check(lib.dflash_gemm_sample(_ptr(W), V, V, K, _ptr(X), mb, 0, mb, rows, 1.0, 9, step, _ptr(cv), _ptr(ci),
+                                          _ptr(toks), 148, 0, st))
+        t = toks[:rows].cpu().tolist()
+        assert all(0 <= x < V for x in t)
+        seen.add(tuple(t))
+    assert len(seen) == 8
+
+
 def test_gemm_argmax_matches_own_logits():
     dev = _cuda()
     from dflash_b200 import _lib

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DFLASH_LIB: another build of the same library (kernel-tuning experiments, scripts/sweep_*.sh); never a fallback
@@ -34,6 +34,14 @@ def _declare(lib):
         c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
         c_longlong, c_void_p, c_longlong, c_int, c_int, c_void_p,
     ]
+    lib.dflash_gemm_rows.restype = c_int
+    lib.dflash_gemm_rows.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_longlong, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.dflash_gemm_swiglu.restype = c_int
+    lib.dflash_gemm_swiglu.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_longlong,
+                                       c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.dflash_rms_norm_rows.restype = c_int
+    lib.dflash_rms_norm_rows.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p]
     lib.dflash_gemm_argmax.restype = c_int
     lib.dflash_gemm_argmax.argtypes = [
         c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

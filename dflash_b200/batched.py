@@ -22,10 +22,6 @@ from .engine import DraftEngine
 from .utils import ContextTap, sample
 
 
-def _pow2_at_least(n: int) -> int:
-    return 1 << max(0, (int(n) - 1).bit_length())
-
-
 @torch.inference_mode()
 def spec_generate_batch(draft, target, prompts: Sequence[torch.Tensor], max_new_tokens: int,
                         stop_token_ids: Optional[List[int]], temperature: float, *, max_requests: Optional[int] = None,
@@ -34,7 +30,7 @@ def spec_generate_batch(draft, target, prompts: Sequence[torch.Tensor], max_new_
                         graph_target: bool = False, sync_every: int = 1) -> List[torch.Tensor]:
     """prompts: LongTensor[1, P_i] each (ragged). Returns one LongTensor[1, P_i + n_i] per prompt, in order.
 
-    max_requests: request streams resident in the engine (power of two <= 64; default: enough for all prompts).
+    max_requests: request streams resident in the engine (<= 64; default: enough for all prompts).
     forced_k[i]: harness hook, per-prompt forced-acceptance schedule. noise_fn(cycle) -> fp32
     [R * block_size, V] Exp(1) draws for the posterior race at temperature > 0 (tests); otherwise Philox(seed).
     graph_target: every slot replays the (unmodified) target's verify forward from its own CUDA graph over a static
@@ -47,7 +43,7 @@ def spec_generate_batch(draft, target, prompts: Sequence[torch.Tensor], max_new_
         return []
     dev = target.device
     bs = draft.block_size
-    R = _pow2_at_least(min(n, max_requests or 64))
+    R = min(n, max_requests or 64)
     if R > 64:
         raise ValueError("at most 64 request streams per engine")
     Pmax = max(int(p.shape[1]) for p in prompts)

@@ -9,8 +9,6 @@
 #include "../../include/dflash_b200.h"
 #include "attention.cuh"
 #include "fused_ops.cuh"
-#include "attn_fused.cuh"
-#include "step_mega.cuh"
 #include "verify.cuh"
 
 namespace dfl {
@@ -29,10 +27,9 @@ struct Engine {
   Region reg[DFLASH_BUF_COUNT];
   int R, SL, RS, H, I, L, Hq, Hkv, V, nsel, bs, grid, nsplit_attn, nsplit_post;
   bool pdl;
-  int max_slots;
   // plans
-  GemmPlan fc;                  // ctx_feat -> partials
-  std::vector<GemmPlan> qkv;    // a_in (ctx + block rows)
+  GemmPlan fc;                  // ctx_feat -> bf16 rows + per-tile sums of squares
+  std::vector<GemmPlan> qkv;    // a_in (ctx + block rows) -> q buffer, K/V cache
   // prompt pass (c = P rows at once): fc and the K/V rows of wqkv over the dedicated prompt buffers,
   // one plan per UMMA width so that short prompts do not pay for 256 columns
   GemmPlan fc_pf[5];            // mb = 16 << i
@@ -43,11 +40,8 @@ struct Engine {
   GemmPlan lm_sample;           // same GEMM with the Gumbel-max epilogue (draft tokens sampled at temperature > 0)
   bool has_sample = false;
   int max_cand = 1;
-  // persistent draft-step kernel (step_mega.cuh): tables live in the workspace
-  bool mega = false;
-  int fused_attn = 0;  // 1: cluster-fused qkv_post + attention + combine, 2: attention + combine only (attn_fused.cuh)
-  bool want_mega = false;
-  int mega_phases = 0;
+  size_t flags_used = 0;        // bump allocator over DFLASH_BUF_FLAGS (one arrival counter per (group, tile) per plan)
+  int ss_ld_step = 0;           // row pitch of the per-tile sum-of-squares planes 0 (fc rows) and 1 (residual rows)
 
   template <class T>
   T* buf(int id) const { return reinterpret_cast<T*>(base + reg[id].off); }
@@ -56,6 +50,7 @@ struct Engine {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 constexpr int kPrefillRows = 256;  // prompt rows projected per pass (one full-width UMMA)
+constexpr int kMaxRowTiles = 64;   // hidden <= 8192: per-tile sum-of-squares planes have 64 tile rows
 
 // UMMA N (activation rows per MMA) for a GEMM over `rows` activation rows; more rows run as column groups.
 inline int round_mb(int rows) {
@@ -64,6 +59,8 @@ inline int round_mb(int rows) {
   return 256;
 }
 inline int groups_of(int rows) { const int mb = round_mb(rows); return (rows + mb - 1) / mb; }
+// rows an activation buffer is allocated with, so that a TMA box of mb rows never leaves it
+inline int rows_padded(int rows) { return groups_of(rows) * round_mb(rows); }
 
 // KV splits of the draft attention: enough (request, kv head, split) CTAs for about two waves, at most 16.
 // One stream needs all 16 to fill the machine; 64 streams already give 512 CTAs and would only pay for the
@@ -86,48 +83,46 @@ inline int default_post_splits(const dflash_config_t& c, int sm_count) {
 }
 
 // Fills reg[] (offsets/sizes) for cfg; returns total bytes or 0 on a bad config.
-inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_count, int* max_slots_out) {
+inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_count) {
   const int SL = c.block_size <= 16 ? 16 : 32;
   const int R = c.max_requests;
   const int RS = R * SL;
+  const int RSp = rows_padded(RS), RS2p = rows_padded(2 * RS);
   const int H = c.hidden, I = c.intermediate, Hq = c.n_q_heads, Hkv = c.n_kv_heads;
   const int grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
   const int nsa = default_attn_splits(c, sm_count);
   const int nsp = default_post_splits(c, sm_count);
-  const int qkv_cols = (Hq + 2 * Hkv) * 128;
-  // widest fp32 partial plane over all GEMMs of the step
-  long long ws_elems = 0;
-  int max_slots = 1;
-  struct G { int rows, N, K; } gs[] = {{RS, H, c.n_sel * H}, {2 * RS, qkv_cols, H}, {RS, H, Hq * 128},
-                                       {RS, 2 * I, H},       {RS, H, I},
-                                       {kPrefillRows, H, c.n_sel * H}, {kPrefillRows, 2 * Hkv * 128, H}};
-  for (auto& g : gs) {
-    const int nt = (g.N + kTileN - 1) / kTileN, kb = g.K / kTileK;
-    const long long T = static_cast<long long>(nt) * kb;
-    const int ranges = ranges_for(grid, groups_of(g.rows));
-    const int gg = T < ranges ? static_cast<int>(T) : ranges;
-    const int s = max_slots_for(nt, kb, gg);
-    const long long e = static_cast<long long>(s) * groups_of(g.rows) * round_mb(g.rows) * g.N;
-    if (e > ws_elems) ws_elems = e;
-    if (s > max_slots) max_slots = s;
+  // partial-accumulator exchange of the fused GEMMs: one [128 x mb] fp32 tile per CTA, the widest launch decides
+  long long part_elems = 0;
+  for (int rows : {RS, 2 * RS, kPrefillRows}) {
+    const long long e = static_cast<long long>(grid) * kTileN * round_mb(rows);  // groups * ranges <= grid CTAs
+    if (e > part_elems) part_elems = e;
   }
-  if (max_slots_out) *max_slots_out = max_slots;
+  // arrival counters: one per (column group, tile) of every fused plan
+  const long long tiles_step = H / kTileN + static_cast<long long>(c.n_layers) *
+                                                ((Hq + 2 * Hkv) + 2 * (H / kTileN) + I / (kTileN / 2));
+  const long long tiles_pf = 5ll * (H / kTileN) + 5ll * c.n_layers * (2 * Hkv);
+  const long long n_flags = tiles_step * groups_of(2 * RS) + tiles_pf;
   size_t sz[DFLASH_BUF_COUNT] = {0};
-  sz[DFLASH_BUF_X] = static_cast<size_t>(RS) * H * 2;
-  sz[DFLASH_BUF_A_IN] = static_cast<size_t>(2 * RS) * H * 2;
-  sz[DFLASH_BUF_CTX_FEAT] = static_cast<size_t>(RS) * c.n_sel * H * 2;
-  sz[DFLASH_BUF_Q] = static_cast<size_t>(RS) * Hq * 128 * 2;
-  sz[DFLASH_BUF_ATTN_OUT] = static_cast<size_t>(RS) * Hq * 128 * 2;
-  sz[DFLASH_BUF_A2] = static_cast<size_t>(RS) * H * 2;
-  sz[DFLASH_BUF_HMID] = static_cast<size_t>(RS) * I * 2;
-  sz[DFLASH_BUF_HN] = static_cast<size_t>(RS) * H * 2;
+  sz[DFLASH_BUF_X] = static_cast<size_t>(RSp) * H * 2;
+  sz[DFLASH_BUF_A_IN] = static_cast<size_t>(RS2p) * H * 2;
+  sz[DFLASH_BUF_CTX_FEAT] = static_cast<size_t>(RSp) * c.n_sel * H * 2;
+  sz[DFLASH_BUF_Q] = static_cast<size_t>(RSp) * Hq * 128 * 2;
+  sz[DFLASH_BUF_ATTN_OUT] = static_cast<size_t>(RSp) * Hq * 128 * 2;
+  sz[DFLASH_BUF_A2] = static_cast<size_t>(RSp) * H * 2;
+  sz[DFLASH_BUF_HMID] = static_cast<size_t>(RSp) * I * 2;
+  sz[DFLASH_BUF_HN] = static_cast<size_t>(RSp) * H * 2;
   sz[DFLASH_BUF_KV] = static_cast<size_t>(c.n_layers) * 2 * R * Hkv * c.max_seq * 128 * 2;
-  sz[DFLASH_BUF_WS] = static_cast<size_t>(ws_elems) * 4;
+  sz[DFLASH_BUF_Y_CTX] = static_cast<size_t>(RSp) * H * 2;
+  sz[DFLASH_BUF_TILE_SS] = static_cast<size_t>(kMaxRowTiles) * (2 * RSp + kPrefillRows) * 4;
+  sz[DFLASH_BUF_PART] = static_cast<size_t>(part_elems) * 4;
+  sz[DFLASH_BUF_FLAGS] = static_cast<size_t>(n_flags) * 4;
+  sz[DFLASH_BUF_COUNTERS] = static_cast<size_t>(R + 2) * 4;
   sz[DFLASH_BUF_ATTN_PO] = static_cast<size_t>(nsa) * RS * Hq * 128 * 4;
   sz[DFLASH_BUF_ATTN_ML] = static_cast<size_t>(nsa) * RS * Hq * 2 * 4;
   const int ncand = c.max_candidates > 1 ? 4 : 1;
-  sz[DFLASH_BUF_CAND_VAL] = static_cast<size_t>(grid) * RS * 4 * ncand;
-  sz[DFLASH_BUF_CAND_IDX] = static_cast<size_t>(grid) * RS * 4 * ncand;
+  sz[DFLASH_BUF_CAND_VAL] = static_cast<size_t>(grid) * RSp * 4 * ncand;
+  sz[DFLASH_BUF_CAND_IDX] = static_cast<size_t>(grid) * RSp * 4 * ncand;
   sz[DFLASH_BUF_POST_VAL] = static_cast<size_t>(R) * c.block_size * nsp * 4 * ncand;
   sz[DFLASH_BUF_POST_IDX] = static_cast<size_t>(R) * c.block_size * nsp * 4 * ncand;
   sz[DFLASH_BUF_TOPK_IDX] = static_cast<size_t>(RS) * 4 * 4;
@@ -143,13 +138,10 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
       sz[DFLASH_BUF_BLK_LEN] = sz[DFLASH_BUF_MAX_LEN] = static_cast<size_t>(R) * 4;
   sz[DFLASH_BUF_ACC_HIST] = static_cast<size_t>(R) * c.hist_len * 4;
   sz[DFLASH_BUF_RNG_STEP] = 8;
-  sz[DFLASH_BUF_DRAFT_LOGITS] = c.keep_draft_logits ? static_cast<size_t>(RS) * c.vocab * 2 : 0;
-  const int max_phases = 3 + 12 * c.n_layers + 2, max_gemms = 2 + 4 * c.n_layers;
-  sz[DFLASH_BUF_MEGA_GEMMS] = static_cast<size_t>(max_gemms) * sizeof(MegaGemm);
-  sz[DFLASH_BUF_MEGA_PHASES] = static_cast<size_t>(max_phases) * sizeof(MegaPhase);
-  sz[DFLASH_BUF_MEGA_SYNC] = static_cast<size_t>(4 * max_phases + 16) * 8;
+  sz[DFLASH_BUF_DRAFT_LOGITS] = c.keep_draft_logits ? static_cast<size_t>(RSp) * c.vocab * 2 : 0;
   sz[DFLASH_BUF_PF_FEAT] = static_cast<size_t>(kPrefillRows) * c.n_sel * H * 2;
   sz[DFLASH_BUF_PF_A] = static_cast<size_t>(kPrefillRows) * H * 2;
+  sz[DFLASH_BUF_PF_Y] = static_cast<size_t>(kPrefillRows) * H * 2;
   size_t off = 0;
   for (int i = 0; i < DFLASH_BUF_COUNT; ++i) {
     reg[i].off = off;
@@ -161,8 +153,8 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
 
 inline int check_config(const dflash_config_t& c) {
   if (c.head_dim != 128) { set_error("head_dim %d unsupported (128 only)", c.head_dim); return DFLASH_ERR_ARG; }
-  if (c.hidden % 64 || c.intermediate % 64 || c.hidden > 8192) {
-    set_error("hidden/intermediate must be multiples of 64 and hidden <= 8192");
+  if (c.hidden % 128 || c.intermediate % 64 || c.hidden > 8192) {
+    set_error("hidden must be a multiple of 128 (<= 8192) and intermediate a multiple of 64");
     return DFLASH_ERR_ARG;
   }
   if (c.block_size < 2 || c.block_size > 32) { set_error("block_size must be in [2,32]"); return DFLASH_ERR_ARG; }
@@ -173,10 +165,6 @@ inline int check_config(const dflash_config_t& c) {
   const int SL = c.block_size <= 16 ? 16 : 32;
   if (c.max_requests < 1 || c.max_requests > 64) {
     set_error("max_requests %d unsupported: 1..64 request streams per engine", c.max_requests);
-    return DFLASH_ERR_ARG;
-  }
-  if ((c.max_requests & (c.max_requests - 1)) != 0) {
-    set_error("max_requests %d must be a power of two (activation buffers are exact UMMA widths)", c.max_requests);
     return DFLASH_ERR_ARG;
   }
   if (c.max_candidates < 0 || c.max_candidates > 4 || (c.max_candidates > 1 && c.max_requests * SL > 32)) {
@@ -192,23 +180,15 @@ inline int check_config(const dflash_config_t& c) {
   return DFLASH_OK;
 }
 
-// Timing ablation only (results become wrong): DFLASH_DEBUG_SKIP bitmask drops kernels from the schedule.
-// 1 finalize_rows, 2 swiglu, 4 attn_combine, 8 qkv_post, 16 attn_split, 32 partial GEMMs, 64 lm_head GEMM
-inline int dbg_skip() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DFLASH_DEBUG_SKIP"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
 #define DFL_CUDA(expr, what)                              \
   do {                                                    \
     cudaError_t _e = (expr);                              \
     if (_e != cudaSuccess) return cuda_fail(_e, what);    \
   } while (0)
 
-template <class Kern, class Args>
+template <class Kern, class... Args>
 inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
-                              const Args& args) {
+                              const Args&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -220,28 +200,30 @@ inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, args);
+  return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-template <class Kern, class Args>
-inline cudaError_t launch_cluster_pdl(Kern kern, dim3 grid, dim3 block, dim3 cluster, size_t smem, cudaStream_t st,
-                                      bool pdl, const Args& args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cluster.x;
-  at[0].val.clusterDim.y = cluster.y;
-  at[0].val.clusterDim.z = cluster.z;
-  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, args);
+inline QkvPostArgs qkv_post_args(Engine* e, int l, bool kv_only) {
+  QkvPostArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = e->R; a.SL = e->SL; a.bs = e->bs; a.Hq = e->Hq; a.Hkv = e->Hkv;
+  a.q_cols = kv_only ? 0 : e->Hq * 128;
+  a.start = e->buf<int>(DFLASH_BUF_START);
+  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  a.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  a.q_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].q_norm);
+  a.k_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].k_norm);
+  const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(e->layers[l].bqkv);
+  a.bias = b == nullptr ? nullptr : (kv_only ? b + e->Hq * 128 : b);
+  a.inv_freq = e->w.inv_freq;
+  a.rope_scale = e->cfg.rope_scale;
+  a.eps = e->cfg.rms_eps;
+  a.q_out = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
+  const size_t per = static_cast<size_t>(e->R) * e->Hkv * e->cfg.max_seq * 128;
+  a.k_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 0) * per;
+  a.v_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 1) * per;
+  a.S_max = e->cfg.max_seq;
+  return a;
 }
 
 inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, void* workspace,
@@ -262,7 +244,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->nsplit_attn = default_attn_splits(c, sm_count);
   e->nsplit_post = default_post_splits(c, sm_count);
   e->pdl = c.use_pdl != 0;
-  e->total = layout_workspace(c, e->reg, sm_count, &e->max_slots);
+  e->total = layout_workspace(c, e->reg, sm_count);
   if (workspace == nullptr || workspace_bytes < e->total) {
     set_error("workspace too small: need %zu bytes, got %zu", e->total, workspace_bytes);
     delete e;
@@ -276,242 +258,187 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->base = static_cast<uint8_t*>(workspace);
 
   const int RS = e->RS, H = e->H, I = e->I;
+  const int RSp = rows_padded(RS), RS2p = rows_padded(2 * RS);
   const int qkv_cols = (e->Hq + 2 * e->Hkv) * 128;
   const int mb_blk = round_mb(RS), mb_all = round_mb(2 * RS);
-  float* ws = e->buf<float>(DFLASH_BUF_WS);
-  auto finish = [&](GemmPlan& p, int) {
-    p.args.ws = ws;
-    p.args.ws_rows = p.groups * p.mb;
-    p.args.ws_ld = p.args.N;
+  e->ss_ld_step = RSp;
+  float* ss_fc = e->buf<float>(DFLASH_BUF_TILE_SS);
+  float* ss_x = ss_fc + static_cast<size_t>(kMaxRowTiles) * RSp;
+  float* ss_pf = ss_x + static_cast<size_t>(kMaxRowTiles) * RSp;
+  __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
+  // every fused plan gets the shared partial-exchange region and its own arrival counters
+  auto finish = [&](GemmPlan& p) -> int {
+    p.args.part = e->buf<float>(DFLASH_BUF_PART);
+    const size_t need = static_cast<size_t>(p.groups) * p.grid * kTileN * p.mb * 4;
+    const size_t nflags = static_cast<size_t>(p.groups) * p.args.n_tiles;
+    if (need > e->reg[DFLASH_BUF_PART].bytes || (e->flags_used + nflags) * 4 > e->reg[DFLASH_BUF_FLAGS].bytes) {
+      set_error("internal: fused GEMM scratch regions too small");
+      return -1;
+    }
+    p.args.flags = e->buf<unsigned int>(DFLASH_BUF_FLAGS) + e->flags_used;
+    e->flags_used += nflags;
+    return 0;
+  };
+  auto rows_epi = [&](GemmPlan& p, const void* bias, __nv_bfloat16* resid, __nv_bfloat16* out, float* ss, int ss_ld) {
+    p.args.rows.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.args.rows.resid = resid;
+    p.args.rows.out = out;
+    p.args.rows.ld = H;
+    p.args.rows.tile_ss = ss;
+    p.args.rows.ss_ld = ss_ld;
   };
 #define DFL_PLAN(call)        \
   do {                        \
     int _rc = (call);         \
     if (_rc) { delete e; return DFLASH_ERR_ARG; } \
   } while (0)
-  // activation TMA tensors are declared with mb rows so the box never leaves the allocation:
-  // buffers of RS (or 2*RS) rows are exactly mb rows when RS is a power of two >= 16.
-  DFL_PLAN(make_gemm_plan(&e->fc, w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_CTX_FEAT), RS, 0, mb_blk, RS,
-                          kModePartials, e->grid));
-  finish(e->fc, mb_blk);
+  // activation TMA tensors are declared with the buffers' padded row counts (a multiple of the UMMA width), so a box
+  // never leaves the allocation; rows past the live ones are zero and their outputs are never written.
+  DFL_PLAN(make_gemm_plan(&e->fc, w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_CTX_FEAT), RSp, 0, mb_blk, RS,
+                          kModeRows, e->grid));
+  DFL_PLAN(finish(e->fc));
+  rows_epi(e->fc, nullptr, nullptr, e->buf<__nv_bfloat16>(DFLASH_BUF_Y_CTX), ss_fc, RSp);
   e->qkv.resize(e->L); e->kv_pf.resize(e->L * 5); e->o.resize(e->L); e->gu.resize(e->L); e->d.resize(e->L);
   for (int i = 0; i < 5; ++i) {
     DFL_PLAN(make_gemm_plan(&e->fc_pf[i], w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_PF_FEAT), kPrefillRows, 0,
-                            16 << i, 16 << i, kModePartials, e->grid));
-    finish(e->fc_pf[i], 0);
+                            16 << i, 16 << i, kModeRows, e->grid));
+    DFL_PLAN(finish(e->fc_pf[i]));
+    rows_epi(e->fc_pf[i], nullptr, nullptr, e->buf<__nv_bfloat16>(DFLASH_BUF_PF_Y), ss_pf, kPrefillRows);
   }
   for (int l = 0; l < e->L; ++l) {
     const dflash_layer_weights_t& lw = e->layers[l];
-    DFL_PLAN(make_gemm_plan(&e->qkv[l], lw.wqkv, qkv_cols, 0, qkv_cols, H, e->buf<void>(DFLASH_BUF_A_IN), 2 * RS, 0,
-                            mb_all, 2 * RS, kModePartials, e->grid));
-    finish(e->qkv[l], mb_all);
+    DFL_PLAN(make_gemm_plan(&e->qkv[l], lw.wqkv, qkv_cols, 0, qkv_cols, H, e->buf<void>(DFLASH_BUF_A_IN), RS2p, 0,
+                            mb_all, 2 * RS, kModeQkv, e->grid));
+    DFL_PLAN(finish(e->qkv[l]));
+    e->qkv[l].args.qkv = qkv_post_args(e, l, false);
     for (int i = 0; i < 5; ++i) {
       GemmPlan& kp = e->kv_pf[l * 5 + i];
       DFL_PLAN(make_gemm_plan(&kp, lw.wqkv, qkv_cols, e->Hq * 128, 2 * e->Hkv * 128, H, e->buf<void>(DFLASH_BUF_PF_A),
-                              kPrefillRows, 0, 16 << i, 16 << i, kModePartials, e->grid));
-      finish(kp, 0);
+                              kPrefillRows, 0, 16 << i, 16 << i, kModeQkv, e->grid));
+      DFL_PLAN(finish(kp));
+      kp.args.qkv = qkv_post_args(e, l, true);
     }
-    DFL_PLAN(make_gemm_plan(&e->o[l], lw.wo, H, 0, H, e->Hq * 128, e->buf<void>(DFLASH_BUF_ATTN_OUT), RS, 0, mb_blk, RS,
-                            kModePartials, e->grid));
-    finish(e->o[l], mb_blk);
-    DFL_PLAN(make_gemm_plan(&e->gu[l], lw.wgu, 2 * I, 0, 2 * I, H, e->buf<void>(DFLASH_BUF_A2), RS, 0, mb_blk, RS,
-                            kModePartials, e->grid));
-    finish(e->gu[l], mb_blk);
-    DFL_PLAN(make_gemm_plan(&e->d[l], lw.wd, H, 0, H, I, e->buf<void>(DFLASH_BUF_HMID), RS, 0, mb_blk, RS,
-                            kModePartials, e->grid));
-    finish(e->d[l], mb_blk);
+    DFL_PLAN(make_gemm_plan(&e->o[l], lw.wo, H, 0, H, e->Hq * 128, e->buf<void>(DFLASH_BUF_ATTN_OUT), RSp, 0, mb_blk, RS,
+                            kModeRows, e->grid));
+    DFL_PLAN(finish(e->o[l]));
+    rows_epi(e->o[l], lw.bo, x, x, ss_x, RSp);
+    DFL_PLAN(make_gemm_plan(&e->gu[l], lw.wgu, 2 * I, 0, 2 * I, H, e->buf<void>(DFLASH_BUF_A2), RSp, 0, mb_blk, RS,
+                            kModeSwiglu, e->grid));
+    DFL_PLAN(finish(e->gu[l]));
+    e->gu[l].args.sw.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
+    e->gu[l].args.sw.ld = I;
+    DFL_PLAN(make_gemm_plan(&e->d[l], lw.wd, H, 0, H, I, e->buf<void>(DFLASH_BUF_HMID), RSp, 0, mb_blk, RS,
+                            kModeRows, e->grid));
+    DFL_PLAN(finish(e->d[l]));
+    rows_epi(e->d[l], nullptr, x, x, ss_x, RSp);
   }
-  const int lm_grid = getenv("DFLASH_LM_GRID") ? atoi(getenv("DFLASH_LM_GRID")) : e->grid;  // (make_gemm_plan balances it)
-  DFL_PLAN(make_gemm_plan(&e->lm, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
-                          c.keep_draft_logits ? kModeArgmaxDump : kModeArgmax, lm_grid));
-  e->lm.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
-  e->lm.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
+  unsigned int* counters = e->buf<unsigned int>(DFLASH_BUF_COUNTERS);
+  auto tok_fields = [&](GemmPlan& p) {
+    p.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
+    p.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
+    p.args.tok_counter = counters + e->R + 1;
+    p.args.tok_block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+    p.args.tok_draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
+    p.args.tok_SL = e->SL;
+    p.args.tok_bs = e->bs;
+    p.args.tok_rows = RS;
+  };
+  DFL_PLAN(make_gemm_plan(&e->lm, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RSp, 0, mb_blk, RS,
+                          c.keep_draft_logits ? kModeArgmaxDump : kModeArgmax, e->grid));
+  tok_fields(e->lm);
   e->lm.args.logits = c.keep_draft_logits ? e->buf<__nv_bfloat16>(DFLASH_BUF_DRAFT_LOGITS) : nullptr;
   e->lm.args.logits_ld = e->V;
   if (mb_blk <= 32) {
-    DFL_PLAN(make_gemm_plan(&e->lm_sample, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
-                            kModeSample, lm_grid));
-    e->lm_sample.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
-    e->lm_sample.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
+    DFL_PLAN(make_gemm_plan(&e->lm_sample, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RSp, 0, mb_blk, RS,
+                            kModeSample, e->grid));
+    tok_fields(e->lm_sample);
     e->lm_sample.args.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
     e->has_sample = true;
   }
   e->max_cand = c.max_candidates > 1 ? c.max_candidates : 1;
   if (e->max_cand > 1) {
-    DFL_PLAN(make_gemm_plan(&e->lm_topk, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RS, 0, mb_blk, RS,
-                            kModeTopK, lm_grid));
+    DFL_PLAN(make_gemm_plan(&e->lm_topk, w.lm_head, e->V, 0, e->V, H, e->buf<void>(DFLASH_BUF_HN), RSp, 0, mb_blk, RS,
+                            kModeTopK, e->grid));
     e->lm_topk.args.cand_val = e->buf<float>(DFLASH_BUF_CAND_VAL);
     e->lm_topk.args.cand_idx = e->buf<int>(DFLASH_BUF_CAND_IDX);
   }
 #undef DFL_PLAN
-  // Pre-wait L2 prefetch budget per GEMM (HBM work for the time the small kernel in front of it runs).
-  // OFF by default: measured on B200 (profiles/r1_summary.md) it never beat plain TMA streaming -- a byte
-  // that is prefetched crosses the L2 twice (fill, then hit), and L2 throughput is only ~1.6x HBM.
-  {
-    const long long bytes = c.prefetch_mb <= 0 ? 0 : static_cast<long long>(c.prefetch_mb) << 20;
-    set_gemm_prefetch(&e->fc, bytes);
-    for (int l = 0; l < e->L; ++l) {
-      set_gemm_prefetch(&e->qkv[l], bytes);
-      set_gemm_prefetch(&e->o[l], bytes);
-      set_gemm_prefetch(&e->gu[l], bytes);
-      set_gemm_prefetch(&e->d[l], bytes);
-    }
-    set_gemm_prefetch(&e->lm, bytes);
-  }
   cudaError_t ce = cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
-  ce = cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
-  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize smem attribute"); }
-  ce = cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
-  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize2 smem attribute"); }
   // One shared-memory carveout for every kernel of the step: consecutive kernels with different L1/smem splits
   // cannot share an SM, which would serialise exactly the PDL overlaps the schedule relies on.
-  if (!getenv("DFLASH_NO_CARVEOUT")) {
+  {
     const int mx = cudaSharedmemCarveoutMaxShared;
-    cudaFuncSetAttribute(gemm_skinny_kernel<16, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<32, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<64, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<128, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<256, kModePartials>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<16, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<32, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<64, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<128, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(gemm_skinny_kernel<256, kModeArgmax>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(finalize_rows_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(swiglu_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(norm_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(rows_pre_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(draft_tokens_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(verify_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(accept_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(ctx_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaGetLastError();
-  }
-  e->want_mega = c.use_mega != 0;
-  {
-    const char* fe = getenv("DFLASH_FUSED_ATTN");
-    const int group = e->Hq / e->Hkv;
-    e->fused_attn = fe != nullptr ? atoi(fe) : 0;  // opt-in: measured 758 vs 750 us/step, no gain
-    if (e->fused_attn) {
-      ce = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_fused_smem(group));
-      if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "fused attention smem attribute"); }
-    }
   }
   *out = e;
   return DFLASH_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-inline RowsArgs rows_args_base(const Engine* e) {
-  RowsArgs a;
+inline NormArgs norm_args(const Engine* e, const __nv_bfloat16* x, const float* ss, int ss_ld, const void* w,
+                          __nv_bfloat16* out) {
+  NormArgs a;
   memset(&a, 0, sizeof(a));
+  a.x = x;
+  a.tile_ss = ss;
+  a.ss_ld = ss_ld;
   a.H = e->H;
+  a.w = static_cast<const __nv_bfloat16*>(w);
+  a.out = out;
+  a.eps = e->cfg.rms_eps;
   a.SL = e->SL;
-  a.bs = e->bs;
-  a.eps = e->cfg.rms_eps;
-  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-  a.valid_mode = kRowsAll;
   return a;
 }
 
-// Per-layer row pass (partials + residual + RMSNorm): four CTAs per row when the width allows it
-inline cudaError_t launch_finalize(Engine* e, const RowsArgs& a, int rows, cudaStream_t st) {
-  static const bool no_cluster = getenv("DFLASH_NO_ROW_CLUSTER") != nullptr;
-  const bool ok = !no_cluster && a.ws != nullptr && a.embed == nullptr && a.norm_w != nullptr &&
-                  e->H % (4 * kRowCtas) == 0 && e->H / kRowCtas <= kRowClThreads * 4 * kRowClGroups;
-  if (ok)
-    return launch_cluster_pdl(finalize_rows_cluster_kernel, dim3(kRowCtas, rows), dim3(kRowClThreads),
-                              dim3(kRowCtas, 1, 1), 0, st, e->pdl, a);
-  return launch_pdl(finalize_rows_kernel, dim3(rows), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a);
-}
-
-// fc GEMM + hidden_norm over the pending context rows -> a_in rows [0, RS)   (dflash.py:177)
-inline RowsArgs ctx_finalize_args(Engine* e) {
-  RowsArgs a = rows_args_base(e);
-  a.ws = e->fc.args.ws;
-  a.sm = slot_map_of(e->fc);
-  a.valid_mode = kRowsCtx;
-  a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
-  a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  return a;
-}
-
-inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_only) {
-  QkvPostArgs a;
-  memset(&a, 0, sizeof(a));
-  a.ws = p.args.ws;
-  a.sm = slot_map_of(p);
-  a.R = e->R; a.SL = e->SL; a.bs = e->bs; a.Hq = e->Hq; a.Hkv = e->Hkv;
-  a.q_cols = kv_only ? 0 : e->Hq * 128;
-  a.row0 = 0;
-  a.rows = kv_only ? e->RS : 2 * e->RS;
-  a.start = e->buf<int>(DFLASH_BUF_START);
-  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-  a.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
-  a.q_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].q_norm);
-  a.k_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].k_norm);
-  a.inv_freq = e->w.inv_freq;
-  a.rope_scale = e->cfg.rope_scale;
-  a.eps = e->cfg.rms_eps;
-  a.q_out = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
-  const size_t per = static_cast<size_t>(e->R) * e->Hkv * e->cfg.max_seq * 128;
-  a.k_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 0) * per;
-  a.v_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 1) * per;
-  a.S_max = e->cfg.max_seq;
-  return a;
-}
-
-// One draft step: block embedding -> ctx inject -> L layers -> final norm -> lm_head + argmax.
-// Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247).
-inline int enqueue_draft_step_mega(Engine* e, cudaStream_t st);
-
+// One draft step: ctx injection -> block embedding -> L layers -> final norm -> lm_head + argmax.
+// Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247). 2 + 8 L + 1 launches:
+//   fc GEMM [bf16 rows + sums of squares]            rows_pre [hidden_norm of the ctx rows | embed + ln1 of the block]
+//   per layer: qkv GEMM [q/k norm, RoPE, cache write] - attention split - merge - o GEMM [+ residual] - norm -
+//              gate/up GEMM [SwiGLU] - down GEMM [+ residual] - norm
+//   lm_head GEMM [argmax, drafted tokens]
 // n_candidates > 1: top-4 lm_head epilogue + candidate blocks (fixed_prefix_rank) instead of the plain argmax tail
 inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st,
                               int n_candidates = 1, int fixed_prefix_len = 0, float draft_temperature = 0.f,
                               unsigned long long draft_seed = 0) {
-  if (e->mega && noise_embedding == nullptr && run_lm_head && n_candidates <= 1 && draft_temperature < 1e-5f)
-    return enqueue_draft_step_mega(e, st);
-  const int RS = e->RS;
+  const int RS = e->RS, RSp = e->ss_ld_step;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
+  const float* ss_fc = e->buf<float>(DFLASH_BUF_TILE_SS);
+  const float* ss_x = ss_fc + static_cast<size_t>(kMaxRowTiles) * RSp;
   // ctx injection GEMM first (it only reads the features gathered by the previous verify step), then ONE row kernel
-  // for both the context finalize (fc -> hidden_norm -> a_in ctx rows) and the block rows
+  // for both the context rows (hidden_norm -> a_in ctx rows) and the block rows
   // (embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows)
-  if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
+  DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
   {
-    RowsArgs a = rows_args_base(e);
+    NormArgs c = norm_args(e, e->buf<__nv_bfloat16>(DFLASH_BUF_Y_CTX), ss_fc, RSp, e->w.hidden_norm, a_in);
+    c.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+    EmbedArgs b;
+    memset(&b, 0, sizeof(b));
     if (noise_embedding != nullptr) {
-      a.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
-      a.ids = nullptr;
+      b.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
+      b.ids = nullptr;
     } else {
-      a.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
-      a.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+      b.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
+      b.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
     }
-    a.ids_ld = e->bs;
-    a.pad_token = e->cfg.mask_token_id;
-    a.resid = x;
-    a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
-    a.out = a_in + static_cast<size_t>(RS) * e->H;
-    const RowsArgs c = ctx_finalize_args(e);
-    if (!(dbg_skip() & 1)) {
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(2 * RS);
-      cfg.blockDim = dim3(kRowsThreads);
-      cfg.dynamicSmemBytes = static_cast<size_t>(e->H) * 6;
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = e->pdl ? 1 : 0;
-      DFL_CUDA(cudaLaunchKernelEx(&cfg, finalize_rows2_kernel, c, a, RS), "ctx finalize + embed + ln1");
-    }
+    b.ids_ld = e->bs;
+    b.pad_token = e->cfg.mask_token_id;
+    b.bs = e->bs; b.H = e->H; b.SL = e->SL;
+    b.resid = x;
+    b.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
+    b.out = a_in + static_cast<size_t>(RS) * e->H;
+    b.eps = e->cfg.rms_eps;
+    DFL_CUDA(launch_pdl(rows_pre_kernel, dim3(2 * RS), dim3(kNormThreads), 0, st, e->pdl, c, b, RS),
+             "ctx norm + embed + ln1");
   }
   AttnArgs aa;
   memset(&aa, 0, sizeof(aa));
@@ -519,9 +446,7 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   aa.nsplit = e->nsplit_attn;
   aa.start = e->buf<int>(DFLASH_BUF_START);
   aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
-#ifndef DFLASH_NO_KV_PREFETCH
   aa.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-#endif
   aa.q = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
   aa.part_o = e->buf<float>(DFLASH_BUF_ATTN_PO);
   aa.part_ml = e->buf<float>(DFLASH_BUF_ATTN_ML);
@@ -529,65 +454,24 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   aa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_ATTN_OUT);
   const int group = e->Hq / e->Hkv;
   for (int l = 0; l < e->L; ++l) {
-    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->qkv[l], st, e->pdl), "qkv gemm");
-    QkvPostArgs qa = qkv_post_args(e, l, e->qkv[l], false);
-    const int items = qa.rows * (e->Hq + 2 * e->Hkv);
-    aa.k_cache = qa.k_cache;
-    aa.v_cache = qa.v_cache;
-    if (e->fused_attn && !dbg_skip()) {
-      if (e->fused_attn == 2)
-        DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, qa), "qkv post");
-      AttnFusedArgs fa;
-      fa.post = qa;
-      fa.attn = aa;
-      fa.fuse_post = e->fused_attn == 1;
-      fa.attn.nsplit = kFusedSplits;
-      DFL_CUDA(launch_cluster_pdl(attn_fused_kernel, dim3(kFusedSplits, e->Hkv, e->R * (e->SL / 16)),
-                                  dim3(32 * (group + kFusedPostWarps)), dim3(kFusedSplits, 1, 1), attn_fused_smem(group), st, e->pdl, fa),
-               "fused attention");
-    } else {
-    if (!(dbg_skip() & 8)) DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, qa), "qkv post");
-    if (!(dbg_skip() & 16)) DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
-                        kAttnSmem, st, e->pdl, aa),
-             "attention");
-    if (!(dbg_skip() & 4)) DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, aa),
-             "attention combine");
-    }
-    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
-    {
-      RowsArgs a = rows_args_base(e);
-      a.ws = e->o[l].args.ws;
-      a.sm = slot_map_of(e->o[l]);
-      a.resid = x;
-      a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
-      a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
-      if (!(dbg_skip() & 1)) DFL_CUDA(launch_finalize(e, a, RS, st), "o finalize");
-    }
-    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
-    {
-      SwigluArgs sa;
-      sa.ws = e->gu[l].args.ws;
-      sa.sm = slot_map_of(e->gu[l]);
-      sa.rows = RS;
-      sa.I = e->I;
-      sa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
-      if (!(dbg_skip() & 2)) DFL_CUDA(launch_pdl(swiglu_kernel, dim3((e->I / 4 + kSwigluThreads - 1) / kSwigluThreads, RS), dim3(kSwigluThreads), 0, st, e->pdl, sa), "swiglu");
-    }
-    if (!(dbg_skip() & 32)) DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
-    {
-      RowsArgs a = rows_args_base(e);
-      a.ws = e->d[l].args.ws;
-      a.sm = slot_map_of(e->d[l]);
-      a.resid = x;
-      if (l + 1 < e->L) {
-        a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l + 1].ln1);
-        a.out = a_in + static_cast<size_t>(RS) * e->H;
-      } else {
-        a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
-        a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
-      }
-      if (!(dbg_skip() & 1)) DFL_CUDA(launch_finalize(e, a, RS, st), "down finalize");
-    }
+    DFL_CUDA(launch_gemm(e->qkv[l], st, e->pdl), "qkv gemm");
+    aa.k_cache = e->qkv[l].args.qkv.k_cache;
+    aa.v_cache = e->qkv[l].args.qkv.v_cache;
+    DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
+                        kAttnSmem, st, e->pdl, aa), "attention");
+    DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0,
+                        st, e->pdl, aa), "attention combine");
+    DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
+    DFL_CUDA(launch_pdl(norm_rows_kernel, dim3(RS), dim3(kNormThreads), 0, st, e->pdl,
+                        norm_args(e, x, ss_x, RSp, e->layers[l].ln2, e->buf<__nv_bfloat16>(DFLASH_BUF_A2))),
+             "post-attention norm");
+    DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
+    DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
+    const bool last = l + 1 == e->L;
+    DFL_CUDA(launch_pdl(norm_rows_kernel, dim3(RS), dim3(kNormThreads), 0, st, e->pdl,
+                        norm_args(e, x, ss_x, RSp, last ? e->w.final_norm : e->layers[l + 1].ln1,
+                                  last ? e->buf<__nv_bfloat16>(DFLASH_BUF_HN) : a_in + static_cast<size_t>(RS) * e->H)),
+             "layer-output norm");
   }
   if (!run_lm_head) return DFLASH_OK;
   if (n_candidates > 1) {
@@ -609,196 +493,15 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     DFL_CUDA(launch_pdl(candidates_kernel, dim3(e->R), dim3(256), 0, st, e->pdl, ca), "candidate blocks");
     return DFLASH_OK;
   }
-  const bool sampled = draft_temperature >= 1e-5f;
-  if (sampled) {
+  if (draft_temperature >= 1e-5f) {
     GemmPlan p = e->lm_sample;
     p.args.inv_temp = 1.0f / draft_temperature;
     p.args.seed = draft_seed;
     p.args.step_base = 0;
     DFL_CUDA(launch_gemm(p, st, e->pdl), "lm_head sampling gemm");
-  } else if (!(dbg_skip() & 64)) {
+  } else {
     DFL_CUDA(launch_gemm(e->lm, st, e->pdl), "lm_head gemm");
   }
-  DraftTokArgs ta;
-  ta.cand_val = e->lm.args.cand_val;
-  ta.cand_idx = e->lm.args.cand_idx;
-  ta.n_cta = e->lm.grid;
-  ta.mb = e->lm.args.cand_ld;
-  ta.R = e->R; ta.SL = e->SL; ta.bs = e->bs;
-  ta.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
-  ta.draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
-  DFL_CUDA(launch_pdl(draft_tokens_kernel, dim3(RS), dim3(32), 0, st, e->pdl, ta), "draft tokens");
-  return DFLASH_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Persistent step kernel: phase / GEMM tables (same argument structs as the stand-alone schedule above).
-inline bool mega_supported(const Engine* e) {
-  return e->RS == 16 && e->Hq / e->Hkv <= 4 && e->H * 6 <= kMegaScratch && e->lm.mb == 16;
-}
-
-inline int build_mega(Engine* e) {
-  std::vector<MegaGemm> gemms;
-  std::vector<MegaPhase> phases;
-  auto add_gemm = [&](const GemmPlan& p) {
-    MegaGemm g;
-    memset(&g, 0, sizeof(g));
-    g.tmW = p.tmW; g.tmX = p.tmX; g.args = p.args; g.mb = p.mb; g.mode = p.mode; g.grid = p.grid;
-    gemms.push_back(g);
-    MegaPhase ph;
-    memset(&ph, 0, sizeof(ph));
-    ph.kind = kPhGemm;
-    ph.gemm = static_cast<int>(gemms.size()) - 1;
-    phases.push_back(ph);
-  };
-  const bool dup_rows = getenv("DFLASH_MEGA_DUP") != nullptr;  // timing experiment only (results wrong)
-  auto add_rows = [&](const RowsArgs& a, int rows) {
-    MegaPhase ph;
-    memset(&ph, 0, sizeof(ph));
-    ph.kind = kPhRows; ph.n_items = rows; ph.u.rows = a;
-    phases.push_back(ph);
-    if (dup_rows && a.resid != nullptr && a.embed == nullptr) phases.push_back(ph);
-  };
-  const int RS = e->RS;
-  __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
-  __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  {
-    RowsArgs a = rows_args_base(e);
-    a.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
-    a.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
-    a.ids_ld = e->bs;
-    a.pad_token = e->cfg.mask_token_id;
-    a.resid = x;
-    a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
-    a.out = a_in + static_cast<size_t>(RS) * e->H;
-    add_rows(a, RS);
-  }
-  add_gemm(e->fc);
-  {
-    RowsArgs a = rows_args_base(e);
-    a.ws = e->fc.args.ws;
-    a.sm = slot_map_of(e->fc);
-    a.valid_mode = kRowsCtx;
-    a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
-    a.out = a_in;
-    add_rows(a, RS);
-  }
-  AttnArgs aa;
-  memset(&aa, 0, sizeof(aa));
-  aa.R = e->R; aa.SL = e->SL; aa.bs = e->bs; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.S_max = e->cfg.max_seq;
-  aa.nsplit = e->nsplit_attn;
-  aa.start = e->buf<int>(DFLASH_BUF_START);
-  aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
-#ifndef DFLASH_NO_KV_PREFETCH
-  aa.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-#endif
-  aa.q = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
-  aa.part_o = e->buf<float>(DFLASH_BUF_ATTN_PO);
-  aa.part_ml = e->buf<float>(DFLASH_BUF_ATTN_ML);
-  aa.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
-  aa.out = e->buf<__nv_bfloat16>(DFLASH_BUF_ATTN_OUT);
-  for (int l = 0; l < e->L; ++l) {
-    add_gemm(e->qkv[l]);
-    QkvPostArgs qa = qkv_post_args(e, l, e->qkv[l], false);
-    {
-      MegaPhase ph;
-      memset(&ph, 0, sizeof(ph));
-      ph.kind = kPhQkvPost; ph.n_items = qa.rows * (e->Hq + 2 * e->Hkv); ph.u.qkv = qa;
-      phases.push_back(ph);
-    }
-    aa.k_cache = qa.k_cache;
-    aa.v_cache = qa.v_cache;
-    {
-      MegaPhase ph;
-      memset(&ph, 0, sizeof(ph));
-      ph.kind = kPhAttn; ph.n_items = e->nsplit_attn * e->Hkv * e->R * (e->SL / 16); ph.u.attn = aa;
-      phases.push_back(ph);
-      ph.kind = kPhCombine; ph.n_items = RS * e->Hq;
-      phases.push_back(ph);
-    }
-    add_gemm(e->o[l]);
-    {
-      RowsArgs a = rows_args_base(e);
-      a.ws = e->o[l].args.ws;
-      a.sm = slot_map_of(e->o[l]);
-      a.resid = x;
-      a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
-      a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
-      add_rows(a, RS);
-    }
-    add_gemm(e->gu[l]);
-    {
-      MegaPhase ph;
-      memset(&ph, 0, sizeof(ph));
-      ph.kind = kPhSwiglu; ph.n_items = RS * (e->I / 4);
-      ph.u.sw.ws = e->gu[l].args.ws;
-      ph.u.sw.sm = slot_map_of(e->gu[l]);
-      ph.u.sw.rows = RS;
-      ph.u.sw.I = e->I;
-      ph.u.sw.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
-      phases.push_back(ph);
-    }
-    add_gemm(e->d[l]);
-    {
-      RowsArgs a = rows_args_base(e);
-      a.ws = e->d[l].args.ws;
-      a.sm = slot_map_of(e->d[l]);
-      a.resid = x;
-      if (l + 1 < e->L) {
-        a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l + 1].ln1);
-        a.out = a_in + static_cast<size_t>(RS) * e->H;
-      } else {
-        a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
-        a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
-      }
-      add_rows(a, RS);
-    }
-  }
-  add_gemm(e->lm);
-  {
-    MegaPhase ph;
-    memset(&ph, 0, sizeof(ph));
-    ph.kind = kPhTokens; ph.n_items = RS;
-    ph.u.tok.cand_val = e->lm.args.cand_val;
-    ph.u.tok.cand_idx = e->lm.args.cand_idx;
-    ph.u.tok.n_cta = e->lm.grid;
-    ph.u.tok.mb = e->lm.mb;
-    ph.u.tok.R = e->R; ph.u.tok.SL = e->SL; ph.u.tok.bs = e->bs;
-    ph.u.tok.block_ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
-    ph.u.tok.draft_tokens = e->buf<long long>(DFLASH_BUF_DRAFT_TOKENS);
-    phases.push_back(ph);
-  }
-  for (size_t i = 0; i < phases.size(); ++i) phases[i].dep = static_cast<int>(i) - 1;
-  phases[1].dep = -1;  // fc GEMM reads ctx_feat (written before this kernel): it overlaps with the embed phase
-  if (gemms.size() * sizeof(MegaGemm) > e->reg[DFLASH_BUF_MEGA_GEMMS].bytes ||
-      phases.size() * sizeof(MegaPhase) > e->reg[DFLASH_BUF_MEGA_PHASES].bytes) {
-    set_error("mega tables do not fit their workspace regions");
-    return DFLASH_ERR_ARG;
-  }
-  DFL_CUDA(cudaMemcpy(e->buf<void>(DFLASH_BUF_MEGA_GEMMS), gemms.data(), gemms.size() * sizeof(MegaGemm),
-                      cudaMemcpyHostToDevice), "mega gemm table upload");
-  DFL_CUDA(cudaMemcpy(e->buf<void>(DFLASH_BUF_MEGA_PHASES), phases.data(), phases.size() * sizeof(MegaPhase),
-                      cudaMemcpyHostToDevice), "mega phase table upload");
-  DFL_CUDA(cudaMemset(e->buf<void>(DFLASH_BUF_MEGA_SYNC), 0, e->reg[DFLASH_BUF_MEGA_SYNC].bytes), "mega sync clear");
-  DFL_CUDA(cudaFuncSetAttribute(draft_step_mega_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kMegaSmemBytes), "mega smem attribute");
-  e->mega_phases = static_cast<int>(phases.size());
-  e->mega = true;
-  return DFLASH_OK;
-}
-
-inline int enqueue_draft_step_mega(Engine* e, cudaStream_t st) {
-  MegaArgs m;
-  m.gemms = e->buf<MegaGemm>(DFLASH_BUF_MEGA_GEMMS);
-  m.phases = e->buf<MegaPhase>(DFLASH_BUF_MEGA_PHASES);
-  m.n_phases = e->mega_phases;
-  unsigned long long* sync = e->buf<unsigned long long>(DFLASH_BUF_MEGA_SYNC);
-  m.bars = sync + 8;
-  m.epoch = sync;
-  m.err = reinterpret_cast<int*>(sync + 1);
-  m.trace = getenv("DFLASH_MEGA_TRACE") ? sync + 8 + (3 + 12 * e->L + 2) : nullptr;
-  draft_step_mega_kernel<16><<<e->grid, kMegaThreads, kMegaSmemBytes, st>>>(m);
-  DFL_CUDA(cudaGetLastError(), "mega step launch");
   return DFLASH_OK;
 }
 
@@ -818,26 +521,25 @@ struct VerifyInputs {
   int n_candidates;  // > 1: rows are [R][n_candidates][bs]
 };
 
-// Posterior sampling -> acceptance/commit/state -> next-cycle context gather  (dflash.py:257-268)
+// Posterior sampling -> acceptance/commit/state -> next-cycle context gather  (dflash.py:257-268).
+// The plain path is ONE kernel (verify_fused_kernel); multi-candidate verify and the given-posterior harness hook
+// keep the three-kernel form (the winner's rows are only known after the acceptance).
 inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st) {
   const int K = v.n_candidates > 1 ? v.n_candidates : 1;
   const int rows = e->R * K * e->bs;
-  if (v.posterior_in == nullptr) {
-    PosteriorArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    pa.logits = static_cast<const __nv_bfloat16*>(v.target_logits);
-    pa.ld = v.logits_ld;
-    pa.rows = rows;
-    pa.V = e->V;
-    pa.nsplit = e->nsplit_post;
-    pa.inv_temp = v.temperature < 1e-5f ? 0.f : 1.0f / v.temperature;
-    pa.noise = v.noise;
-    pa.seed = v.seed;
-    pa.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
-    pa.cand_val = e->buf<float>(DFLASH_BUF_POST_VAL);
-    pa.cand_idx = e->buf<int>(DFLASH_BUF_POST_IDX);
-    DFL_CUDA(launch_pdl(posterior_kernel, dim3(e->nsplit_post, rows), dim3(256), 0, st, e->pdl, pa), "posterior");
-  }
+  PosteriorArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.logits = static_cast<const __nv_bfloat16*>(v.target_logits);
+  pa.ld = v.logits_ld;
+  pa.rows = rows;
+  pa.V = e->V;
+  pa.nsplit = e->nsplit_post;
+  pa.inv_temp = v.temperature < 1e-5f ? 0.f : 1.0f / v.temperature;
+  pa.noise = v.noise;
+  pa.seed = v.seed;
+  pa.rng_step = e->buf<unsigned long long>(DFLASH_BUF_RNG_STEP);
+  pa.cand_val = e->buf<float>(DFLASH_BUF_POST_VAL);
+  pa.cand_idx = e->buf<int>(DFLASH_BUF_POST_IDX);
   AcceptArgs aa;
   memset(&aa, 0, sizeof(aa));
   aa.R = e->R; aa.bs = e->bs; aa.nsplit = e->nsplit_post;
@@ -854,9 +556,6 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
   aa.done = e->buf<int>(DFLASH_BUF_DONE);
   aa.n_cycles = e->buf<int>(DFLASH_BUF_N_CYCLES);
   aa.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
-#ifndef DFLASH_NO_KV_PREFETCH
-  aa.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-#endif
   aa.acc_hist = e->buf<int>(DFLASH_BUF_ACC_HIST);
   aa.hist_ld = e->cfg.hist_len;
   aa.max_len = e->buf<int>(DFLASH_BUF_MAX_LEN);
@@ -871,7 +570,6 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
   aa.cand_ids = e->buf<long long>(DFLASH_BUF_CAND_IDS);
   aa.cand_scores = e->buf<float>(DFLASH_BUF_CAND_SCORES);
   aa.chosen = e->buf<int>(DFLASH_BUF_CHOSEN);
-  DFL_CUDA(launch_pdl(accept_kernel, dim3(e->R), dim3(32), 0, st, e->pdl, aa), "accept");
   GatherArgs ga;
   memset(&ga, 0, sizeof(ga));
   for (int s = 0; s < e->nsel; ++s) ga.src[s] = static_cast<const __nv_bfloat16*>(v.hidden[s]);
@@ -883,6 +581,18 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
   ga.ctx_feat = e->buf<__nv_bfloat16>(DFLASH_BUF_CTX_FEAT);
   ga.K = K;
   ga.chosen = K > 1 ? e->buf<int>(DFLASH_BUF_CHOSEN) : nullptr;
+  if (K == 1 && v.posterior_in == nullptr) {
+    VerifyFusedArgs fa;
+    fa.post = pa;
+    fa.acc = aa;
+    fa.gather = ga;
+    fa.counters = e->buf<unsigned int>(DFLASH_BUF_COUNTERS);
+    DFL_CUDA(launch_pdl(verify_fused_kernel, dim3(e->nsplit_post, rows), dim3(256), 0, st, e->pdl, fa), "verify");
+    return DFLASH_OK;
+  }
+  if (v.posterior_in == nullptr)
+    DFL_CUDA(launch_pdl(posterior_kernel, dim3(e->nsplit_post, rows), dim3(256), 0, st, e->pdl, pa), "posterior");
+  DFL_CUDA(launch_pdl(accept_kernel, dim3(e->R), dim3(32), 0, st, e->pdl, aa), "accept");
   DFL_CUDA(launch_pdl(ctx_gather_kernel, dim3(e->RS, e->nsel), dim3(256), 0, st, e->pdl, ga), "ctx gather");
   return DFLASH_OK;
 }
@@ -897,6 +607,7 @@ inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int n_ro
     set_error("prefill: bad request %d, rows %d or position %d (max_seq %d)", r, n_rows, pos0, e->cfg.max_seq);
     return DFLASH_ERR_ARG;
   }
+  const float* ss_pf = e->buf<float>(DFLASH_BUF_TILE_SS) + 2 * static_cast<size_t>(kMaxRowTiles) * e->ss_ld_step;
   for (int c0 = 0; c0 < n_rows; c0 += kPrefillRows) {
     const int n = n_rows - c0 < kPrefillRows ? n_rows - c0 : kPrefillRows;
     int pi = 0;
@@ -913,24 +624,17 @@ inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int n_ro
     GemmPlan fc = e->fc_pf[pi];
     fc.args.m_valid = n;
     DFL_CUDA(launch_gemm(fc, st, e->pdl), "prefill fc gemm");
-    RowsArgs a = rows_args_base(e);
-    a.ws = fc.args.ws;
-    a.sm = slot_map_of(fc);
-    a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
-    a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_PF_A);
-    DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(n), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a),
-             "prefill fc finalize");
+    DFL_CUDA(launch_pdl(norm_rows_kernel, dim3(n), dim3(kNormThreads), 0, st, e->pdl,
+                        norm_args(e, e->buf<__nv_bfloat16>(DFLASH_BUF_PF_Y), ss_pf, kPrefillRows, e->w.hidden_norm,
+                                  e->buf<__nv_bfloat16>(DFLASH_BUF_PF_A))),
+             "prefill hidden_norm");
     for (int l = 0; l < e->L; ++l) {
       GemmPlan kp = e->kv_pf[l * 5 + pi];
       kp.args.m_valid = n;
+      kp.args.qkv.pf_rows = n;
+      kp.args.qkv.pf_req = r;
+      kp.args.qkv.pf_pos0 = pos0 + c0;
       DFL_CUDA(launch_gemm(kp, st, e->pdl), "prefill kv gemm");
-      QkvPostArgs qa = qkv_post_args(e, l, kp, true);
-      qa.rows = n;
-      qa.pf_rows = n;
-      qa.pf_req = r;
-      qa.pf_pos0 = pos0 + c0;
-      const int items = n * (2 * e->Hkv);
-      DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st, e->pdl, qa), "prefill kv post");
     }
   }
   SetStateArgs sa;

@@ -97,7 +97,22 @@ inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pd
   return cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<MB, MODE>, p.tmW, p.tmX, p.args);
 }
 
+template <int MODE>
+inline cudaError_t launch_gemm_any_mb(const GemmPlan& p, cudaStream_t stream, bool pdl) {
+  switch (p.mb) {
+    case 16: return launch_gemm_t<16, MODE>(p, stream, pdl);
+    case 32: return launch_gemm_t<32, MODE>(p, stream, pdl);
+    case 64: return launch_gemm_t<64, MODE>(p, stream, pdl);
+    case 128: return launch_gemm_t<128, MODE>(p, stream, pdl);
+    case 256: return launch_gemm_t<256, MODE>(p, stream, pdl);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl) {
+  if (p.mode == kModeRows) return launch_gemm_any_mb<kModeRows>(p, stream, pdl);
+  if (p.mode == kModeSwiglu) return launch_gemm_any_mb<kModeSwiglu>(p, stream, pdl);
+  if (p.mode == kModeQkv) return launch_gemm_any_mb<kModeQkv>(p, stream, pdl);
   if (p.mode == kModeSample) {
     switch (p.mb) {
       case 16: return launch_gemm_t<16, kModeSample>(p, stream, pdl);
@@ -142,14 +157,6 @@ inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl)
   }
 }
 
-// Pre-wait L2 prefetch budget: `bytes` of this GEMM's weights in total, split evenly over its CTAs.
-inline void set_gemm_prefetch(GemmPlan* p, long long bytes) {
-  const long long unit_bytes = static_cast<long long>(kTileN) * kTileK * 2;
-  long long per_cta = bytes <= 0 ? 0 : bytes / unit_bytes / (p->grid > 0 ? p->grid : 1);
-  if (bytes > 0 && per_cta < 1) per_cta = 1;
-  p->args.pf_units = static_cast<int>(per_cta);
-}
-
 // Weight ranges a GEMM with `groups` column groups is cut into: the groups of one range run side by side,
 // so ranges * groups ~ one wave of CTAs.
 inline int ranges_for(int grid, int groups) { return grid / groups > 0 ? grid / groups : 1; }
@@ -163,6 +170,8 @@ inline int balanced_tile_grid(int n_tiles, int grid) {
 }
 
 // Fill a plan. W: [w_rows_total, K] bf16 (pitch K); the GEMM covers weight rows [w_row0, w_row0+N).
+// kModeSwiglu: W is the [gate; up] stack, N = 2 * intermediate; tile t = gate rows [64t, 64t+64) + up rows
+// [I + 64t, I + 64t + 64), so there are I / 64 tiles and the weight map has 64-row boxes.
 // X: [x_rows_total, K] bf16 (pitch K); activation rows [x_row0, x_row0+groups*mb) feed the MMA in `groups`
 // slabs of mb rows (groups = ceil(m_valid / mb)).
 inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, int w_row0, int N, int K,
@@ -177,15 +186,14 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   const int groups = m_valid > mb ? (m_valid + mb - 1) / mb : 1;
   if (x_row0 + groups * mb > x_rows_total) { set_error("gemm: activation buffer too small"); return -1; }
   grid = ranges_for(grid, groups);
-  int rc = make_tmap_bf16(&p->tmW, W, w_rows_total, K, K, kTileN);
+  if (mode_is_fused(mode) && N % kTileN != 0) {
+    set_error("gemm: fused epilogues need N (%d) to be a multiple of %d", N, kTileN);
+    return -1;
+  }
+  int rc = make_tmap_bf16(&p->tmW, W, w_rows_total, K, K, mode == kModeSwiglu ? kTileN / 2 : kTileN);
   if (rc) return rc;
   rc = make_tmap_bf16(&p->tmX, X, x_rows_total, K, K, mb);
   if (rc) return rc;
-  p->args.w_ptr = W;
-  p->args.w_ld = K;
-  p->args.w_rows = static_cast<int>(w_rows_total);
-  p->args.pf_units = 0;
-  p->args.late_w = getenv("DFLASH_LATE_W") ? atoi(getenv("DFLASH_LATE_W")) : 0;  // 1: late W issue, 2: no X reloads (timing experiments)
   p->mb = mb;
   p->mode = mode;
   p->groups = groups;
@@ -198,11 +206,12 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   p->args.x_row0 = x_row0;
   p->args.m_valid = m_valid;
   const long long T = static_cast<long long>(p->args.n_tiles) * p->args.k_blocks;
+  if (mode == kModeSwiglu) p->args.sw.I = N / 2;
   if (mode == kModePartials && (T + 1) * grid >= (1ll << 31)) {
     set_error("gemm: %lld work units x %d CTAs overflows the consumers' 32-bit slot arithmetic", T, grid);
     return -1;
   }
-  if (mode != kModePartials) {
+  if (mode_is_whole_tile(mode)) {
     // Whole 128-row tiles per CTA: 1187 vocab tiles over 148 CTAs would leave three CTAs with 9 tiles and the rest
     // with 8, and the kernel would last 9 tiles' time at 8/9 of the bandwidth (in-graph timeline: block 0 done 31 us
     // before the kernel). Take the smallest grid with the same maximum -- ceil(1187 / 9) = 132 CTAs of 9 tiles; the

@@ -19,6 +19,7 @@
 // Replaces the reference's nn.Linear call sites on the hot path: model/dflash.py:70-76,101,177,
 // Qwen3MLP (transformers) via :143, and target.lm_head at :238-245.
 #pragma once
+#include "epilogues.cuh"
 #include "ptx.cuh"
 
 namespace dfl {
@@ -36,6 +37,13 @@ enum GemmMode : int {
                       // (multi-candidate drafting: benchmark_candidate_solutions.py:181-249)
   kModeSample = 4,    // whole tiles per CTA; per-CTA argmax of  logit / T + Gumbel noise  per activation row = a draw
                       // from softmax(logits / T) (Gumbel-max, the construction the posterior sampler uses too)
+  // Fused row epilogues (epilogues.cuh): stream-K as kModePartials, but a split tile is FINISHED inside the GEMM -- the
+  // CTA that owns the tile's first k-blocks (always the last segment of its range) adds the partial accumulators the
+  // other CTAs of the tile left in `part`, in slot order, and runs the epilogue on the finished tile. Tiles that one
+  // CTA owns entirely never leave TMEM/registers. No fp32 partial plane, no consumer kernel.
+  kModeRows = 5,      // bf16 Linear output (+bias) [+ residual] and per-tile sums of squares (fc, o_proj, down_proj)
+  kModeSwiglu = 6,    // tile = 64 gate rows + 64 up rows of the same columns -> bf16 silu(gate) * up
+  kModeQkv = 7,       // tile = one head: q/k RMSNorm + RoPE, K/V written at their cache position, q to the query buffer
 };
 constexpr int kTopK = 4;
 
@@ -55,14 +63,18 @@ struct GemmArgs {
   int* cand_idx;              // [ranges][cand_ld]
   __nv_bfloat16* logits;      // optional [m_valid][logits_ld] (bf16-rounded), may be null
   long long logits_ld;
-  // Pre-wait L2 prefetch: while this (PDL-launched) kernel waits for its predecessor, the four idle
-  // epilogue warps prefetch the CTA's next `pf_units` weight units (beyond the kStages tiles already
-  // in flight to smem) into L2 with plain prefetch.global.L2, one 128-byte weight-row segment per thread.
-  const void* w_ptr;   // weight matrix base (row-major bf16, pitch w_ld elements)
-  long long w_ld;
-  int w_rows;          // rows of the weight matrix (prefetch bound)
-  int pf_units;        // 0 = off
-  int late_w;          // experiment: issue the first weight tiles only after griddepcontrol.wait
+  // Fused modes: exchange of partial accumulators between the CTAs of a split tile
+  float* part;            // [groups * ranges][MB/4][128][4] fp32: the partial of CTA (group, range)'s FIRST segment
+  unsigned int* flags;    // [groups][n_tiles] arrivals of a tile's non-finishing CTAs (reset by the finisher)
+  RowsEpi rows;           // kModeRows
+  SwigluEpi sw;           // kModeSwiglu
+  QkvPostArgs qkv;        // kModeQkv
+  // kModeArgmax / kModeSample inside the engine: the LAST CTA to finish also reduces the per-CTA candidates to the
+  // drafted tokens (block_ids[:, 1:bs], model/dflash.py:247) -- no separate reduce launch. Off when tok_counter is null.
+  unsigned int* tok_counter;
+  long long* tok_block_ids;     // [R][tok_bs]
+  long long* tok_draft_tokens;  // [R*tok_SL]
+  int tok_SL, tok_bs, tok_rows;
   // optional per-CTA phase timestamps (globaltimer ns), [ranges * groups][8]: 0 kernel entry, 1 prologue done,
   // 2 producer past griddepcontrol.wait, 3 first stage landed (MMA warp), 4 last MMA issued, 5 last accumulator
   // complete (epilogue), 6 epilogue stores issued (scripts/gemm_trace.py)
@@ -96,37 +108,48 @@ __host__ __device__ inline int tile_num_slots(int t, int k_blocks, long long T, 
 }
 
 // smem budget of the TMA pipeline per mode (measured on B200, profiles/r1_summary.md):
-//  * partials GEMMs (33-200 MB each, 21 per step, chained by PDL): ~110 KB, so that the successor's CTA
-//    can be co-resident and pre-load its first stages while the predecessor drains (755 us/step vs 768 us
-//    with 215 KB);
+//  * chained projection GEMMs (33-200 MB each, 21 per step, chained by PDL): ~100 KB + the 8 KB epilogue tile, so that
+//    the successor's CTA can be co-resident and pre-load its first stages while the predecessor drains (755 us/step
+//    vs 768 us with 215 KB);
 //  * lm_head argmax GEMM (1.24 GB in one launch): everything, 11 stages -> 0.967 of the measured copy
 //    bandwidth instead of 0.93.
 #ifndef DFLASH_GEMM_SMEM_KB_PARTIALS
 #define DFLASH_GEMM_SMEM_KB_PARTIALS 110
 #endif
+#ifndef DFLASH_GEMM_SMEM_KB_FUSED
+#define DFLASH_GEMM_SMEM_KB_FUSED 100
+#endif
 #ifndef DFLASH_GEMM_SMEM_KB_ARGMAX
 #define DFLASH_GEMM_SMEM_KB_ARGMAX 215
 #endif
-#ifndef DFLASH_GEMM_SMEM_KB_WIDE   // partials GEMMs with >= 64 activation rows per group (+ 16 KB store staging)
+#ifndef DFLASH_GEMM_SMEM_KB_WIDE   // projection GEMMs with >= 64 activation rows per group (+ 16 KB epilogue tile)
 #define DFLASH_GEMM_SMEM_KB_WIDE 196
 #endif
 
+constexpr bool mode_is_fused(int mode) { return mode >= kModeRows; }
+constexpr bool mode_is_whole_tile(int mode) { return mode >= kModeArgmax && mode <= kModeSample; }
+
 template <int MB, int MODE = 0>
 struct GemmCfg {
+  static constexpr bool kFused = mode_is_fused(MODE);
+  static constexpr bool kWhole = mode_is_whole_tile(MODE);
   static constexpr int kWBytes = kTileN * kTileK * 2;   // 16 KB
   static constexpr int kXBytes = MB * kTileK * 2;
   static constexpr int kStageBytes = kWBytes + kXBytes;
   // wide activation tiles (batched engines) need the whole SM to keep >= 4 stages in flight
   static constexpr int kBudget =
-      (MODE != 0 ? DFLASH_GEMM_SMEM_KB_ARGMAX : (MB >= 64 ? DFLASH_GEMM_SMEM_KB_WIDE : DFLASH_GEMM_SMEM_KB_PARTIALS)) * 1024;
+      (kWhole ? DFLASH_GEMM_SMEM_KB_ARGMAX
+              : (MB >= 64 ? DFLASH_GEMM_SMEM_KB_WIDE : (kFused ? DFLASH_GEMM_SMEM_KB_FUSED : DFLASH_GEMM_SMEM_KB_PARTIALS))) * 1024;
   static constexpr int kStages = kBudget / kStageBytes < 3 ? 3 : kBudget / kStageBytes;
   static constexpr int kTmemCols = (2 * MB < 32) ? 32 : 2 * MB;
   // epilogue warps: warp w drains TMEM lane quarter w % 4. The 256-wide argmax epilogue keeps one packed running
   // best per activation row in registers, so it splits the columns over two warp sets (128 registers each).
-  static constexpr int kEpiWarps = (MODE != 0 && MB >= 128) ? 8 : 4;
+  static constexpr int kEpiWarps = (kWhole && MB >= 128) ? 8 : 4;
   static constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
   static constexpr int kColsPerThread = MB / (kEpiWarps / 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // fused modes: activation rows per shared-memory epilogue tile (tile[m][128] fp32)
+  static constexpr int kEpiRows = MB < 64 ? 16 : 32;
 };
 
 // Order-preserving 16-bit key of a bf16 value (larger value <=> larger key; -0 == +0; key 0 is below every value).
@@ -146,10 +169,19 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int MB, int MODE>
 __global__ void __launch_bounds__(GemmCfg<MB, MODE>::kThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                   const GemmArgs a) {
+                   const __grid_constant__ GemmArgs a) {
   using Cfg = GemmCfg<MB, MODE>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -169,16 +201,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   unsigned long long* tr = a.trace ? a.trace + (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = global_ns();
   DFL_TRACE(0);
-#ifdef DFLASH_GEMM_TOP_TRIGGER
-  pdl_trigger();  // (experiment) release the dependent before this kernel's own prologue
-#endif
   const long long T = static_cast<long long>(a.n_tiles) * a.k_blocks;
   const long long G = gridDim.y;           // weight ranges
   const int cta = blockIdx.y;              // this CTA's weight range
   const int m0 = blockIdx.x * MB;          // first activation row of this CTA's column group
   const int mv = a.m_valid - m0;           // valid rows in the group (may exceed MB)
   long long u0, u1;
-  constexpr bool kArgmax = MODE != kModePartials;
+  constexpr bool kArgmax = Cfg::kWhole;
+  constexpr bool kFused = Cfg::kFused;
   if (kArgmax) {  // whole tiles only
     u0 = (cta * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
     u1 = ((cta + 1) * static_cast<long long>(a.n_tiles) / G) * a.k_blocks;
@@ -214,9 +244,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   if (tr && threadIdx.x == 0) tr[1] = global_ns();
   // Let the next kernel in the stream start its own prologue / weight prefetch right away.
-#if !defined(DFLASH_GEMM_LATE_TRIGGER) && !defined(DFLASH_GEMM_TOP_TRIGGER)
   pdl_trigger();
-#endif
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -226,27 +254,25 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const uint64_t polX = l2_policy_evict_last();
       const long long n_units = u1 - u0;
       const int npre = n_units < S ? static_cast<int>(n_units) : S;
-      // weight tiles first: they do not depend on the predecessor kernel
-      if (a.late_w == 1) pdl_wait();
-#ifdef DFLASH_PREWAIT_STAGES   // (experiment) only this many weight tiles before griddepcontrol.wait, the rest after
-      const int n_early = npre < DFLASH_PREWAIT_STAGES ? npre : DFLASH_PREWAIT_STAGES;
-#else
-      const int n_early = npre;
-#endif
-      auto issue_w = [&](int i) {
-        const long long u = u0 + i;
-        const int tile = static_cast<int>(u / a.k_blocks);
-        const int kb = static_cast<int>(u % a.k_blocks);
-        mbar_expect_tx(&full[i], Cfg::kStageBytes);
-        tma_load_2d(sW + i * Cfg::kWBytes, &tmW, &full[i], kb * kTileK, a.w_row0 + tile * kTileN,
-                    polW);
+      // the weight tile of unit (tile, kb) into stage s. kModeSwiglu: 64 gate rows + 64 up rows of the same columns
+      // (two 64-row boxes of the [gate; up] stack; the 128-byte swizzle is a function of the shared-memory address,
+      // so the two halves form the same 128-row operand tile one box would)
+      auto load_w = [&](int s, int tile, int kb) {
+        if (MODE == kModeSwiglu) {
+          tma_load_2d(sW + s * Cfg::kWBytes, &tmW, &full[s], kb * kTileK, a.w_row0 + tile * (kTileN / 2), polW);
+          tma_load_2d(sW + s * Cfg::kWBytes + Cfg::kWBytes / 2, &tmW, &full[s], kb * kTileK,
+                      a.w_row0 + a.sw.I + tile * (kTileN / 2), polW);
+        } else {
+          tma_load_2d(sW + s * Cfg::kWBytes, &tmW, &full[s], kb * kTileK, a.w_row0 + tile * kTileN, polW);
+        }
       };
-      for (int i = 0; i < n_early; ++i) issue_w(i);
+      // weight tiles first: they do not depend on the predecessor kernel
+      for (int i = 0; i < npre; ++i) {
+        const long long u = u0 + i;
+        mbar_expect_tx(&full[i], Cfg::kStageBytes);
+        load_w(i, static_cast<int>(u / a.k_blocks), static_cast<int>(u % a.k_blocks));
+      }
       pdl_wait();
-      for (int i = n_early; i < npre; ++i) issue_w(i);
-#ifdef DFLASH_GEMM_LATE_TRIGGER
-      pdl_trigger();  // (experiment) the dependent small kernel becomes resident only once this GEMM really starts
-#endif
       if (tr) tr[2] = global_ns();
       DFL_TRACE_ANY(1);
       for (int i = 0; i < npre; ++i) {
@@ -259,15 +285,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int tile = static_cast<int>(u / a.k_blocks);
         const int kb = static_cast<int>(u % a.k_blocks);
         mbar_wait(&empty[stage], phase ^ 1u);
-        if (a.late_w == 2) {  // timing experiment only (wrong results): no activation tile after the first S units
-          mbar_expect_tx(&full[stage], Cfg::kWBytes);
-          tma_load_2d(sW + stage * Cfg::kWBytes, &tmW, &full[stage], kb * kTileK, a.w_row0 + tile * kTileN, polW);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-          continue;
-        }
         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-        tma_load_2d(sW + stage * Cfg::kWBytes, &tmW, &full[stage], kb * kTileK,
-                    a.w_row0 + tile * kTileN, polW);
+        load_w(stage, tile, kb);
         tma_load_2d(sX + stage * Cfg::kXBytes, &tmX, &full[stage], kb * kTileK, a.x_row0 + m0, polX);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -313,21 +332,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..kEpiWarps-1)
-    if (a.pf_units > 0) {
-      // pre-wait L2 prefetch of units [u0 + S, u0 + S + pf_units): thread t takes weight row t of each
-      // unit's 128 x 128 B box, so one pass of the 128 threads covers one 16 KB unit
-      const char* wb = static_cast<const char*>(a.w_ptr);
-      long long u = u0 + S;
-      const long long ue = u + a.pf_units < u1 ? u + a.pf_units : u1;
-      for (; u < ue; ++u) {
-        const int tile = static_cast<int>(u / a.k_blocks);
-        const int kb = static_cast<int>(u % a.k_blocks);
-        const int wrow = a.w_row0 + tile * kTileN + static_cast<int>(threadIdx.x);
-        if (threadIdx.x < kTileN && wrow < a.w_rows)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;\n" ::"l"(
-              wb + (static_cast<long long>(wrow) * a.w_ld + kb * kTileK) * 2));
-      }
-    }
     pdl_wait();
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -338,6 +342,101 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int row_in_tile = quarter * 32 + lane;
     const int epi_tid = static_cast<int>(threadIdx.x);  // epilogue warps are warps [0, kEpiWarps)
 
+    if constexpr (kFused) {
+      // ---------------------------------------------------------------- fused row epilogues
+      constexpr int kCh = Cfg::kEpiRows;
+      static_assert(MB % kCh == 0 && kCh % 16 == 0, "epilogue tile");
+      __shared__ __align__(16) float s_t[kCh * kTileN];  // tile[m][n] of the current chunk of activation rows
+      const long long part_stride = static_cast<long long>(kTileN) * MB;  // floats per CTA partial
+      float* my_part = a.part + (static_cast<long long>(blockIdx.x) * G + cta) * part_stride;
+      long long u = u0;
+      while (u < u1) {
+        const int tile = static_cast<int>(u / a.k_blocks);
+        const long long seg_end =
+            static_cast<long long>(tile + 1) * a.k_blocks < u1 ? static_cast<long long>(tile + 1) * a.k_blocks : u1;
+        const int first = tile_first_cta(tile, a.k_blocks, T, G);
+        const int nslots = tile_num_slots(tile, a.k_blocks, T, G);
+        const int slot = cta - first;
+        const bool writer = slot > 0;                  // the tile began in an earlier CTA: leave a partial for it
+        const bool finisher = slot == 0 && nslots > 1; // the tile continues in later CTAs: they left partials for us
+        unsigned int* flag = a.flags + static_cast<long long>(blockIdx.x) * a.n_tiles + tile;
+        if (finisher) {
+          // The other CTAs of this tile computed their share at the START of their ranges (or are whole-range
+          // middle slots that end when we do): in practice the partials are already there.
+          if (epi_tid == 0) {
+            while (ld_acquire_u32(flag) < static_cast<unsigned int>(nslots - 1)) __nanosleep(40);
+            *flag = 0u;  // next use is a later launch of this plan
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        if (tr && seg_end >= u1 && threadIdx.x == 0) tr[5] = global_ns();
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < MB / kCh; ++c) {
+          float v[kCh];
+#pragma unroll
+          for (int q = 0; q < kCh / 16; ++q)
+            tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + c * kCh + q * 16), v + q * 16);
+          tmem_ld_wait();
+          if (c == MB / kCh - 1) {
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);  // the accumulator stage goes back to the MMA warp
+          }
+          // partial layout: [m / 4][n][4] -> a warp's float4 accesses are 512 contiguous bytes
+          const long long pofs = (static_cast<long long>(c * (kCh / 4)) * kTileN + row_in_tile) * 4;
+          if (writer) {
+#pragma unroll
+            for (int i = 0; i < kCh / 4; ++i)
+              *reinterpret_cast<float4*>(my_part + pofs + static_cast<long long>(i) * kTileN * 4) =
+                  make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            continue;
+          }
+          if (finisher) {
+            for (int s = 1; s < nslots; ++s) {  // slot order: the summation order is fixed
+              const float* op = my_part + static_cast<long long>(s) * part_stride + pofs;
+              float4 p[kCh / 4];
+#pragma unroll
+              for (int i = 0; i < kCh / 4; ++i)
+                p[i] = __ldcg(reinterpret_cast<const float4*>(op + static_cast<long long>(i) * kTileN * 4));
+#pragma unroll
+              for (int i = 0; i < kCh / 4; ++i) {
+                v[4 * i] += p[i].x; v[4 * i + 1] += p[i].y; v[4 * i + 2] += p[i].z; v[4 * i + 3] += p[i].w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kCh; ++j) s_t[j * kTileN + row_in_tile] = v[j];
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          for (int j = quarter; j < kCh; j += 4) {
+            const int m = c * kCh + j;
+            if (m >= mv) break;
+            const int row = a.x_row0 + m0 + m;  // row of the activation matrix == row of the output
+            if constexpr (MODE == kModeRows) {
+              rows_epi_apply(a.rows, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]), tile, row, lane);
+            } else if constexpr (MODE == kModeSwiglu) {
+              swiglu_epi_apply(a.sw, &s_t[j * kTileN], tile, row, lane);
+            } else {
+              const QkvItem it = qkv_post_prepare(a.qkv, row, tile, lane);
+              qkv_post_apply(a.qkv, it, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]), tile, lane);
+            }
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
+        if (writer) {
+          // publish: every thread's stores are ordered before the barrier, the release covers them (cumulativity)
+          __threadfence();
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          if (epi_tid == 0) red_release_add_u32(flag, 1u);
+        }
+        u = seg_end;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (tr && threadIdx.x == 0) tr[6] = global_ns();
+      DFL_TRACE(2);
+    } else {
+    // ------------------------------------------------------------------ partial planes / whole-tile reductions
     // kModeArgmax: one running best per activation row in a register, packed as
     //   (order key of the bf16-rounded logit) << 16 | (0xFFFF - tile)
     // so that keeping the best is ONE integer max per logit, and a tie keeps the lower tile = the lower vocab
@@ -536,6 +635,48 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           a.cand_idx[o + q] = bk[q] ? static_cast<int>(0xFFFFu - (bk[q] & 0xFFFFu)) * kTileN + brow[q] : 0x7fffffff;
         }
       }
+    }
+    if constexpr (MODE == kModeArgmax || MODE == kModeArgmaxDump || MODE == kModeSample) {
+      // Drafted tokens: the last CTA of the grid to get here reduces everybody's candidates (one warp per block row;
+      // ties -> lowest vocab index = torch.argmax on the bf16 logits, model/utils.py:27-29) and writes slots 1..bs-1
+      // of block_ids (slot 0 is the committed token, model/dflash.py:247).
+      if (a.tok_counter != nullptr) {
+        __shared__ unsigned int s_last;
+        __threadfence();
+        asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kEpiWarps * 32) : "memory");
+        if (epi_tid == 0) {
+          const unsigned int total = gridDim.x * gridDim.y;
+          const unsigned int prev = atomicAdd(a.tok_counter, 1u);
+          s_last = (prev == total - 1u) ? 1u : 0u;
+          if (prev == total - 1u) *a.tok_counter = 0u;
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::kEpiWarps * 32) : "memory");
+        if (s_last) {
+          __threadfence();
+          const int n_cta = static_cast<int>(gridDim.y);
+          for (int row = warp; row < a.tok_rows; row += Cfg::kEpiWarps) {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int g = lane; g < n_cta; g += 32) {
+              const float v = __ldcg(a.cand_val + static_cast<long long>(g) * a.cand_ld + row);
+              const int i = __ldcg(a.cand_idx + static_cast<long long>(g) * a.cand_ld + row);
+              if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+              a.tok_draft_tokens[row] = bi;
+              const int r = row / a.tok_SL, i = row % a.tok_SL;
+              if (i >= 1 && i < a.tok_bs) a.tok_block_ids[static_cast<long long>(r) * a.tok_bs + i] = bi;
+            }
+          }
+        }
+      }
+    }
     }
   }
 

@@ -24,9 +24,7 @@ struct PosteriorArgs {
 
 // key_i = logit_i (greedy) or logit_i / T - log(e_i), e_i ~ Exp(1): argmax_i key_i is a draw from
 // softmax(logits / T) -- the same exponential race torch.multinomial runs (argmax(p / q)).
-__global__ void __launch_bounds__(256) posterior_kernel(const PosteriorArgs a) {
-  DFL_VERIFY_SYNC();
-  const int row = blockIdx.y, split = blockIdx.x;
+__device__ __forceinline__ void posterior_body(const PosteriorArgs& a, int row, int split) {
   int seg = (a.V + a.nsplit - 1) / a.nsplit;
   seg = (seg + 7) & ~7;
   const int c0 = split * seg;
@@ -100,6 +98,11 @@ __global__ void __launch_bounds__(256) posterior_kernel(const PosteriorArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(256) posterior_kernel(const PosteriorArgs a) {
+  DFL_VERIFY_SYNC();
+  posterior_body(a, blockIdx.y, blockIdx.x);
+}
+
 // tokens[row] = best candidate over the splits of posterior_kernel (standalone sampler)
 __global__ void __launch_bounds__(32) sample_reduce_kernel(const float* __restrict__ cand_val,
                                                            const int* __restrict__ cand_idx, int nsplit,
@@ -150,10 +153,7 @@ struct AcceptArgs {
 };
 
 // One warp per request.
-__global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
-  DFL_VERIFY_SYNC();
-  const int r = blockIdx.x, lane = threadIdx.x;
-  if (r == 0 && lane == 0 && a.rng_step != nullptr) *a.rng_step += 1ull;
+__device__ __forceinline__ void accept_request(const AcceptArgs& a, int r, int lane) {
   // every scalar of the request's state is requested up front: one L2 round trip instead of one per use
   const int done = a.done[r];
   const int st = a.start[r];
@@ -243,6 +243,12 @@ __global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
   for (int i = 1; i < bs; ++i) blk[i] = a.mask_token;
 }
 
+__global__ void __launch_bounds__(32) accept_kernel(const AcceptArgs a) {
+  DFL_VERIFY_SYNC();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.rng_step != nullptr) *a.rng_step += 1ull;
+  accept_request(a, blockIdx.x, threadIdx.x);
+}
+
 // Next-cycle context features: the first ctx_len[r] rows of each selected target hidden state,
 // concatenated on the feature dim (extract_context_feature + [:, :tau] slice, dflash.py:263).
 struct GatherArgs {
@@ -278,6 +284,64 @@ __global__ void __launch_bounds__(256) ctx_gather_kernel(const GatherArgs a) {
       a.src[sel] + (static_cast<long long>(rr) * a.src_rows + a.src_row0 + j) * a.H);
   uint4* d = reinterpret_cast<uint4*>(a.ctx_feat + drow * a.n_sel * a.H + static_cast<long long>(sel) * a.H);
   for (int i = threadIdx.x; i < a.H / 8; i += 256) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole verify step as ONE kernel (model/dflash.py:257-268): grid = (vocab splits, R * bs block rows).
+//   every CTA   copies its share of the next cycle's context features -- ALL bs rows of the selected hidden states
+//               go to ctx_feat; the rows past the accepted length are dead (ctx_len masks them), so the copy does not
+//               depend on the acceptance -- and reduces its vocab slice of the posterior (argmax / exponential race);
+//   last CTA of a request (arrival counter)  runs acceptance, commit, bonus token, both cache-length rollbacks,
+//               stop check and the next block for that request;
+//   last CTA of the grid  bumps the Philox step.
+struct VerifyFusedArgs {
+  PosteriorArgs post;
+  AcceptArgs acc;
+  GatherArgs gather;
+  unsigned int* counters;  // [R + 1] arrivals per request, then of the whole grid (self-resetting)
+};
+
+__global__ void __launch_bounds__(256) verify_fused_kernel(const VerifyFusedArgs v) {
+  DFL_VERIFY_SYNC();
+  const int row = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+  const int bs = v.acc.bs;
+  const int r = row / bs, i = row % bs;
+  {
+    const GatherArgs& g = v.gather;
+    const int per_sel = g.H / 8;                 // uint4 per (row, selected layer)
+    const int total = g.n_sel * per_sel;
+    const int share = (total + nsplit - 1) / nsplit;
+    const int e0 = split * share, e1 = min(total, e0 + share);
+    uint4* d = reinterpret_cast<uint4*>(g.ctx_feat + (static_cast<long long>(r) * g.SL + i) * g.n_sel * g.H);
+    for (int e = e0 + threadIdx.x; e < e1; e += 256) {
+      const int sel = e / per_sel, c = e % per_sel;
+      d[e] = reinterpret_cast<const uint4*>(g.src[sel] + static_cast<long long>(row) * g.H)[c];
+    }
+  }
+  posterior_body(v.post, row, split);
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int n_req = static_cast<unsigned int>(nsplit) * bs;
+    const unsigned int prev = atomicAdd(&v.counters[r], 1u);
+    s_last = (prev == n_req - 1u) ? 1u : 0u;
+    if (prev == n_req - 1u) v.counters[r] = 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < 32) accept_request(v.acc, r, threadIdx.x);
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int n_all = gridDim.x * gridDim.y;
+    const unsigned int prev = atomicAdd(&v.counters[v.acc.R], 1u);
+    if (prev == n_all - 1u) {
+      v.counters[v.acc.R] = 0u;
+      if (v.acc.rng_step != nullptr) *v.acc.rng_step += 1ull;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -23,12 +23,12 @@ class CConfig(Structure):
         ("max_requests", c_int), ("max_seq", c_int), ("out_len", c_int), ("hist_len", c_int),
         ("rms_eps", c_float), ("rope_scale", c_float), ("mask_token_id", c_longlong), ("attn_splits", c_int),
         ("post_splits", c_int), ("gemm_grid", c_int), ("use_pdl", c_int), ("keep_draft_logits", c_int),
-        ("prefetch_mb", c_int), ("use_mega", c_int), ("max_candidates", c_int),
+        ("max_candidates", c_int),
     ]
 
 
 class CLayerWeights(Structure):
-    _fields_ = [(n, c_void_p) for n in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm")]
+    _fields_ = [(n, c_void_p) for n in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm", "bqkv", "bo")]
 
 
 class CWeights(Structure):
@@ -40,15 +40,15 @@ class CWeights(Structure):
 BUFFERS = [
     ("x", torch.bfloat16), ("a_in", torch.bfloat16), ("ctx_feat", torch.bfloat16), ("q", torch.bfloat16),
     ("attn_out", torch.bfloat16), ("a2", torch.bfloat16), ("hmid", torch.bfloat16), ("hn", torch.bfloat16),
-    ("kv", torch.bfloat16), ("ws", torch.float32), ("attn_po", torch.float32), ("attn_ml", torch.float32),
+    ("kv", torch.bfloat16), ("y_ctx", torch.bfloat16), ("tile_ss", torch.float32), ("part", torch.float32),
+    ("flags", torch.int32), ("counters", torch.int32), ("attn_po", torch.float32), ("attn_ml", torch.float32),
     ("cand_val", torch.float32), ("cand_idx", torch.int32), ("post_val", torch.float32), ("post_idx", torch.int32),
     ("draft_tokens", torch.int64), ("block_ids", torch.int64), ("posterior", torch.int64),
     ("output_ids", torch.int64), ("start", torch.int32), ("ctx_len", torch.int32), ("done", torch.int32),
     ("n_cycles", torch.int32), ("blk_len", torch.int32), ("max_len", torch.int32), ("acc_hist", torch.int32),
-    ("rng_step", torch.int64), ("draft_logits", torch.bfloat16), ("mega_gemms", torch.uint8),
-    ("mega_phases", torch.uint8), ("mega_sync", torch.int64), ("pf_feat", torch.bfloat16), ("pf_a", torch.bfloat16),
-    ("topk_idx", torch.int32), ("topk_val", torch.float32), ("cand_ids", torch.int64), ("cand_scores", torch.float32),
-    ("chosen", torch.int32),
+    ("rng_step", torch.int64), ("draft_logits", torch.bfloat16), ("pf_feat", torch.bfloat16), ("pf_a", torch.bfloat16),
+    ("pf_y", torch.bfloat16), ("topk_idx", torch.int32), ("topk_val", torch.float32), ("cand_ids", torch.int64),
+    ("cand_scores", torch.float32), ("chosen", torch.int32),
 ]
 
 
@@ -92,8 +92,8 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else c_void_p(t.data_ptr())
 
 
-def _stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class PackedDraftWeights:
@@ -106,8 +106,6 @@ class PackedDraftWeights:
         self.layers = []
         for layer in draft.layers:
             at, mlp = layer.self_attn, layer.mlp
-            if getattr(at.q_proj, "bias", None) is not None:
-                raise _lib.DFlashNativeError("attention_bias=True drafts are not supported by the CUDA path")
             wqkv = torch.cat([at.q_proj.weight, at.k_proj.weight, at.v_proj.weight], 0).to(device=device, dtype=bf).contiguous()
             wgu = torch.cat([mlp.gate_proj.weight, mlp.up_proj.weight], 0).to(device=device, dtype=bf).contiguous()
             ent = dict(
@@ -118,7 +116,12 @@ class PackedDraftWeights:
                 ln2=layer.post_attention_layernorm.weight.detach().to(device=device, dtype=bf).contiguous(),
                 q_norm=at.q_norm.weight.detach().to(device=device, dtype=bf).contiguous(),
                 k_norm=at.k_norm.weight.detach().to(device=device, dtype=bf).contiguous(),
+                bqkv=None, bo=None,
             )
+            if getattr(at.q_proj, "bias", None) is not None:  # config.attention_bias (model/dflash.py:41-50)
+                ent["bqkv"] = torch.cat([at.q_proj.bias, at.k_proj.bias, at.v_proj.bias], 0).detach().to(
+                    device=device, dtype=bf).contiguous()
+                ent["bo"] = at.o_proj.bias.detach().to(device=device, dtype=bf).contiguous()
             if alias and at.q_proj.weight.dtype == bf and at.q_proj.weight.device == wqkv.device:
                 nq, nk = at.q_proj.weight.shape[0], at.k_proj.weight.shape[0]
                 at.q_proj.weight.data = wqkv[:nq]
@@ -159,12 +162,12 @@ class PackedDraftWeights:
 
 
 class DraftEngine:
-    """One GPU's draft+verify engine for `max_requests` request streams (a power of two, 1..64)."""
+    """One GPU's draft+verify engine for `max_requests` request streams (1..64)."""
 
     def __init__(self, draft, embed_weight: torch.Tensor, lm_head_weight: torch.Tensor, *, max_seq: int,
                  out_len: int, max_requests: int = 1, block_size: Optional[int] = None, use_pdl: bool = True,
-                 keep_draft_logits: bool = False, gemm_grid: int = 0, attn_splits: int = 0, hist_len: int = 4096,
-                 prefetch_mb: int = 0, use_mega: Optional[bool] = None, max_candidates: int = 0, device=None):
+                 keep_draft_logits: bool = False, gemm_grid: int = 0, attn_splits: int = 0,
+                 hist_len: Optional[int] = None, max_candidates: int = 0, device=None):
         self.lib = _lib.load()
         _declare(self.lib)
         if not torch.cuda.is_available():
@@ -186,6 +189,11 @@ class DraftEngine:
         self.lm_head = lm_head_weight.detach().contiguous()
         self.weights = PackedDraftWeights.for_draft(draft, self.device)
         head_dim = getattr(cfg, "head_dim", cfg.hidden_size // cfg.num_attention_heads)
+        if any(t != "full_attention" for t in (getattr(cfg, "layer_types", None) or [])):
+            raise _lib.DFlashNativeError("sliding-window draft layers are not supported by the CUDA path")
+        # one acceptance-length entry per cycle; a cycle commits at least one token, so out_len bounds the cycles
+        hist_len = int(out_len) if hist_len is None else int(hist_len)
+        self.hist_len = hist_len
         self.ccfg = CConfig(
             hidden=cfg.hidden_size, intermediate=cfg.intermediate_size, n_layers=cfg.num_hidden_layers,
             n_q_heads=cfg.num_attention_heads, n_kv_heads=cfg.num_key_value_heads, head_dim=head_dim,
@@ -193,10 +201,8 @@ class DraftEngine:
             max_seq=int(max_seq), out_len=int(out_len), hist_len=int(hist_len), rms_eps=float(cfg.rms_norm_eps),
             rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id,
             attn_splits=int(os.environ.get("DFLASH_ATTN_SPLITS", attn_splits)),
-            post_splits=0, gemm_grid=int(os.environ.get("DFLASH_GEMM_GRID", gemm_grid)), use_pdl=int(use_pdl), keep_draft_logits=int(keep_draft_logits),
-            prefetch_mb=int(os.environ.get("DFLASH_PREFETCH_MB", prefetch_mb)),
-            use_mega=int(os.environ.get("DFLASH_MEGA", "0")) if use_mega is None else int(use_mega),
-            max_candidates=int(max_candidates))
+            post_splits=0, gemm_grid=int(os.environ.get("DFLASH_GEMM_GRID", gemm_grid)), use_pdl=int(use_pdl),
+            keep_draft_logits=int(keep_draft_logits), max_candidates=int(max_candidates))
         self.max_candidates = int(max_candidates)
         self.max_seq, self.out_len = int(max_seq), int(out_len)
         with torch.cuda.device(self.device):
@@ -208,8 +214,8 @@ class DraftEngine:
             self._ws_view = self.workspace[off:off + nbytes]
             arr = (CLayerWeights * len(self.weights.layers))()
             for i, ent in enumerate(self.weights.layers):
-                for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm"):
-                    setattr(arr[i], k, ent[k].data_ptr())
+                for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm", "bqkv", "bo"):
+                    setattr(arr[i], k, None if ent[k] is None else ent[k].data_ptr())
             self._layer_arr = arr
             cw = CWeights(embed=self.embed.data_ptr(), lm_head=self.lm_head.data_ptr(), fc=self.weights.fc.data_ptr(),
                           hidden_norm=self.weights.hidden_norm.data_ptr(), final_norm=self.weights.final_norm.data_ptr(),
@@ -235,12 +241,10 @@ class DraftEngine:
         self.SL = 16 if bs <= 16 else 32
         self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
         # launches per draft step of the schedule actually enqueued (engine.cuh): fc GEMM, one row kernel (context
-        # finalize + block embedding + first layernorm), per layer {qkv GEMM, qkv_post, attn, combine, o GEMM, finalize,
-        # gate/up GEMM, swiglu, down GEMM, finalize}, lm_head GEMM, token reduce
-        mega = bool(self.ccfg.use_mega) and self.R * (16 if self.block_size <= 16 else 32) == 16
-        fused = os.environ.get("DFLASH_FUSED_ATTN", "0") not in ("", "0")
-        self.kernels_per_draft_step = 1 if mega else 2 + (8 if fused else 10) * cfg.num_hidden_layers + 2
-        self.kernels_per_verify_step = 3
+        # hidden_norm + block embedding + first layernorm), per layer {qkv GEMM, attention, merge, o GEMM, norm,
+        # gate/up GEMM, down GEMM, norm}, lm_head GEMM (argmax + drafted tokens); the verify step is one kernel
+        self.kernels_per_draft_step = 2 + 8 * cfg.num_hidden_layers + 1
+        self.kernels_per_verify_step = 1
         self._graph = None
 
     # ------------------------------------------------------------------------------------------
@@ -276,6 +280,15 @@ class DraftEngine:
         self.buf["n_cycles"][r] = 0
         self.buf["blk_len"][r] = self.block_size
         self.buf["max_len"][r] = P + max_new_tokens
+        if P + max_new_tokens > self.hist_len:
+            raise ValueError("hist_len too small: one acceptance-length entry per cycle is kept")
+        if self.R == 1:  # a fresh request restarts the Philox step: same seed -> same draws (engines are cached)
+            self.buf["rng_step"].zero_()
+
+    def _call(self, name: str, *args):
+        """Every library call runs with the engine's device current (the C side launches on the current device)."""
+        with torch.cuda.device(self.device):
+            _lib.check(getattr(self.lib, name)(*args), name)
 
     def prefill_context(self, r: int, hidden: Sequence[torch.Tensor], pos0: int = 0):
         """hidden[s]: [P, H] bf16 rows of the selected target layers; they become the context at cache positions
@@ -284,13 +297,11 @@ class DraftEngine:
         hs = [h.contiguous() for h in hidden]
         P = hs[0].shape[0]
         arr = (c_void_p * self.n_sel)(*[h.data_ptr() for h in hs])
-        _lib.check(self.lib.dflash_prefill_context_at(self.handle, r, arr, P, int(pos0), _stream()),
-                   "dflash_prefill_context_at")
+        self._call("dflash_prefill_context_at", self.handle, r, arr, P, int(pos0), _stream(self.device))
         self._keep = hs
 
     def draft_step(self, noise_embedding: Optional[torch.Tensor] = None, lm_head: bool = True):
-        _lib.check(self.lib.dflash_draft_step(self.handle, _p(noise_embedding), int(lm_head), _stream()),
-                   "dflash_draft_step")
+        self._call("dflash_draft_step", self.handle, _p(noise_embedding), int(lm_head), _stream(self.device))
 
     def verify_step(self, target_logits: Optional[torch.Tensor], hidden: Sequence[torch.Tensor], *,
                     temperature: float = 0.0, posterior_in: Optional[torch.Tensor] = None,
@@ -301,22 +312,20 @@ class DraftEngine:
         ld = 0 if target_logits is None else target_logits.stride(-2)
         n_stop = 0 if stop_ids is None else int(stop_ids.numel())
         fld = 0 if forced_k is None else int(forced_k.shape[-1])
-        _lib.check(self.lib.dflash_verify_step(self.handle, _p(target_logits), ld, _p(posterior_in), arr,
+        self._call("dflash_verify_step", self.handle, _p(target_logits), ld, _p(posterior_in), arr,
                                                float(temperature), _p(noise), int(seed) & (2**64 - 1), _p(stop_ids),
-                                               n_stop, _p(forced_k), fld, int(clamp_tail), _stream()),
-                   "dflash_verify_step")
+                                               n_stop, _p(forced_k), fld, int(clamp_tail), _stream(self.device))
 
     def draft_step_sampled(self, temperature: float, seed: int = 0):
         """Draft step whose tokens are drawn from softmax(draft_logits / temperature) in the lm_head epilogue
         (benchmark_dynamic_schedule.py:342); temperature 0 = the greedy step."""
-        _lib.check(self.lib.dflash_draft_step_sampled(self.handle, float(temperature), int(seed) & (2**64 - 1),
-                                                      _stream()), "dflash_draft_step_sampled")
+        self._call("dflash_draft_step_sampled", self.handle, float(temperature), int(seed) & (2**64 - 1),
+                                                      _stream(self.device))
 
     def draft_step_candidates(self, n_candidates: int, fixed_prefix_len: int):
         """Draft step with the top-4 lm_head epilogue; fills cand_ids[:, :n_candidates] / cand_scores
         (fixed_prefix_rank candidates, benchmark_candidate_solutions.py:181-249)."""
-        _lib.check(self.lib.dflash_draft_step_candidates(self.handle, int(n_candidates), int(fixed_prefix_len), _stream()),
-                   "dflash_draft_step_candidates")
+        self._call("dflash_draft_step_candidates", self.handle, int(n_candidates), int(fixed_prefix_len), _stream(self.device))
 
     def verify_step_candidates(self, n_candidates: int, target_logits: torch.Tensor, hidden: Sequence[torch.Tensor], *,
                                temperature: float = 0.0, noise: Optional[torch.Tensor] = None, seed: int = 0,
@@ -324,10 +333,10 @@ class DraftEngine:
         """target_logits [R*K*bs, V] bf16, hidden[s] [R*K*bs, H] bf16 from ONE target forward over all candidates."""
         arr = (c_void_p * self.n_sel)(*[h.data_ptr() for h in hidden])
         n_stop = 0 if stop_ids is None else int(stop_ids.numel())
-        _lib.check(self.lib.dflash_verify_step_candidates(self.handle, int(n_candidates), _p(target_logits),
+        self._call("dflash_verify_step_candidates", self.handle, int(n_candidates), _p(target_logits),
                                                           target_logits.stride(-2), arr, float(temperature), _p(noise),
                                                           int(seed) & (2**64 - 1), _p(stop_ids), n_stop, int(clamp_tail),
-                                                          _stream()), "dflash_verify_step_candidates")
+                                                          _stream(self.device))
 
     def sample(self, logits: torch.Tensor, temperature: float, seed: int = 0, noise: Optional[torch.Tensor] = None):
         """sample() of model/utils.py:27-34 on [rows, V] bf16 logits -> int64 [rows]."""
@@ -336,9 +345,8 @@ class DraftEngine:
         sv = torch.empty(rows * nsplit, dtype=torch.float32, device=logits.device)
         si = torch.empty(rows * nsplit, dtype=torch.int32, device=logits.device)
         out = torch.empty(rows, dtype=torch.int64, device=logits.device)
-        _lib.check(self.lib.dflash_sample(_p(logits), logits.stride(0), rows, V, float(temperature), _p(noise),
-                                          int(seed) & (2**64 - 1), _p(sv), _p(si), nsplit, _p(out), _stream()),
-                   "dflash_sample")
+        self._call("dflash_sample", _p(logits), logits.stride(0), rows, V, float(temperature), _p(noise),
+                                          int(seed) & (2**64 - 1), _p(sv), _p(si), nsplit, _p(out), _stream(self.device))
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -347,8 +355,13 @@ class DraftEngine:
         torch.cuda.synchronize(self.device)
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
+        # the warm-up step runs on live request state: keep the block (slots 1.. are mask tokens until the first real
+        # draft step fills them, model/dflash.py:233-235) and the draft tokens it would overwrite
+        keep_blk, keep_tok = self.buf["block_ids"].clone(), self.buf["draft_tokens"].clone()
         with torch.cuda.stream(s):
             self.draft_step()  # warm up (module load, func attributes) outside capture
+            self.buf["block_ids"].copy_(keep_blk)
+            self.buf["draft_tokens"].copy_(keep_tok)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DFLASH_ABI_VERSION 1
+#define DFLASH_ABI_VERSION 2
 
 #define DFLASH_OK 0
 #define DFLASH_ERR_ARG (-1)   /* bad argument / unsupported shape */
@@ -47,9 +47,9 @@ typedef struct dflash_config {
   int vocab;            /* rows of the target's lm_head / embed_tokens */
   int n_sel;            /* len(target_layer_ids) */
   int block_size;       /* slots per block (2..32); slot 0 is the last committed token */
-  int max_requests;     /* request streams resident in this engine: a power of two, 1..64. Up to 256 activation
-                           rows ride on one UMMA; wider batches run as column groups of 256 rows inside the same
-                           launch (the groups of one weight range share it through L2) */
+  int max_requests;     /* request streams resident in this engine, 1..64. Up to 256 activation rows ride on one
+                           UMMA; wider batches run as column groups of 256 rows inside the same launch (the groups
+                           of one weight range share it through L2) */
   int max_seq;          /* positions per request in the static draft KV cache */
   int out_len;          /* row length of output_ids (>= prompt + max_new_tokens + block_size) */
   int hist_len;         /* acceptance-length history entries per request */
@@ -61,15 +61,12 @@ typedef struct dflash_config {
   int gemm_grid;        /* CTAs per streaming GEMM (0 = SM count) */
   int use_pdl;          /* programmatic dependent launch between the step's kernels */
   int keep_draft_logits;/* also store the draft's bf16 logits (parity tests) */
-  int prefetch_mb;      /* MB of its own weights each GEMM prefetches into L2 while it waits for the
-                           kernel in front of it (<= 0 = off, the default: it did not pay on B200) */
-  int use_mega;         /* 1 = run the draft step as ONE persistent kernel (one CTA per SM, grid barriers between
-                           phases, weights streamed continuously) when the shape allows it (R = 1, bs <= 16) */
   int max_candidates;   /* candidate blocks per request for multi-candidate verify: 0/1 = off, up to 4 (needs
                            max_requests * row slots <= 32: the lm_head epilogue then keeps a top-4 per row) */
 } dflash_config_t;
 
-/* Packed bf16 weights of one draft layer. wqkv = [q_proj; k_proj; v_proj] rows, wgu = [gate; up]. */
+/* Packed bf16 weights of one draft layer. wqkv = [q_proj; k_proj; v_proj] rows, wgu = [gate; up].
+ * bqkv / bo: the projections' biases when config.attention_bias is set (model/dflash.py:41-50), else NULL. */
 typedef struct dflash_layer_weights {
   const void* wqkv;   /* [(Hq+2Hkv)*128, hidden] */
   const void* wo;     /* [hidden, Hq*128] */
@@ -79,6 +76,8 @@ typedef struct dflash_layer_weights {
   const void* ln2;    /* post_attention_layernorm.weight [hidden] */
   const void* q_norm; /* [128] */
   const void* k_norm; /* [128] */
+  const void* bqkv;   /* [(Hq+2Hkv)*128] = [q_proj.bias; k_proj.bias; v_proj.bias], or NULL */
+  const void* bo;     /* [hidden] o_proj.bias, or NULL */
 } dflash_layer_weights_t;
 
 typedef struct dflash_weights {
@@ -102,7 +101,12 @@ enum dflash_buffer_id {
   DFLASH_BUF_HMID,         /* bf16 [R*SL, intermediate] */
   DFLASH_BUF_HN,           /* bf16 [R*SL, hidden] final-normed hidden = DFlashDraftModel.forward output */
   DFLASH_BUF_KV,           /* bf16 [n_layers, 2, R, Hkv, max_seq, 128] static draft KV cache */
-  DFLASH_BUF_WS,           /* fp32 split-K partials */
+  DFLASH_BUF_Y_CTX,        /* bf16 [R*SL, hidden] fc output of the pending context rows (before hidden_norm) */
+  DFLASH_BUF_TILE_SS,      /* fp32 [3][64][rows]: per 128-column tile sums of squares of the fc rows, the residual
+                              rows and the prompt-pass rows (the RMSNorm pass adds them in tile order) */
+  DFLASH_BUF_PART,         /* fp32 partial accumulators exchanged between the CTAs of a split output tile */
+  DFLASH_BUF_FLAGS,        /* uint32 arrival counters per (GEMM, column group, tile); zero between launches */
+  DFLASH_BUF_COUNTERS,     /* uint32 [R + 2] arrival counters of the verify kernel and of the token reduce */
   DFLASH_BUF_ATTN_PO,
   DFLASH_BUF_ATTN_ML,
   DFLASH_BUF_CAND_VAL,
@@ -122,11 +126,9 @@ enum dflash_buffer_id {
   DFLASH_BUF_ACC_HIST,     /* int32 [R, hist_len] tau per cycle */
   DFLASH_BUF_RNG_STEP,     /* uint64 [1] */
   DFLASH_BUF_DRAFT_LOGITS, /* bf16 [R*SL, vocab] when keep_draft_logits */
-  DFLASH_BUF_MEGA_GEMMS,   /* persistent step kernel: GEMM table (TMA descriptors) */
-  DFLASH_BUF_MEGA_PHASES,  /* persistent step kernel: phase table */
-  DFLASH_BUF_MEGA_SYNC,    /* uint64: [0] steps done, [1] error code, [8..] per-phase arrival counters */
   DFLASH_BUF_PF_FEAT,      /* bf16 [256, n_sel*hidden] prompt pass: gathered target features */
   DFLASH_BUF_PF_A,         /* bf16 [256, hidden] prompt pass: hidden_norm(fc(features)) */
+  DFLASH_BUF_PF_Y,         /* bf16 [256, hidden] prompt pass: fc(features) */
   DFLASH_BUF_TOPK_IDX,     /* int32 [R*SL, 4] top-4 vocab indices of every block row's draft logits */
   DFLASH_BUF_TOPK_VAL,     /* fp32 [R*SL, 4] their bf16-rounded logits */
   DFLASH_BUF_CAND_IDS,     /* int64 [R, 4, block_size] candidate blocks (feeds the target's batched verify forward) */
@@ -236,6 +238,25 @@ int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K
                        int x_rows_total, int x_row0, int mb, int m_valid, float* ws, int ws_rows,
                        long long ws_ld, float* out, long long out_ld, int grid, int use_pdl,
                        void* stream);
+
+/* The projection GEMMs of the step with their fused row epilogues, as raw operators. A 128-column output tile that
+ * several CTAs share (stream-K) is finished INSIDE the launch: `part` (fp32, grid * 128 * mb elements) carries the
+ * partial accumulators, `flags` (uint32, ceil(m_valid/mb) * tiles, zero on entry and on exit) the arrivals.
+ *   dflash_gemm_rows:   out[m, n] = bf16(resid[m, n] + bf16(sum_k X[m,k] W[n,k] + bias[n]))  (resid / bias optional;
+ *                       out may alias resid) and tile_ss[n / 128][m] = sum of out[m, n]^2 over the tile's columns.
+ *                       Replaces fc (model/dflash.py:177), o_proj + residual (:101,140), down_proj + residual (:143-144).
+ *   dflash_gemm_swiglu: out[m, i] = bf16(bf16(silu(gate[m, i])) * up[m, i]) with Wgu = [gate_proj; up_proj] stacked
+ *                       (rows [0, I) and [I, 2I)); N = I must be a multiple of 64. Replaces Qwen3MLP's
+ *                       act_fn(gate_proj(x)) * up_proj(x).
+ *   dflash_rms_norm_rows: out[m] = weight * bf16(x[m] * rsqrt(sum_t tile_ss[t][m] / hidden + eps))  (Qwen3RMSNorm over
+ *                       rows a dflash_gemm_rows launch produced). */
+int dflash_gemm_rows(const void* W, int N, int K, const void* X, int x_rows_total, int mb, int m_valid,
+                     const void* bias, void* resid, void* out, long long ld, float* tile_ss, int ss_ld, float* part,
+                     unsigned int* flags, int grid, int use_pdl, void* stream);
+int dflash_gemm_swiglu(const void* Wgu, int I, int K, const void* X, int x_rows_total, int mb, int m_valid, void* out,
+                       long long ld, float* part, unsigned int* flags, int grid, int use_pdl, void* stream);
+int dflash_rms_norm_rows(const void* x, const float* tile_ss, int ss_ld, int hidden, const void* weight, void* out,
+                         int rows, float eps, void* stream);
 
 /* tokens_out[m] = argmax_n bf16(sum_k X[x_row0+m,k] * W[n,k]), ties -> lowest n; optionally also
  * writes the bf16 logits. Replaces target.lm_head(...) + sample(draft_logits)

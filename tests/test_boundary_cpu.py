@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
             "dflash_sample", "dflash_gemm_skinny", "dflash_gemm_argmax", "dflash_workspace_bytes"} <= set(names)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dflash_b200.h but not exported"
-    assert lib.dflash_abi_version() == 1
+    assert lib.dflash_abi_version() == 2
 
 
 def test_no_torch_types_in_abi():
@@ -86,8 +86,11 @@ def test_bad_config_is_rejected(lib):
     cfg.head_dim = 128
     n = lib.dflash_workspace_bytes(ctypes.byref(cfg))
     assert n > 5 * 2 * 8 * 4096 * 128 * 2  # at least the static draft KV cache
-    cfg.max_requests = 3
+    cfg.max_requests = 3  # any stream count up to 64 (buffers are padded to the UMMA width)
+    assert lib.dflash_workspace_bytes(ctypes.byref(cfg)) > n
+    cfg.max_requests = 65
     assert lib.dflash_workspace_bytes(ctypes.byref(cfg)) == 0
+    assert b"max_requests" in lib.dflash_last_error()
 
 
 def test_product_class_keeps_reference_contract():

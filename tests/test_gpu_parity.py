@@ -77,6 +77,90 @@ def test_gemm_skinny_column_groups(N, K, mb, rows):
     assert (out - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
 
 
+def _fused_scratch(dev, N_tiles, mb, rows, grid=148):
+    groups = max(1, (rows + mb - 1) // mb)
+    part = torch.zeros(grid * 128 * mb, dtype=torch.float32, device=dev)
+    flags = torch.zeros(groups * N_tiles, dtype=torch.int32, device=dev)
+    return groups, part, flags
+
+
+@pytest.mark.parametrize("N,K,mb,rows,grid", [
+    (4096, 4096, 16, 16, 148), (4096, 12288, 16, 16, 148), (4096, 20480, 16, 11, 148), (2560, 4096, 16, 16, 148),
+    (4096, 4096, 16, 16, 37), (256, 128, 16, 16, 148), (4096, 4096, 32, 32, 148), (2048, 2048, 64, 64, 148),
+    (4096, 4096, 128, 100, 148), (4096, 12288, 256, 256, 148), (4096, 4096, 256, 1024, 148), (2048, 6144, 256, 520, 148)])
+@pytest.mark.parametrize("with_resid", [False, True])
+def test_gemm_rows_fused_epilogue(N, K, mb, rows, grid, with_resid):
+    """kModeRows: split tiles are finished inside the GEMM; out = bf16(resid + bf16(X W^T + bias)), per-tile sums of
+    squares of the bf16 result; then the RMSNorm pass over them (dflash.py:101,140,143-144,177 + Qwen3RMSNorm).
+    Run twice on the same scratch: the arrival counters must be back at zero after a launch."""
+    dev = _cuda()
+    from dflash_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(N + K + rows)
+    groups, part, flags = _fused_scratch(dev, N // 128, mb, rows, grid)
+    W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+    X = torch.randn(groups * mb, K, device=dev).to(torch.bfloat16)
+    bias = (torch.randn(N, device=dev) * 0.5).to(torch.bfloat16) if with_resid else None
+    resid0 = torch.randn(rows, N, device=dev).to(torch.bfloat16) if with_resid else None
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lin = (X[:rows].float() @ W.float().t())
+    if bias is not None:
+        lin = lin + bias.float()
+    lin_bf = lin.to(torch.bfloat16)
+    exp = (resid0.float() + lin_bf.float()).to(torch.bfloat16) if with_resid else lin_bf
+    for rep in range(2):
+        out = resid0.clone() if with_resid else torch.zeros(rows, N, dtype=torch.bfloat16, device=dev)
+        ss = torch.zeros(N // 128, rows, dtype=torch.float32, device=dev)
+        _lib.check(lib.dflash_gemm_rows(_ptr(W), N, K, _ptr(X), groups * mb, mb, rows,
+                                        None if bias is None else _ptr(bias), _ptr(out) if with_resid else None,
+                                        _ptr(out), N, _ptr(ss), rows, _ptr(part), _ptr(flags), grid, 0, st))
+        torch.cuda.synchronize()
+        assert int(flags.abs().sum()) == 0, "arrival counters not reset"
+        # bf16 rounding of an fp32 sum that differs in the last bits: allow one bf16 ulp on a tiny fraction
+        diff = (out.float() - exp.float()).abs()
+        ulp = exp.float().abs().clamp_min(1e-3) * 2 ** -7
+        assert (diff <= ulp).all(), (rep, diff.max().item())
+        assert (diff > 0).float().mean().item() < 0.02
+        ss_ref = out.float().pow(2).view(rows, N // 128, 128).sum(-1).t()
+        assert torch.allclose(ss, ss_ref, rtol=1e-4, atol=1e-5)
+        w = (torch.rand(N, device=dev) + 0.5).to(torch.bfloat16)
+        y = torch.zeros(rows, N, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.dflash_rms_norm_rows(_ptr(out), _ptr(ss), rows, N, _ptr(w), _ptr(y), rows, 1e-6, st))
+        torch.cuda.synchronize()
+        xf = out.float()
+        yr = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(torch.bfloat16)
+        d = (y.float() - yr.float()).abs()
+        assert (d <= yr.float().abs().clamp_min(1e-3) * 2 ** -6).all(), d.max().item()
+        assert (d > 0).float().mean().item() < 0.01
+
+
+@pytest.mark.parametrize("I,K,mb,rows,grid", [(12288, 4096, 16, 16, 148), (9728, 2560, 16, 16, 148), (6144, 2048, 64, 64, 148),
+                                              (1024, 512, 16, 9, 37), (12288, 4096, 256, 1024, 148), (14336, 4096, 128, 128, 148)])
+def test_gemm_swiglu_fused_epilogue(I, K, mb, rows, grid):
+    """kModeSwiglu: 64 gate + 64 up rows per tile out of the [gate; up] stack -> bf16(bf16(silu(g)) * u) (Qwen3MLP)."""
+    dev = _cuda()
+    from dflash_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(I + K + rows)
+    groups, part, flags = _fused_scratch(dev, I // 64, mb, rows, grid)
+    W = (torch.randn(2 * I, K, device=dev) * 0.05).to(torch.bfloat16)
+    X = torch.randn(groups * mb, K, device=dev).to(torch.bfloat16)
+    out = torch.zeros(rows, I, dtype=torch.bfloat16, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for rep in range(2):
+        out.zero_()
+        _lib.check(lib.dflash_gemm_swiglu(_ptr(W), I, K, _ptr(X), groups * mb, mb, rows, _ptr(out), I, _ptr(part),
+                                          _ptr(flags), grid, 0, st))
+        torch.cuda.synchronize()
+        assert int(flags.abs().sum()) == 0
+        gu = (X[:rows].float() @ W.float().t()).to(torch.bfloat16)
+        g, u = gu[:, :I], gu[:, I:]
+        exp = torch.nn.functional.silu(g) * u
+        assert _rel_err(out, exp) < 4e-3
+        diff = (out.float() - exp.float()).abs()
+        assert (diff <= exp.float().abs() * 2 ** -5 + 2e-3).all(), diff.max().item()
+
+
 @pytest.mark.parametrize("mb,rows", [(128, 512), (256, 256), (256, 1024)])
 def test_gemm_argmax_column_groups(mb, rows):
     dev = _cuda()

@@ -40,6 +40,7 @@ if os.environ.get("DFLASH_BENCH_BS"):  # block-size sweep (BASELINE configs[4] s
     Q8 = dict(Q8, block_size=int(os.environ["DFLASH_BENCH_BS"]))
 PROMPT_LEN = 128
 MAX_NEW = 2048
+SHARDED_BATCH = 64  # BASELINE.json configs[4]: global batch sharded over the GPUs of the job
 TAU_SCHEDULE_LEN = 64
 MEAN_TAU_TARGET = 7.3  # published Qwen3-8B-DFlash-b16 math-average acceptance length
 
@@ -65,6 +66,19 @@ def forced_schedule(seed=0, n=TAU_SCHEDULE_LEN, bs=None):
         out.append(k)
         tot += k
     return out
+
+
+def workload_config(world, R=1):
+    """The `config` object BOTH arms print (the driver compares them): BASELINE.json configs[1]."""
+    ks = forced_schedule(seed=0)
+    mean_tau = sum(k + 1 for k in ks) / len(ks)
+    return dict(workload="Qwen3-8B + DFlash-b16 draft+verify step (target forward excluded, SURVEY 8d), "
+                         f"batch {R} per GPU, bs {Q8['block_size']}, prompt {PROMPT_LEN}, up to {MAX_NEW} new tokens, "
+                         f"forced-tau schedule mean {mean_tau:.2f} (BASELINE.json configs[1])",
+                l2="inputs larger than L2: 3.34 GB of weights streamed per step vs 126 MB L2",
+                parallelism=f"dp{world} (independent request streams per GPU; one packed all-gather of the results "
+                            "per generation)",
+                mean_tau=mean_tau)
 
 
 def algorithmic_bytes(dims, S, c, R=1):
@@ -208,14 +222,18 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: take every core this process may run on
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     steps = min(args.steps, 60)   # bounded sample: ~10 s of CPU work at ~0.17 s per step
-    warmup = min(max(args.warmup, 1), 3)
+    warmup = args.warmup
     tps, ms, cores, sample = cpu_step_bench(Q8, steps, warmup)
     line = dict(metric="draft_verify_tokens_per_s", value=tps, unit="tokens/s", n_gpus=args.gpus, steps=steps,
                 warmup=warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="Qwen3-8B + DFlash-b16 draft+verify step, batch 1, bs 16, prompt 128, forced-tau "
-                                     "schedule mean 7.3 (BASELINE.json configs[1])", step_us=ms * 1e3),
+                config=workload_config(args.gpus, args.requests), step_us=dict(median=ms * 1e3),
                 cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 torch_threads=torch.get_num_threads())
@@ -259,6 +277,59 @@ def build_engine(dims, device, seed, R=1, max_new=None, keep_draft_logits=False)
     return draft, eng, embed, lm_head
 
 
+def gpu_reference_bench(dims, draft, embed, lm_head, device, ks, steps=100, warmup=10):
+    """The reference's torch op sequence for the SAME step on the SAME GPU (north-star comparison: ">= 5x lower
+    draft+verify step latency than the reference torch/sdpa path"). The reference source cannot travel to the GPU box,
+    so this runs the oracle's op-for-op restatement (oracle/dflash_oracle.py, pinned to the reference by
+    tests/test_oracle_golden.py) in bf16 on the engine's own weights, with the reference's concat cache and per-cycle
+    host sync (model/dflash.py:235-268), once with sdpa (transformers' default dispatch) and once with eager attention.
+    Spans as benchmark.py:99-160 (CUDA events around the step). A reported baseline: the oracle is the thing timed
+    here, never the thing shipped."""
+    import torch
+    from oracle import dflash_oracle as O
+    H, V, L, bs = dims["hidden"], dims["vocab"], dims["draft_layers"], dims["block_size"]
+    nsel = L
+    bf = torch.bfloat16
+    sd = {k: v for k, v in draft.state_dict().items()}
+    cfg = O.DraftConfig.from_hf(draft)
+    cfg.inv_freq = cfg.get_inv_freq().to(device)
+    g = torch.Generator(device=device).manual_seed(100)
+    tlogits = torch.randn(1, bs, V, device=device, generator=g).to(bf)
+    hsel = [(torch.randn(1, bs, H, device=device, generator=g) * 0.5).to(bf) for _ in range(nsel)]
+    out = {}
+    for impl in ("sdpa", "eager"):
+        O.ATTN_IMPL = impl
+        cache = O.DraftCache()
+        start = PROMPT_LEN
+        block = torch.full((1, bs), dims["mask_token_id"], dtype=torch.long, device=device)
+        block[0, 0] = 1
+        th = (torch.randn(1, PROMPT_LEN, nsel * H, device=device, generator=g) * 0.5).to(bf)
+        times = []
+        with torch.inference_mode():
+            for it in range(warmup + steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                pos = torch.arange(cache.get_seq_length(), start + bs, device=device).unsqueeze(0)
+                O.draft_verify_step_cpu(sd, cfg, embed, lm_head, block, th, pos, cache, start, tlogits, hsel, 0.0)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= warmup:
+                    times.append(e0.elapsed_time(e1) * 1e3)
+                tau = ks[it % len(ks)] + 1  # the same forced-acceptance schedule as the CUDA arm
+                th = torch.cat(hsel, dim=-1)[:, :tau, :]
+                start += tau
+        times.sort()
+        out[impl] = dict(step_us_median=times[len(times) // 2], step_us_p10=times[len(times) // 10],
+                         step_us_p90=times[len(times) * 9 // 10], steps=steps, final_cache_len=cache.get_seq_length())
+    O.ATTN_IMPL = "sdpa"
+    out["note"] = ("oracle port of model/dflash.py:235-268 (torch bf16 ops, concat KV cache, host sync per cycle) on this "
+                   "GPU, same weights / dims / forced-tau schedule as the CUDA arm; sdpa = transformers' default dispatch "
+                   "(its per-step KV length change makes the fused-attention backend re-plan every call), eager = "
+                   "softmax(QK^T)V in torch ops")
+    return out
+
+
 def full_cycle_bench(dims, draft, eng, embed, lm_head, device, ks, new_tokens=512):
     """Whole spec-decode cycles through the public API (`draft.spec_generate`) with a random-init HF target of
     Qwen3-8B shape: (a) the target called eagerly with a DynamicCache exactly as the reference does, (b) the same
@@ -287,7 +358,7 @@ def full_cycle_bench(dims, draft, eng, embed, lm_head, device, ks, new_tokens=51
     prompt = torch.randint(0, dims["vocab"] - 1, (1, PROMPT_LEN), device=device, generator=g)
     out = {}
     # (attn_implementation="eager" cannot be captured: transformers builds a CPU tensor in its mask path)
-    rows = (("eager_target", False), ("graphed_target", True))
+    rows = (("default", None), ("eager_target", False), ("graphed_target", True))
     for name, graph in rows:
         draft.spec_generate(target, prompt, 64, None, 0.0, forced_k=ks, graph_target=graph)  # warm-up / capture
         torch.cuda.synchronize()
@@ -299,17 +370,161 @@ def full_cycle_bench(dims, draft, eng, embed, lm_head, device, ks, new_tokens=51
         n = ids.shape[1] - prompt.shape[1]
         out[name] = dict(tokens_per_s=n / dt, new_tokens=n, cycles=len(taus), mean_tau=sum(taus) / max(1, len(taus)),
                          ms_per_cycle=dt / max(1, len(taus)) * 1e3, wall_s=dt)
+    # the reference's own loop (oracle port of model/dflash.py:192-277: torch ops for the draft, the same HF target
+    # called eagerly with a DynamicCache), same prompt / schedule / GPU
+    from oracle import dflash_oracle as O
+    sd = {k: v for k, v in draft.state_dict().items()}
+    ocfg = O.DraftConfig.from_hf(draft)
+    ocfg.inv_freq = ocfg.get_inv_freq().to(device)
+    O.spec_generate(sd, ocfg, target, prompt, 64, None, 0.0, forced_k=ks)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ids, taus = O.spec_generate(sd, ocfg, target, prompt, new_tokens, None, 0.0, forced_k=ks)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n = ids.shape[1] - prompt.shape[1]
+    out["reference_loop"] = dict(tokens_per_s=n / dt, new_tokens=n, cycles=len(taus),
+                                 mean_tau=sum(taus) / max(1, len(taus)), ms_per_cycle=dt / max(1, len(taus)) * 1e3,
+                                 wall_s=dt)
+    out["speedup_vs_reference_loop"] = {k: out[k]["tokens_per_s"] / out["reference_loop"]["tokens_per_s"]
+                                        for k in ("default", "eager_target", "graphed_target")}
     out["note"] = ("prefill + decode wall clock of spec_generate, batch 1, random-init Qwen3-8B target (bf16, sdpa), "
-                   "forced-tau schedule; target forward is the caller's HF module in both rows")
+                   "forced-tau schedule; the target forward is the caller's HF module in every row; `default` = what "
+                   "spec_generate does without extra arguments (graphed target when capturable); reference_loop = the "
+                   "oracle port of the reference's loop on the same GPU")
     draft.release_engine()
     del target
     torch.cuda.empty_cache()
     return out
 
 
+TAU_HIST_COLS = 512  # acceptance lengths per request carried by the result gather
+
+
+class StepRunner:
+    """R request streams of the BASELINE workload in one engine: synthetic target outputs resident in HBM, the whole
+    draft+verify step (2 + 8 L + 1 + 1 kernels, device-resident state, PDL edges) captured in ONE CUDA graph."""
+
+    def __init__(self, eng, dims, device, R, seed, ks):
+        import torch
+        self.eng, self.R, self.ks, self.device = eng, R, ks, device
+        bs, H, V, nsel = dims["block_size"], dims["hidden"], dims["vocab"], dims["draft_layers"]
+        g = torch.Generator(device=device).manual_seed(seed)
+        self.tlogits = torch.randn(R * bs, V, device=device, generator=g).to(torch.bfloat16)
+        self.hsel = [(torch.randn(R * bs, H, device=device, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        self.prompt_hidden = [(torch.randn(PROMPT_LEN, H, device=device, generator=g) * 0.5).to(torch.bfloat16)
+                              for _ in range(nsel)]
+        self.prompt = torch.randint(0, V - 1, (PROMPT_LEN,), device=device, generator=g)
+        self.forced = torch.tensor([ks] * R, dtype=torch.int32, device=device)  # every stream: the same schedule
+        self.steps_per_gen, cum = 0, 0  # cycles one 2048-token generation lasts under the schedule
+        while cum + ks[self.steps_per_gen % len(ks)] + 1 <= MAX_NEW - bs:
+            cum += ks[self.steps_per_gen % len(ks)] + 1
+            self.steps_per_gen += 1
+        self.since_reset, self.tokens = 0, 0
+        self.reset()
+        self.enqueue_step()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream())
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            self.enqueue_step()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.enqueue_step()
+        torch.cuda.synchronize()
+        self.side = side
+        self.reset()
+
+    def enqueue_step(self):
+        self.eng.draft_step()
+        self.eng.verify_step(self.tlogits, self.hsel, temperature=0.0, forced_k=self.forced)
+
+    def reset(self):
+        for r in range(self.R):
+            self.eng.reset_request(r, self.prompt, 1, MAX_NEW)
+            self.eng.prefill_context(r, self.prompt_hidden)
+        self.since_reset = 0
+
+    def run(self, n, events=None):
+        """n graph replays on the current stream. When the 2048-token generation is used up the requests are
+        re-initialised (a few memsets + the prompt context pass: inside the timed region, ~0.3% of it)."""
+        ks = self.ks
+        for i in range(n):
+            if self.since_reset >= self.steps_per_gen:
+                self.reset()
+            if events is not None:
+                events[i][0].record()
+            self.graph.replay()
+            if events is not None:
+                events[i][1].record()
+            self.tokens += self.R * (ks[self.since_reset % len(ks)] + 1)
+            self.since_reset += 1
+
+    def packed_result(self):
+        """The generation's result rows [R, 1 + MAX_NEW + TAU_HIST_COLS] int32 (what a DP rank contributes)."""
+        from dflash_b200 import dist as ddist
+        eng = self.eng
+        n_out = (eng.buf["start"][: self.R] - PROMPT_LEN).to(self.tlogits.device)
+        toks = eng.output_ids[: self.R, PROMPT_LEN:PROMPT_LEN + MAX_NEW]
+        taus = eng.acc_hist[: self.R, :TAU_HIST_COLS]
+        return ddist.pack_streams(n_out, toks, taus)
+
+    def check(self):
+        import torch
+        eng, ks = self.eng, self.ks
+        n_dev = int(eng.buf["n_cycles"][0])
+        assert n_dev == self.since_reset, (n_dev, self.since_reset)
+        assert eng.acc_hist[0, :n_dev].tolist() == [ks[i % len(ks)] + 1 for i in range(n_dev)], "forced-tau drifted"
+        assert int(eng.buf["done"][: self.R].sum()) == 0
+        assert torch.equal(eng.buf["start"][: self.R], eng.buf["start"][:1].expand(self.R))
+
+
+def timed_steps(runner, steps, warmup, device, local, sample_clocks=True):
+    """W warm-up steps, then exactly `steps` steps + ONE packed all-gather of the results (the data path's only
+    collective, once per generation) between two events, barrier + synchronize on both sides. Returns a dict."""
+    import torch
+    from dflash_b200 import dist as ddist
+    world = ddist.world_size()
+    runner.reset()
+    runner.run(warmup)
+    packed = runner.packed_result()
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=device)
+    ddist.all_gather_packed(packed, gathered)  # communicator set-up happens here, outside the timed region
+    torch.cuda.synchronize()
+    ddist.barrier()
+    clocks = ClockSampler(local) if sample_clocks else None
+    if clocks:
+        clocks.start()
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t_begin, t_end, t_g0 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    ddist.barrier()
+    runner.tokens = 0
+    t_begin.record()
+    runner.run(steps, events)
+    t_g0.record()
+    ddist.all_gather_packed(runner.packed_result(), gathered)
+    t_end.record()
+    torch.cuda.synchronize()
+    ddist.barrier()
+    clock_info = clocks.stop() if clocks else None
+    runner.check()
+    total_ms = t_begin.elapsed_time(t_end)
+    step_us = sorted(e0.elapsed_time(e1) * 1e3 for e0, e1 in events)
+    total_ms_max = ddist.max_over_ranks(total_ms, device)
+    tokens_all = ddist.sum_over_ranks(runner.tokens, device)
+    n_expect = int(runner.eng.buf["start"][0]) - PROMPT_LEN
+    assert gathered.shape[0] == world and bool((gathered[:, :, 0] == n_expect).all()), "gathered lengths differ"
+    return dict(value=tokens_all / (total_ms_max / 1e3), total_ms=total_ms_max, step_us=step_us,
+                gather_us=ddist.max_over_ranks(t_g0.elapsed_time(t_end) * 1e3, device), clocks=clock_info,
+                gather_bytes_per_rank=packed.numel() * 4)
+
+
 def run_cuda_arm(args):
     import torch
     from dflash_b200 import dist as ddist
+    from dflash_b200.engine import DraftEngine
     rank, world, local = ddist.init()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
@@ -320,97 +535,20 @@ def run_cuda_arm(args):
     nsel = L
     R = args.requests
     draft, eng, embed, lm_head = build_engine(dims, device, seed=rank, R=R)
-    g = torch.Generator(device=device).manual_seed(100 + rank)
-    # synthetic target outputs for the block (resident in HBM for `value`; pinned host copies for `e2e`)
-    tlogits = torch.randn(R * bs, V, device=device, generator=g).to(torch.bfloat16)
-    hsel = [(torch.randn(R * bs, H, device=device, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
-    prompt_hidden = [(torch.randn(PROMPT_LEN, H, device=device, generator=g) * 0.5).to(torch.bfloat16)
-                     for _ in range(nsel)]
-    prompt = torch.randint(0, V - 1, (PROMPT_LEN,), device=device, generator=g)
     ks = forced_schedule(seed=0)
-    forced = torch.tensor([ks] * R, dtype=torch.int32, device=device)  # every stream follows the same schedule
     mean_tau = sum(k + 1 for k in ks) / len(ks)
-    steps_per_gen, cum = 0, 0  # cycles one 2048-token generation lasts under the schedule
-    while cum + ks[steps_per_gen % len(ks)] + 1 <= MAX_NEW - bs:
-        cum += ks[steps_per_gen % len(ks)] + 1
-        steps_per_gen += 1
-
-    def reset():
-        for r in range(R):
-            eng.reset_request(r, prompt, 1, MAX_NEW)
-            eng.prefill_context(r, prompt_hidden)
-
-    def enqueue_step():
-        eng.draft_step()
-        eng.verify_step(tlogits, hsel, temperature=0.0, forced_k=forced)
-
-    reset()
-    enqueue_step()
-    torch.cuda.synchronize()
-    # one CUDA graph = one whole draft+verify step (57 kernels, device-resident state, PDL edges)
-    side = torch.cuda.Stream(device=device)
-    side.wait_stream(torch.cuda.current_stream())
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        enqueue_step()
-    torch.cuda.synchronize()
-    with torch.cuda.graph(graph, stream=side):
-        enqueue_step()
-    torch.cuda.synchronize()
+    runner = StepRunner(eng, dims, device, R, 100 + rank, ks)
+    tlogits, hsel, forced, side = runner.tlogits, runner.hsel, runner.forced, runner.side
+    steps_per_gen = runner.steps_per_gen
     launches_per_step = eng.kernels_per_draft_step + eng.kernels_per_verify_step
 
-    ctr = dict(since_reset=0, tokens=0)
-
-    def do_reset():
-        reset()
-        ctr["since_reset"] = 0
-
-    def run_steps(n, events=None):
-        """n graph replays on the current stream. When the 2048-token generation is used up the request is
-        re-initialised (a few memsets + the prompt context pass: inside the timed region, ~0.3% of it)."""
-        for i in range(n):
-            if ctr["since_reset"] >= steps_per_gen:
-                do_reset()
-            if events is not None:
-                events[i][0].record()
-            graph.replay()
-            if events is not None:
-                events[i][1].record()
-            ctr["tokens"] += R * (ks[ctr["since_reset"] % len(ks)] + 1)
-            ctr["since_reset"] += 1
-
-    do_reset()
-    run_steps(args.warmup)
-    torch.cuda.synchronize()
-    ddist.barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_begin = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ddist.barrier()
-    ctr["tokens"] = 0
-    t_begin.record()
-    run_steps(args.steps, events)
-    t_end.record()
-    torch.cuda.synchronize()
-    ddist.barrier()
-    clock_info = clocks.stop()
-    total_ms = t_begin.elapsed_time(t_end)
-    step_us = sorted(e0.elapsed_time(e1) * 1e3 for e0, e1 in events)
-    # tokens committed in the timed region: counted from the schedule, cross-checked against the device's
-    # own acceptance history of the current generation
-    tokens = ctr["tokens"]
-    n_dev = int(eng.buf["n_cycles"][0])
-    assert n_dev == ctr["since_reset"], (n_dev, ctr)
-    assert eng.acc_hist[0, :n_dev].tolist() == [ks[i % len(ks)] + 1 for i in range(n_dev)], "forced-tau drifted"
-    assert int(eng.buf["done"][0]) == 0
-    total_ms_max = ddist.max_over_ranks(total_ms, device)
-    tokens_all = ddist.sum_over_ranks(tokens, device)
-    value = tokens_all / (total_ms_max / 1e3)
+    res = timed_steps(runner, args.steps, args.warmup, device, local)
+    value, total_ms_max, step_us, clock_info = res["value"], res["total_ms"], res["step_us"], res["clocks"]
     med = step_us[len(step_us) // 2]
     p10, p90 = step_us[len(step_us) // 10], step_us[(len(step_us) * 9) // 10]
+
+    def do_reset():
+        runner.reset()
 
     # ---- e2e: host buffers in, result out, through the C-ABI call sequence, copies inside the timed region
     # the step's host inputs live in ONE pinned staging buffer (logits rows, then the n_sel hidden-state blocks) so
@@ -515,23 +653,46 @@ def run_cuda_arm(args):
     lm_bytes = 2 * V * H + 16 * H * 2
     achieved = lm_bytes / (lm_us * 1e-6) / 1e9
 
+    # DRAM traffic of that kernel: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
+    # command, kept under profiles/ by scripts/ncu_table.py (not re-measured per run; null when no capture is committed)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_lm_head_r2.json")))
+        traffic, traffic_src = float(tj["dram_bytes_per_launch"]), "profiles/ncu_lm_head_r2.json (" + tj.get("source", "") + ")"
+    except Exception:
+        pass
+
     # whole-step roofline at the mean cache length of the timed region
     S_mid = PROMPT_LEN + int(mean_tau * min(args.steps, steps_per_gen) / 2)
     ab = algorithmic_bytes(dims, S_mid, round(mean_tau), R)
     step_gbs = ab["total"] / (med * 1e-6) / 1e9
 
-    # ---- DP result gather over NCCL (outside the timed region; latency reported)
-    n_cyc = int(eng.buf["n_cycles"][0])
-    n_out = (eng.buf["start"][0:1] - PROMPT_LEN).to(torch.int32)
-    toks_out = eng.output_ids[0:1, PROMPT_LEN:PROMPT_LEN + MAX_NEW].contiguous()
-    taus = eng.acc_hist[0:1, :512].contiguous()
-    torch.cuda.synchronize()
-    tg = time.perf_counter()
-    g_n, g_t, g_a = ddist.gather_streams(n_out, toks_out, taus, world)
-    torch.cuda.synchronize()
-    gather_us = (time.perf_counter() - tg) * 1e6
-    assert g_n.shape[0] == world and g_t.shape == (world, MAX_NEW)
-    del n_cyc
+    # ---- BASELINE configs[4] shape: a global batch of 64 requests sharded over the GPUs of the job (64 / N request
+    #      streams per engine), same step, the packed all-gather of all 64 results inside the timed region
+    sharded = None
+    if not args.no_sharded and R == 1 and SHARDED_BATCH % world == 0:
+        Rs = SHARDED_BATCH // world
+        span = PROMPT_LEN + MAX_NEW + 64
+        eng_s = DraftEngine(draft, embed, lm_head, max_seq=span, out_len=span, max_requests=Rs, block_size=bs,
+                            device=device)
+        runner_s = StepRunner(eng_s, dims, device, Rs, 200 + rank, ks)
+        rs = timed_steps(runner_s, max(10, min(args.steps, 40)), 5, device, local, sample_clocks=False)
+        su = rs["step_us"]
+        sharded = dict(workload=f"global batch {SHARDED_BATCH} requests, {Rs} request streams per GPU (BASELINE.json "
+                                "configs[4] shape at bs 16), forced-tau schedule, one packed all-gather per generation",
+                       scaling="strong", global_batch=SHARDED_BATCH, streams_per_gpu=Rs, tokens_per_s=rs["value"],
+                       step_us_median=su[len(su) // 2], steps=len(su), gather_us=rs["gather_us"],
+                       gather_bytes_per_rank=rs["gather_bytes_per_rank"])
+        eng_s.close()
+        del runner_s, eng_s
+        torch.cuda.empty_cache()
+
+    gpu_ref = None
+    if rank == 0 and world == 1 and R == 1 and not args.no_gpu_reference:
+        try:
+            gpu_ref = gpu_reference_bench(dims, draft, embed, lm_head, device, ks)
+        except Exception as ex:  # the headline numbers do not depend on this section
+            gpu_ref = dict(error=f"{type(ex).__name__}: {ex}")
 
     full_cycle = None
     if rank == 0 and world == 1 and R == 1 and not args.no_full_cycle:
@@ -552,19 +713,13 @@ def run_cuda_arm(args):
             metric="draft_verify_tokens_per_s", value=value, unit="tokens/s", n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak",
             vs_baseline=None, dtype="bf16", data="synthetic",
-            config=dict(workload="Qwen3-8B + DFlash-b16 draft+verify step (target forward excluded, SURVEY 8d), "
-                                 f"batch {R} per GPU, bs {bs}, prompt 128, up to 2048 new tokens, forced-tau schedule "
-                                 f"mean {mean_tau:.2f} (BASELINE.json configs[1])",
-                        l2="inputs larger than L2: 3.34 GB of weights streamed per step vs 126 MB L2",
-                        parallelism=f"dp{world} (independent request stream per GPU, no data-path collective)",
-                        mean_tau=mean_tau, pdl=bool(eng.ccfg.use_pdl)),
+            config=workload_config(world, R),
             step_us=dict(median=med, p10=p10, p90=p90),
             hbm_gbs_step=step_gbs,
             step_roofline=dict(bound="hbm", achieved=step_gbs, peak=peak_gbs, unit="GB/s", frac=step_gbs / peak_gbs,
                                algorithmic_bytes=ab["total"], note=f"all {launches_per_step} kernels of the step, median step time"),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
-                          traffic=1244.860e6 + 4.830e6,  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one
-                          # `ncu --set full` capture of this command (profiles/ncu_gemm_r1_table.md); not re-measured per run
+                          traffic=traffic, traffic_source=traffic_src,
                           kernel="gemm_skinny_kernel<16,argmax> (lm_head 151936x4096 + fused argmax)",
                           launch_us=lm_us, algorithmic_bytes=lm_bytes, peak_source=peak_src),
             cpu_baseline=cpu,
@@ -573,7 +728,14 @@ def run_cuda_arm(args):
             gpu_launches=launches_per_step * args.steps,
             launches_per_step=launches_per_step,
             clocks=clock_info,
-            gather_us=gather_us,
+            gather_us=res["gather_us"],
+            gather=dict(collective="all_gather_into_tensor (NCCL), one packed int32 buffer per generation, inside the "
+                                   "timed region", bytes_per_rank=res["gather_bytes_per_rank"], us=res["gather_us"]),
+            sharded_batch=sharded,
+            gpu_reference=gpu_ref,
+            step_speedup_vs_torch=(None if not gpu_ref or "error" in gpu_ref else
+                                   dict(sdpa=gpu_ref["sdpa"]["step_us_median"] / med,
+                                        eager=gpu_ref["eager"]["step_us_median"] / med)),
             full_cycle=full_cycle,
         )
         emit(line)
@@ -611,6 +773,9 @@ def main():
     ap.add_argument("--requests", type=int, default=1, choices=[1, 2, 4, 8, 16, 32, 64],
                     help="request streams per GPU sharing one weight stream (headline metric is quoted at 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the global-batch-64 sharded section")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the torch op sequence of the same step on the GPU (north-star comparison)")
     ap.add_argument("--no-full-cycle", action="store_true",
                     help="skip the whole-cycle section (spec_generate with a random-init Qwen3-8B target)")
     args = ap.parse_args()

@@ -118,6 +118,8 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   sz[DFLASH_BUF_PART] = static_cast<size_t>(part_elems) * 4;
   sz[DFLASH_BUF_FLAGS] = static_cast<size_t>(n_flags) * 4;
   sz[DFLASH_BUF_COUNTERS] = static_cast<size_t>(R + 2) * 4;
+  sz[DFLASH_BUF_ROW_POS] = static_cast<size_t>(RS2p + kPrefillRows) * 4;
+  sz[DFLASH_BUF_ROPE] = static_cast<size_t>(RS2p + kPrefillRows) * 128 * 4;
   sz[DFLASH_BUF_ATTN_PO] = static_cast<size_t>(nsa) * RS * Hq * 128 * 4;
   sz[DFLASH_BUF_ATTN_ML] = static_cast<size_t>(nsa) * RS * Hq * 2 * 4;
   const int ncand = c.max_candidates > 1 ? 4 : 1;
@@ -203,20 +205,35 @@ inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+// rows of the position / rotary table: [0, 2 RS padded) = the step's activation rows, then the prompt-pass rows
+inline int rope_pf_row0(const Engine* e) { return rows_padded(2 * e->RS); }
+
+inline RopeTableArgs rope_table_args(Engine* e) {
+  RopeTableArgs t;
+  memset(&t, 0, sizeof(t));
+  t.R = e->R; t.SL = e->SL; t.S_max = e->cfg.max_seq;
+  t.start = e->buf<int>(DFLASH_BUF_START);
+  t.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  t.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  t.inv_freq = e->w.inv_freq;
+  t.rope_scale = e->cfg.rope_scale;
+  t.row_pos = e->buf<int>(DFLASH_BUF_ROW_POS);
+  t.rope = e->buf<float>(DFLASH_BUF_ROPE);
+  return t;
+}
+
 inline QkvPostArgs qkv_post_args(Engine* e, int l, bool kv_only) {
   QkvPostArgs a;
   memset(&a, 0, sizeof(a));
-  a.R = e->R; a.SL = e->SL; a.bs = e->bs; a.Hq = e->Hq; a.Hkv = e->Hkv;
+  a.R = e->R; a.SL = e->SL; a.Hq = e->Hq; a.Hkv = e->Hkv;
   a.q_cols = kv_only ? 0 : e->Hq * 128;
-  a.start = e->buf<int>(DFLASH_BUF_START);
-  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-  a.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  const int t0 = kv_only ? rope_pf_row0(e) : 0;
+  a.row_pos = e->buf<int>(DFLASH_BUF_ROW_POS) + t0;
+  a.rope = e->buf<float>(DFLASH_BUF_ROPE) + static_cast<size_t>(t0) * 128;
   a.q_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].q_norm);
   a.k_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].k_norm);
   const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(e->layers[l].bqkv);
   a.bias = b == nullptr ? nullptr : (kv_only ? b + e->Hq * 128 : b);
-  a.inv_freq = e->w.inv_freq;
-  a.rope_scale = e->cfg.rope_scale;
   a.eps = e->cfg.rms_eps;
   a.q_out = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
   const size_t per = static_cast<size_t>(e->R) * e->Hkv * e->cfg.max_seq * 128;
@@ -437,8 +454,8 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     b.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
     b.out = a_in + static_cast<size_t>(RS) * e->H;
     b.eps = e->cfg.rms_eps;
-    DFL_CUDA(launch_pdl(rows_pre_kernel, dim3(2 * RS), dim3(kNormThreads), 0, st, e->pdl, c, b, RS),
-             "ctx norm + embed + ln1");
+    DFL_CUDA(launch_pdl(rows_pre_kernel, dim3(2 * RS), dim3(kNormThreads), 0, st, e->pdl, c, b, rope_table_args(e), RS),
+             "ctx norm + embed + ln1 + rope table");
   }
   AttnArgs aa;
   memset(&aa, 0, sizeof(aa));
@@ -628,12 +645,19 @@ inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int n_ro
                         norm_args(e, e->buf<__nv_bfloat16>(DFLASH_BUF_PF_Y), ss_pf, kPrefillRows, e->w.hidden_norm,
                                   e->buf<__nv_bfloat16>(DFLASH_BUF_PF_A))),
              "prefill hidden_norm");
+    {
+      RopeTableArgs t = rope_table_args(e);
+      t.row_pos += rope_pf_row0(e);
+      t.rope += static_cast<size_t>(rope_pf_row0(e)) * 128;
+      t.pf_rows = n;
+      t.pf_pos0 = pos0 + c0;
+      DFL_CUDA(launch_pdl(rope_table_kernel, dim3(n), dim3(64), 0, st, e->pdl, t), "prefill rope table");
+    }
     for (int l = 0; l < e->L; ++l) {
       GemmPlan kp = e->kv_pf[l * 5 + pi];
       kp.args.m_valid = n;
       kp.args.qkv.pf_rows = n;
       kp.args.qkv.pf_req = r;
-      kp.args.qkv.pf_pos0 = pos0 + c0;
       DFL_CUDA(launch_gemm(kp, st, e->pdl), "prefill kv gemm");
     }
   }

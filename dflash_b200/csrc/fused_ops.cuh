@@ -236,11 +236,15 @@ __device__ __forceinline__ void embed_row_body(const EmbedArgs& a, int row, int 
 }
 
 // The step's first small kernel: CTAs [0, rows0) finish the context injection (hidden_norm over the fc GEMM's bf16
-// rows, model/dflash.py:177), the rest embed the block and apply layer 0's input_layernorm.
-__global__ void __launch_bounds__(kNormThreads) rows_pre_kernel(const NormArgs c, const EmbedArgs e, const int rows0) {
+// rows, model/dflash.py:177), the rest embed the block and apply layer 0's input_layernorm. CTA b also fills row b of
+// the step's position / rotary table (Qwen3RotaryEmbedding, model/dflash.py:178), which every layer's QKV epilogue
+// reads: request state is only read after griddepcontrol.wait (the verify kernel of the previous cycle wrote it).
+__global__ void __launch_bounds__(kNormThreads) rows_pre_kernel(const NormArgs c, const EmbedArgs e, const RopeTableArgs t,
+                                                               const int rows0) {
   __shared__ float red[kNormThreads / 32];
   if (static_cast<int>(blockIdx.x) < rows0) norm_row_body(c, blockIdx.x, threadIdx.x);
   else embed_row_body(e, blockIdx.x - rows0, threadIdx.x, red);
+  rope_table_row(t, blockIdx.x, threadIdx.x);
   DFL_TRACE(2);
 }
 

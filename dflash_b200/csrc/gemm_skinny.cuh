@@ -345,10 +345,31 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     if constexpr (kFused) {
       // ---------------------------------------------------------------- fused row epilogues
       constexpr int kCh = Cfg::kEpiRows;
+      constexpr int kRpw = kCh / 4;  // activation rows of a chunk per warp (row j = quarter + 4 * i)
       static_assert(MB % kCh == 0 && kCh % 16 == 0, "epilogue tile");
       __shared__ __align__(16) float s_t[kCh * kTileN];  // tile[m][n] of the current chunk of activation rows
       const long long part_stride = static_cast<long long>(kTileN) * MB;  // floats per CTA partial
       float* my_part = a.part + (static_cast<long long>(blockIdx.x) * G + cta) * part_stride;
+      // Per-row operands of the epilogue that do not depend on the accumulator (residual values; row position and
+      // rotary table entries) are requested BEFORE the wait for the accumulator: at the end of the kernel the
+      // epilogue of the last tile is exposed, and an L2 round trip per row there costs more than the math.
+      uint2 pre_rs[MODE == kModeRows ? kRpw : 1];
+      QkvRowPre pre_q[MODE == kModeQkv ? kRpw : 1];
+      float4 norm_wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto prefetch_rows = [&](int tile, int c) {
+#pragma unroll
+        for (int i = 0; i < kRpw; ++i) {
+          const int m = c * kCh + quarter + 4 * i;
+          const int row = a.x_row0 + m0 + (m < mv ? m : 0);
+          if constexpr (MODE == kModeRows) {
+            if (a.rows.resid != nullptr)
+              pre_rs[i] = __ldcg(reinterpret_cast<const uint2*>(a.rows.resid + static_cast<long long>(row) * a.rows.ld +
+                                                                tile * kTileN + lane * 4));
+          } else if constexpr (MODE == kModeQkv) {
+            pre_q[i] = qkv_row_prefetch(a.qkv, row, lane);
+          }
+        }
+      };
       long long u = u0;
       while (u < u1) {
         const int tile = static_cast<int>(u / a.k_blocks);
@@ -360,31 +381,53 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const bool writer = slot > 0;                  // the tile began in an earlier CTA: leave a partial for it
         const bool finisher = slot == 0 && nslots > 1; // the tile continues in later CTAs: they left partials for us
         unsigned int* flag = a.flags + static_cast<long long>(blockIdx.x) * a.n_tiles + tile;
-        if (finisher) {
-          // The other CTAs of this tile computed their share at the START of their ranges (or are whole-range
-          // middle slots that end when we do): in practice the partials are already there.
-          if (epi_tid == 0) {
-            while (ld_acquire_u32(flag) < static_cast<unsigned int>(nslots - 1)) __nanosleep(40);
-            *flag = 0u;  // next use is a later launch of this plan
+        if (!writer) {
+          prefetch_rows(tile, 0);
+          if constexpr (MODE == kModeQkv) {
+            const int kind = qkv_kind(a.qkv, tile);
+            if (kind < 2)
+              norm_wv = unpack4_bf16(*reinterpret_cast<const uint2*>((kind == 0 ? a.qkv.q_norm_w : a.qkv.k_norm_w) + lane * 4));
           }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
         }
         mbar_wait(&tfull[acc], acc_phase);
         if (tr && seg_end >= u1 && threadIdx.x == 0) tr[5] = global_ns();
+        if (seg_end >= u1) DFL_TRACE(4);
         tc_fence_after();
+        if (finisher) {
+          // The other CTAs of this tile computed their share at the START of their ranges, or are whole-range middle
+          // slots that end when we do.
+          if (epi_tid == 0) {
+            while (ld_acquire_u32(flag) < static_cast<unsigned int>(nslots - 1)) { }
+            *flag = 0u;  // next use is a later launch of this plan
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          DFL_TRACE(5);
+        }
 #pragma unroll 1
         for (int c = 0; c < MB / kCh; ++c) {
           float v[kCh];
 #pragma unroll
           for (int q = 0; q < kCh / 16; ++q)
             tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + c * kCh + q * 16), v + q * 16);
+          // partial layout: [m / 4][n][4] -> a warp's float4 accesses are 512 contiguous bytes
+          const long long pofs = (static_cast<long long>(c * (kCh / 4)) * kTileN + row_in_tile) * 4;
+          constexpr int kSlotBatch = 64 / kCh;  // other CTAs' partials in flight together (register budget)
+          float4 p[kSlotBatch][kCh / 4];
+          if (finisher) {  // first batch of the other slots' partials: requested before the TMEM load completes
+#pragma unroll
+            for (int b = 0; b < kSlotBatch; ++b)
+              if (1 + b < nslots) {
+                const float* op = my_part + static_cast<long long>(1 + b) * part_stride + pofs;
+#pragma unroll
+                for (int i = 0; i < kCh / 4; ++i)
+                  p[b][i] = __ldcg(reinterpret_cast<const float4*>(op + static_cast<long long>(i) * kTileN * 4));
+              }
+          }
           tmem_ld_wait();
           if (c == MB / kCh - 1) {
             tc_fence_before();
             mbar_arrive(&tempty[acc]);  // the accumulator stage goes back to the MMA warp
           }
-          // partial layout: [m / 4][n][4] -> a warp's float4 accesses are 512 contiguous bytes
-          const long long pofs = (static_cast<long long>(c * (kCh / 4)) * kTileN + row_in_tile) * 4;
           if (writer) {
 #pragma unroll
             for (int i = 0; i < kCh / 4; ++i)
@@ -393,34 +436,47 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             continue;
           }
           if (finisher) {
-            for (int s = 1; s < nslots; ++s) {  // slot order: the summation order is fixed
-              const float* op = my_part + static_cast<long long>(s) * part_stride + pofs;
-              float4 p[kCh / 4];
+            for (int s0 = 1; s0 < nslots; s0 += kSlotBatch) {  // slot order: the summation order is fixed
+              if (s0 > 1) {
 #pragma unroll
-              for (int i = 0; i < kCh / 4; ++i)
-                p[i] = __ldcg(reinterpret_cast<const float4*>(op + static_cast<long long>(i) * kTileN * 4));
+                for (int b = 0; b < kSlotBatch; ++b)
+                  if (s0 + b < nslots) {
+                    const float* op = my_part + static_cast<long long>(s0 + b) * part_stride + pofs;
 #pragma unroll
-              for (int i = 0; i < kCh / 4; ++i) {
-                v[4 * i] += p[i].x; v[4 * i + 1] += p[i].y; v[4 * i + 2] += p[i].z; v[4 * i + 3] += p[i].w;
+                    for (int i = 0; i < kCh / 4; ++i)
+                      p[b][i] = __ldcg(reinterpret_cast<const float4*>(op + static_cast<long long>(i) * kTileN * 4));
+                  }
               }
+#pragma unroll
+              for (int b = 0; b < kSlotBatch; ++b)
+                if (s0 + b < nslots) {
+#pragma unroll
+                  for (int i = 0; i < kCh / 4; ++i) {
+                    v[4 * i] += p[b][i].x; v[4 * i + 1] += p[b][i].y; v[4 * i + 2] += p[b][i].z; v[4 * i + 3] += p[b][i].w;
+                  }
+                }
             }
           }
 #pragma unroll
           for (int j = 0; j < kCh; ++j) s_t[j * kTileN + row_in_tile] = v[j];
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          for (int j = quarter; j < kCh; j += 4) {
+#pragma unroll
+          for (int i = 0; i < kRpw; ++i) {
+            const int j = quarter + 4 * i;
             const int m = c * kCh + j;
-            if (m >= mv) break;
-            const int row = a.x_row0 + m0 + m;  // row of the activation matrix == row of the output
-            if constexpr (MODE == kModeRows) {
-              rows_epi_apply(a.rows, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]), tile, row, lane);
-            } else if constexpr (MODE == kModeSwiglu) {
-              swiglu_epi_apply(a.sw, &s_t[j * kTileN], tile, row, lane);
-            } else {
-              const QkvItem it = qkv_post_prepare(a.qkv, row, tile, lane);
-              qkv_post_apply(a.qkv, it, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]), tile, lane);
+            if (m < mv) {
+              const int row = a.x_row0 + m0 + m;  // row of the activation matrix == row of the output
+              if constexpr (MODE == kModeRows) {
+                rows_epi_apply(a.rows, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]), pre_rs[i], tile, row, lane);
+              } else if constexpr (MODE == kModeSwiglu) {
+                swiglu_epi_apply(a.sw, &s_t[j * kTileN], tile, row, lane);
+              } else {
+                qkv_post_apply(a.qkv, pre_q[i], norm_wv, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]),
+                               row, tile, lane);
+              }
             }
           }
+          if (c + 1 < MB / kCh) prefetch_rows(tile, c + 1);
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
         }
         if (writer) {

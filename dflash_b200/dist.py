@@ -42,6 +42,30 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
+def pack_streams(n_out: torch.Tensor, tokens: torch.Tensor, taus: torch.Tensor) -> torch.Tensor:
+    """One int32 row per request: [n_out | tokens (max_new) | taus (max_cyc)] -- the whole result of a request in a
+    single fixed-shape buffer, so the end-of-generate exchange is ONE collective (token ids fit int32)."""
+    return torch.cat([n_out.view(-1, 1).to(torch.int32), tokens.to(torch.int32), taus.to(torch.int32)], dim=1).contiguous()
+
+
+def unpack_streams(packed: torch.Tensor, max_new: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return (packed[:, 0].contiguous(), packed[:, 1:1 + max_new].to(torch.int64).contiguous(),
+            packed[:, 1 + max_new:].contiguous())
+
+
+def all_gather_packed(packed: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """The data path's only collective: all-gather of the packed per-request rows [B_local, W] -> [world, B_local, W]
+    (NCCL over NVLink on GPUs; replaces the reference's pickled `dist.gather_object`, distributed.py:66-83)."""
+    world = world_size()
+    if out is None:
+        out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    if world == 1:
+        out[0].copy_(packed)
+    else:
+        dist.all_gather_into_tensor(out.view(-1, packed.shape[-1]), packed)
+    return out
+
+
 def gather_streams(n_out: torch.Tensor, tokens: torch.Tensor, taus: torch.Tensor,
                    n_items: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """All-gather the per-request results of every rank and put them back in global request order.
@@ -50,31 +74,22 @@ def gather_streams(n_out: torch.Tensor, tokens: torch.Tensor, taus: torch.Tensor
     tokens int64 [B_local, max_new]   generated token streams (padded)
     taus   int32 [B_local, max_cyc]   acceptance lengths per cycle (0-padded)
     Local request j of rank r is global request r + j * world (see shard_indices). Ranks that hold fewer
-    requests than ceil(N / world) pad with rows of zeros. Returns tensors of leading size n_items.
+    requests than ceil(N / world) pad with rows of zeros. ONE collective (`all_gather_packed`). Returns tensors of
+    leading size n_items.
     """
     world = world_size()
     if world == 1:
         return n_out[:n_items], tokens[:n_items], taus[:n_items]
-    rank = dist.get_rank()
     per = (n_items + world - 1) // world
-
-    def pad(t):
-        if t.shape[0] == per:
-            return t.contiguous()
-        out = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        out[: t.shape[0]] = t
-        return out
-
-    outs = []
-    for t in (n_out, tokens, taus):
-        t = pad(t)
-        buf = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(buf, t)
-        # buf row (r * per + j) is global request r + j * world
-        g = buf.view(world, per, *t.shape[1:]).transpose(0, 1).reshape(world * per, *t.shape[1:])
-        outs.append(g[:n_items].contiguous())
-    del rank
-    return outs[0], outs[1], outs[2]
+    max_new = tokens.shape[1]
+    packed = pack_streams(n_out, tokens, taus)
+    if packed.shape[0] != per:
+        pad = torch.zeros((per, packed.shape[1]), dtype=packed.dtype, device=packed.device)
+        pad[: packed.shape[0]] = packed
+        packed = pad
+    buf = all_gather_packed(packed)  # [world, per, W]; row (r, j) is global request r + j * world
+    g = buf.transpose(0, 1).reshape(world * per, -1)[:n_items]
+    return unpack_streams(g, max_new)
 
 
 def generate_data_parallel(local_generate, prompts: Sequence[torch.Tensor], max_new_tokens: int, device,

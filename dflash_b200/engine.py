@@ -41,7 +41,8 @@ BUFFERS = [
     ("x", torch.bfloat16), ("a_in", torch.bfloat16), ("ctx_feat", torch.bfloat16), ("q", torch.bfloat16),
     ("attn_out", torch.bfloat16), ("a2", torch.bfloat16), ("hmid", torch.bfloat16), ("hn", torch.bfloat16),
     ("kv", torch.bfloat16), ("y_ctx", torch.bfloat16), ("tile_ss", torch.float32), ("part", torch.float32),
-    ("flags", torch.int32), ("counters", torch.int32), ("attn_po", torch.float32), ("attn_ml", torch.float32),
+    ("flags", torch.int32), ("counters", torch.int32), ("row_pos", torch.int32), ("rope", torch.float32),
+    ("attn_po", torch.float32), ("attn_ml", torch.float32),
     ("cand_val", torch.float32), ("cand_idx", torch.int32), ("post_val", torch.float32), ("post_idx", torch.int32),
     ("draft_tokens", torch.int64), ("block_ids", torch.int64), ("posterior", torch.int64),
     ("output_ids", torch.int64), ("start", torch.int32), ("ctx_len", torch.int32), ("done", torch.int32),

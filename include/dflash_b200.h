@@ -107,6 +107,8 @@ enum dflash_buffer_id {
   DFLASH_BUF_PART,         /* fp32 partial accumulators exchanged between the CTAs of a split output tile */
   DFLASH_BUF_FLAGS,        /* uint32 arrival counters per (GEMM, column group, tile); zero between launches */
   DFLASH_BUF_COUNTERS,     /* uint32 [R + 2] arrival counters of the verify kernel and of the token reduce */
+  DFLASH_BUF_ROW_POS,      /* int32 [2*R*SL + 256] absolute position of every activation row of the step (-1 = dead) */
+  DFLASH_BUF_ROPE,         /* fp32 [2*R*SL + 256, 128] rotary table of those rows: cos[64] | sin[64], bf16-rounded */
   DFLASH_BUF_ATTN_PO,
   DFLASH_BUF_ATTN_ML,
   DFLASH_BUF_CAND_VAL,

@@ -56,24 +56,24 @@ for _ in range(6):
 torch.cuda.synchronize()
 rec = buf.view(cap, 2).cpu()
 rec = rec[rec[:, 1] != 0]
-names = {(512, 32, 1): "finalize2", (512, 16, 1): "finalize", (256, 4, 16): "finalize_cl", (256, 192, 1): "qkv_post", (128, 16, 8): "attn_split",
-         (256, 64, 1): "attn_combine", (256, 12, 16): "swiglu", (32, 16, 1): "draft_tokens", (256, 32, 16): "posterior",
-         (32, 1, 1): "accept", (256, 16, 5): "ctx_gather", (192, 1, 148): "gemm"}
+names = {(512, 32, 1): "rows_pre", (512, 16, 1): "norm", (128, 16, 8): "attn_split", (256, 64, 1): "attn_combine",
+         (256, 32, 16): "verify", (192, 1, 148): "gemm", (192, 1, 132): "gemm_lm"}
 ev = []
 for tag, t in rec.tolist():
     phase, bd, gx, gy = tag & 15, (tag >> 4) & 0xFFF, (tag >> 16) & 0xFFFFFF, (tag >> 40) & 0xFFFFFF
     ev.append((t, names.get((bd, gx, gy), f"?{bd},{gx},{gy}"), phase))
 ev.sort()
 # one step = from a finalize2 entry to the next
-starts = [i for i, e in enumerate(ev) if e[1] == "finalize2" and e[2] == 0]
+starts = [i for i, e in enumerate(ev) if e[1] == "rows_pre" and e[2] == 0]
 a, b = starts[-3], starts[-2]
 # the fc GEMM of the step starts before finalize2: back up to its entry
-while a > 0 and not (ev[a][1] == "gemm" and ev[a][2] == 0):
+while a > 0 and not (ev[a][1] == "verify" and ev[a][2] == 0):
     a -= 1
-while b > 0 and not (ev[b][1] == "gemm" and ev[b][2] == 0):
+while b > 0 and not (ev[b][1] == "verify" and ev[b][2] == 0):
     b -= 1
 t0 = ev[a][0]
-ph_name = {0: "entry", 1: "past wait", 2: "end", 3: "first stage landed", 4: "loads consumed", 5: "row reduced"}
+ph_name = {0: "entry", 1: "past wait", 2: "end", 3: "first stage landed", 4: "last accumulator complete",
+           5: "other CTAs' partials arrived"}
 print(f"one step: {(ev[b][0] - t0) / 1e3:.1f} us, {b - a} records")
 prev = t0
 for t, n, p in ev[a:b]:

@@ -118,7 +118,7 @@ def test_gemm_rows_fused_epilogue(N, K, mb, rows, grid, with_resid):
         assert int(flags.abs().sum()) == 0, "arrival counters not reset"
         # bf16 rounding of an fp32 sum that differs in the last bits: allow one bf16 ulp on a tiny fraction
         diff = (out.float() - exp.float()).abs()
-        ulp = exp.float().abs().clamp_min(1e-3) * 2 ** -7
+        ulp = (exp.float().abs() + lin_bf.float().abs() + 1e-3) * 2 ** -6  # (a flipped Linear rounding carries over)
         assert (diff <= ulp).all(), (rep, diff.max().item())
         assert (diff > 0).float().mean().item() < 0.02
         ss_ref = out.float().pow(2).view(rows, N // 128, 128).sum(-1).t()

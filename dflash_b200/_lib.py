@@ -34,14 +34,9 @@ def _declare(lib):
         c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
         c_longlong, c_void_p, c_longlong, c_int, c_int, c_void_p,
     ]
-    lib.dflash_gemm_rows.restype = c_int
-    lib.dflash_gemm_rows.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                     c_longlong, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.dflash_gemm_swiglu.restype = c_int
     lib.dflash_gemm_swiglu.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_longlong,
                                        c_void_p, c_void_p, c_int, c_int, c_void_p]
-    lib.dflash_rms_norm_rows.restype = c_int
-    lib.dflash_rms_norm_rows.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p]
     lib.dflash_gemm_argmax.restype = c_int
     lib.dflash_gemm_argmax.argtypes = [
         c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -283,26 +283,6 @@ int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K
   return DFLASH_OK;
 }
 
-int dflash_gemm_rows(const void* W, int N, int K, const void* X, int x_rows_total, int mb, int m_valid,
-                     const void* bias, void* resid, void* out, long long ld, float* tile_ss, int ss_ld, float* part,
-                     unsigned int* flags, int grid, int use_pdl, void* stream) {
-  if (!W || !X || !out || !tile_ss || !part || !flags) { set_error("gemm_rows: null pointer"); return DFLASH_ERR_ARG; }
-  GemmPlan p;
-  int rc = make_gemm_plan(&p, W, N, 0, N, K, X, x_rows_total, 0, mb, m_valid, kModeRows, grid);
-  if (rc) return DFLASH_ERR_ARG;
-  p.args.part = part;
-  p.args.flags = flags;
-  p.args.rows.bias = static_cast<const __nv_bfloat16*>(bias);
-  p.args.rows.resid = static_cast<__nv_bfloat16*>(resid);
-  p.args.rows.out = static_cast<__nv_bfloat16*>(out);
-  p.args.rows.ld = ld;
-  p.args.rows.tile_ss = tile_ss;
-  p.args.rows.ss_ld = ss_ld;
-  cudaError_t e = launch_gemm(p, static_cast<cudaStream_t>(stream), use_pdl != 0);
-  if (e != cudaSuccess) return cuda_fail(e, "gemm_rows launch");
-  return DFLASH_OK;
-}
-
 int dflash_gemm_swiglu(const void* Wgu, int I, int K, const void* X, int x_rows_total, int mb, int m_valid, void* out,
                        long long ld, float* part, unsigned int* flags, int grid, int use_pdl, void* stream) {
   if (!Wgu || !X || !out || !part || !flags || I % 64 != 0) { set_error("gemm_swiglu: bad argument"); return DFLASH_ERR_ARG; }
@@ -315,28 +295,6 @@ int dflash_gemm_swiglu(const void* Wgu, int I, int K, const void* X, int x_rows_
   p.args.sw.ld = ld;
   cudaError_t e = launch_gemm(p, static_cast<cudaStream_t>(stream), use_pdl != 0);
   if (e != cudaSuccess) return cuda_fail(e, "gemm_swiglu launch");
-  return DFLASH_OK;
-}
-
-int dflash_rms_norm_rows(const void* x, const float* tile_ss, int ss_ld, int hidden, const void* weight, void* out,
-                         int rows, float eps, void* stream) {
-  if (!x || !tile_ss || !weight || !out || hidden % 128 != 0 || hidden > 8192 || rows < 1) {
-    set_error("rms_norm_rows: bad argument");
-    return DFLASH_ERR_ARG;
-  }
-  NormArgs a;
-  memset(&a, 0, sizeof(a));
-  a.x = static_cast<const __nv_bfloat16*>(x);
-  a.tile_ss = tile_ss;
-  a.ss_ld = ss_ld;
-  a.H = hidden;
-  a.w = static_cast<const __nv_bfloat16*>(weight);
-  a.out = static_cast<__nv_bfloat16*>(out);
-  a.eps = eps;
-  a.SL = 1;
-  norm_rows_kernel<<<rows, kNormThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "rms_norm_rows launch");
   return DFLASH_OK;
 }
 

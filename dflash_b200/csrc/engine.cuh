@@ -28,8 +28,8 @@ struct Engine {
   int R, SL, RS, H, I, L, Hq, Hkv, V, nsel, bs, grid, nsplit_attn, nsplit_post;
   bool pdl;
   // plans
-  GemmPlan fc;                  // ctx_feat -> bf16 rows + per-tile sums of squares
-  std::vector<GemmPlan> qkv;    // a_in (ctx + block rows) -> q buffer, K/V cache
+  GemmPlan fc;                  // ctx_feat -> partials
+  std::vector<GemmPlan> qkv;    // a_in (ctx + block rows)
   // prompt pass (c = P rows at once): fc and the K/V rows of wqkv over the dedicated prompt buffers,
   // one plan per UMMA width so that short prompts do not pay for 256 columns
   GemmPlan fc_pf[5];            // mb = 16 << i
@@ -41,7 +41,6 @@ struct Engine {
   bool has_sample = false;
   int max_cand = 1;
   size_t flags_used = 0;        // bump allocator over DFLASH_BUF_FLAGS (one arrival counter per (group, tile) per plan)
-  int ss_ld_step = 0;           // row pitch of the per-tile sum-of-squares planes 0 (fc rows) and 1 (residual rows)
 
   template <class T>
   T* buf(int id) const { return reinterpret_cast<T*>(base + reg[id].off); }
@@ -50,7 +49,6 @@ struct Engine {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 constexpr int kPrefillRows = 256;  // prompt rows projected per pass (one full-width UMMA)
-constexpr int kMaxRowTiles = 64;   // hidden <= 8192: per-tile sum-of-squares planes have 64 tile rows
 
 // UMMA N (activation rows per MMA) for a GEMM over `rows` activation rows; more rows run as column groups.
 inline int round_mb(int rows) {
@@ -92,17 +90,23 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   const int grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
   const int nsa = default_attn_splits(c, sm_count);
   const int nsp = default_post_splits(c, sm_count);
-  // partial-accumulator exchange of the fused GEMMs: one [128 x mb] fp32 tile per CTA, the widest launch decides
-  long long part_elems = 0;
-  for (int rows : {RS, 2 * RS, kPrefillRows}) {
-    const long long e = static_cast<long long>(grid) * kTileN * round_mb(rows);  // groups * ranges <= grid CTAs
-    if (e > part_elems) part_elems = e;
+  const int qkv_cols = (Hq + 2 * Hkv) * 128;
+  // widest fp32 partial plane over the GEMMs whose consumers are separate kernels (fc, qkv, o, down + prompt pass)
+  long long ws_elems = 0;
+  struct G { int rows, N, K; } gs[] = {{RS, H, c.n_sel * H}, {2 * RS, qkv_cols, H}, {RS, H, Hq * 128}, {RS, H, I},
+                                       {kPrefillRows, H, c.n_sel * H}, {kPrefillRows, 2 * Hkv * 128, H}};
+  for (auto& g : gs) {
+    const int nt = (g.N + kTileN - 1) / kTileN, kb = g.K / kTileK;
+    const long long T = static_cast<long long>(nt) * kb;
+    const int ranges = ranges_for(grid, groups_of(g.rows));
+    const int gg = T < ranges ? static_cast<int>(T) : ranges;
+    const long long e = static_cast<long long>(max_slots_for(nt, kb, gg)) * rows_padded(g.rows) * g.N;
+    if (e > ws_elems) ws_elems = e;
   }
-  // arrival counters: one per (column group, tile) of every fused plan
-  const long long tiles_step = H / kTileN + static_cast<long long>(c.n_layers) *
-                                                ((Hq + 2 * Hkv) + 2 * (H / kTileN) + I / (kTileN / 2));
-  const long long tiles_pf = 5ll * (H / kTileN) + 5ll * c.n_layers * (2 * Hkv);
-  const long long n_flags = tiles_step * groups_of(2 * RS) + tiles_pf;
+  // gate/up GEMM (SwiGLU epilogue): one [128 x mb] fp32 partial tile per CTA (groups * ranges <= grid CTAs) and one
+  // arrival counter per (column group, tile) per layer
+  const long long part_elems = static_cast<long long>(grid) * kTileN * round_mb(RS);
+  const long long n_flags = static_cast<long long>(c.n_layers) * (I / (kTileN / 2)) * groups_of(RS);
   size_t sz[DFLASH_BUF_COUNT] = {0};
   sz[DFLASH_BUF_X] = static_cast<size_t>(RSp) * H * 2;
   sz[DFLASH_BUF_A_IN] = static_cast<size_t>(RS2p) * H * 2;
@@ -113,13 +117,10 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   sz[DFLASH_BUF_HMID] = static_cast<size_t>(RSp) * I * 2;
   sz[DFLASH_BUF_HN] = static_cast<size_t>(RSp) * H * 2;
   sz[DFLASH_BUF_KV] = static_cast<size_t>(c.n_layers) * 2 * R * Hkv * c.max_seq * 128 * 2;
-  sz[DFLASH_BUF_Y_CTX] = static_cast<size_t>(RSp) * H * 2;
-  sz[DFLASH_BUF_TILE_SS] = static_cast<size_t>(kMaxRowTiles) * (2 * RSp + kPrefillRows) * 4;
+  sz[DFLASH_BUF_WS] = static_cast<size_t>(ws_elems) * 4;
   sz[DFLASH_BUF_PART] = static_cast<size_t>(part_elems) * 4;
   sz[DFLASH_BUF_FLAGS] = static_cast<size_t>(n_flags) * 4;
   sz[DFLASH_BUF_COUNTERS] = static_cast<size_t>(R + 2) * 4;
-  sz[DFLASH_BUF_ROW_POS] = static_cast<size_t>(RS2p + kPrefillRows) * 4;
-  sz[DFLASH_BUF_ROPE] = static_cast<size_t>(RS2p + kPrefillRows) * 128 * 4;
   sz[DFLASH_BUF_ATTN_PO] = static_cast<size_t>(nsa) * RS * Hq * 128 * 4;
   sz[DFLASH_BUF_ATTN_ML] = static_cast<size_t>(nsa) * RS * Hq * 2 * 4;
   const int ncand = c.max_candidates > 1 ? 4 : 1;
@@ -143,7 +144,6 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   sz[DFLASH_BUF_DRAFT_LOGITS] = c.keep_draft_logits ? static_cast<size_t>(RSp) * c.vocab * 2 : 0;
   sz[DFLASH_BUF_PF_FEAT] = static_cast<size_t>(kPrefillRows) * c.n_sel * H * 2;
   sz[DFLASH_BUF_PF_A] = static_cast<size_t>(kPrefillRows) * H * 2;
-  sz[DFLASH_BUF_PF_Y] = static_cast<size_t>(kPrefillRows) * H * 2;
   size_t off = 0;
   for (int i = 0; i < DFLASH_BUF_COUNT; ++i) {
     reg[i].off = off;
@@ -205,44 +205,6 @@ inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-// rows of the position / rotary table: [0, 2 RS padded) = the step's activation rows, then the prompt-pass rows
-inline int rope_pf_row0(const Engine* e) { return rows_padded(2 * e->RS); }
-
-inline RopeTableArgs rope_table_args(Engine* e) {
-  RopeTableArgs t;
-  memset(&t, 0, sizeof(t));
-  t.R = e->R; t.SL = e->SL; t.S_max = e->cfg.max_seq;
-  t.start = e->buf<int>(DFLASH_BUF_START);
-  t.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-  t.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
-  t.inv_freq = e->w.inv_freq;
-  t.rope_scale = e->cfg.rope_scale;
-  t.row_pos = e->buf<int>(DFLASH_BUF_ROW_POS);
-  t.rope = e->buf<float>(DFLASH_BUF_ROPE);
-  return t;
-}
-
-inline QkvPostArgs qkv_post_args(Engine* e, int l, bool kv_only) {
-  QkvPostArgs a;
-  memset(&a, 0, sizeof(a));
-  a.R = e->R; a.SL = e->SL; a.Hq = e->Hq; a.Hkv = e->Hkv;
-  a.q_cols = kv_only ? 0 : e->Hq * 128;
-  const int t0 = kv_only ? rope_pf_row0(e) : 0;
-  a.row_pos = e->buf<int>(DFLASH_BUF_ROW_POS) + t0;
-  a.rope = e->buf<float>(DFLASH_BUF_ROPE) + static_cast<size_t>(t0) * 128;
-  a.q_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].q_norm);
-  a.k_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].k_norm);
-  const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(e->layers[l].bqkv);
-  a.bias = b == nullptr ? nullptr : (kv_only ? b + e->Hq * 128 : b);
-  a.eps = e->cfg.rms_eps;
-  a.q_out = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
-  const size_t per = static_cast<size_t>(e->R) * e->Hkv * e->cfg.max_seq * 128;
-  a.k_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 0) * per;
-  a.v_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 1) * per;
-  a.S_max = e->cfg.max_seq;
-  return a;
-}
-
 inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, void* workspace,
                          size_t workspace_bytes, int sm_count, Engine** out) {
   int rc = check_config(c);
@@ -278,13 +240,15 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   const int RSp = rows_padded(RS), RS2p = rows_padded(2 * RS);
   const int qkv_cols = (e->Hq + 2 * e->Hkv) * 128;
   const int mb_blk = round_mb(RS), mb_all = round_mb(2 * RS);
-  e->ss_ld_step = RSp;
-  float* ss_fc = e->buf<float>(DFLASH_BUF_TILE_SS);
-  float* ss_x = ss_fc + static_cast<size_t>(kMaxRowTiles) * RSp;
-  float* ss_pf = ss_x + static_cast<size_t>(kMaxRowTiles) * RSp;
-  __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
-  // every fused plan gets the shared partial-exchange region and its own arrival counters
-  auto finish = [&](GemmPlan& p) -> int {
+  float* ws = e->buf<float>(DFLASH_BUF_WS);
+  // GEMMs whose consumer is a separate kernel: fp32 partial planes in `ws`
+  auto finish = [&](GemmPlan& p) {
+    p.args.ws = ws;
+    p.args.ws_rows = p.groups * p.mb;
+    p.args.ws_ld = p.args.N;
+  };
+  // gate/up GEMM with the SwiGLU epilogue: the shared partial-exchange region and its own arrival counters
+  auto finish_fused = [&](GemmPlan& p) -> int {
     p.args.part = e->buf<float>(DFLASH_BUF_PART);
     const size_t need = static_cast<size_t>(p.groups) * p.grid * kTileN * p.mb * 4;
     const size_t nflags = static_cast<size_t>(p.groups) * p.args.n_tiles;
@@ -296,58 +260,44 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     e->flags_used += nflags;
     return 0;
   };
-  auto rows_epi = [&](GemmPlan& p, const void* bias, __nv_bfloat16* resid, __nv_bfloat16* out, float* ss, int ss_ld) {
-    p.args.rows.bias = static_cast<const __nv_bfloat16*>(bias);
-    p.args.rows.resid = resid;
-    p.args.rows.out = out;
-    p.args.rows.ld = H;
-    p.args.rows.tile_ss = ss;
-    p.args.rows.ss_ld = ss_ld;
-  };
 #define DFL_PLAN(call)        \
   do {                        \
     int _rc = (call);         \
     if (_rc) { delete e; return DFLASH_ERR_ARG; } \
   } while (0)
   // activation TMA tensors are declared with the buffers' padded row counts (a multiple of the UMMA width), so a box
-  // never leaves the allocation; rows past the live ones are zero and their outputs are never written.
+  // never leaves the allocation; rows past the live ones are zero and their outputs are never used.
   DFL_PLAN(make_gemm_plan(&e->fc, w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_CTX_FEAT), RSp, 0, mb_blk, RS,
-                          kModeRows, e->grid));
-  DFL_PLAN(finish(e->fc));
-  rows_epi(e->fc, nullptr, nullptr, e->buf<__nv_bfloat16>(DFLASH_BUF_Y_CTX), ss_fc, RSp);
+                          kModePartials, e->grid));
+  finish(e->fc);
   e->qkv.resize(e->L); e->kv_pf.resize(e->L * 5); e->o.resize(e->L); e->gu.resize(e->L); e->d.resize(e->L);
   for (int i = 0; i < 5; ++i) {
     DFL_PLAN(make_gemm_plan(&e->fc_pf[i], w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_PF_FEAT), kPrefillRows, 0,
-                            16 << i, 16 << i, kModeRows, e->grid));
-    DFL_PLAN(finish(e->fc_pf[i]));
-    rows_epi(e->fc_pf[i], nullptr, nullptr, e->buf<__nv_bfloat16>(DFLASH_BUF_PF_Y), ss_pf, kPrefillRows);
+                            16 << i, 16 << i, kModePartials, e->grid));
+    finish(e->fc_pf[i]);
   }
   for (int l = 0; l < e->L; ++l) {
     const dflash_layer_weights_t& lw = e->layers[l];
     DFL_PLAN(make_gemm_plan(&e->qkv[l], lw.wqkv, qkv_cols, 0, qkv_cols, H, e->buf<void>(DFLASH_BUF_A_IN), RS2p, 0,
-                            mb_all, 2 * RS, kModeQkv, e->grid));
-    DFL_PLAN(finish(e->qkv[l]));
-    e->qkv[l].args.qkv = qkv_post_args(e, l, false);
+                            mb_all, 2 * RS, kModePartials, e->grid));
+    finish(e->qkv[l]);
     for (int i = 0; i < 5; ++i) {
       GemmPlan& kp = e->kv_pf[l * 5 + i];
       DFL_PLAN(make_gemm_plan(&kp, lw.wqkv, qkv_cols, e->Hq * 128, 2 * e->Hkv * 128, H, e->buf<void>(DFLASH_BUF_PF_A),
-                              kPrefillRows, 0, 16 << i, 16 << i, kModeQkv, e->grid));
-      DFL_PLAN(finish(kp));
-      kp.args.qkv = qkv_post_args(e, l, true);
+                              kPrefillRows, 0, 16 << i, 16 << i, kModePartials, e->grid));
+      finish(kp);
     }
     DFL_PLAN(make_gemm_plan(&e->o[l], lw.wo, H, 0, H, e->Hq * 128, e->buf<void>(DFLASH_BUF_ATTN_OUT), RSp, 0, mb_blk, RS,
-                            kModeRows, e->grid));
-    DFL_PLAN(finish(e->o[l]));
-    rows_epi(e->o[l], lw.bo, x, x, ss_x, RSp);
+                            kModePartials, e->grid));
+    finish(e->o[l]);
     DFL_PLAN(make_gemm_plan(&e->gu[l], lw.wgu, 2 * I, 0, 2 * I, H, e->buf<void>(DFLASH_BUF_A2), RSp, 0, mb_blk, RS,
                             kModeSwiglu, e->grid));
-    DFL_PLAN(finish(e->gu[l]));
+    DFL_PLAN(finish_fused(e->gu[l]));
     e->gu[l].args.sw.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HMID);
     e->gu[l].args.sw.ld = I;
     DFL_PLAN(make_gemm_plan(&e->d[l], lw.wd, H, 0, H, I, e->buf<void>(DFLASH_BUF_HMID), RSp, 0, mb_blk, RS,
-                            kModeRows, e->grid));
-    DFL_PLAN(finish(e->d[l]));
-    rows_epi(e->d[l], nullptr, x, x, ss_x, RSp);
+                            kModePartials, e->grid));
+    finish(e->d[l]);
   }
   unsigned int* counters = e->buf<unsigned int>(DFLASH_BUF_COUNTERS);
   auto tok_fields = [&](GemmPlan& p) {
@@ -382,12 +332,18 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
 #undef DFL_PLAN
   cudaError_t ce = cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
+  ce = cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
+  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize smem attribute"); }
+  ce = cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
+  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize2 smem attribute"); }
   // One shared-memory carveout for every kernel of the step: consecutive kernels with different L1/smem splits
   // cannot share an SM, which would serialise exactly the PDL overlaps the schedule relies on.
   {
     const int mx = cudaSharedmemCarveoutMaxShared;
-    cudaFuncSetAttribute(norm_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(rows_pre_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(finalize_rows_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(verify_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
@@ -400,62 +356,124 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   return DFLASH_OK;
 }
 
+template <class Kern, class Args>
+inline cudaError_t launch_cluster_pdl(Kern kern, dim3 grid, dim3 block, dim3 cluster, size_t smem, cudaStream_t st,
+                                      bool pdl, const Args& args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster.x;
+  at[0].val.clusterDim.y = cluster.y;
+  at[0].val.clusterDim.z = cluster.z;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
 // ------------------------------------------------------------------------------------------------
-inline NormArgs norm_args(const Engine* e, const __nv_bfloat16* x, const float* ss, int ss_ld, const void* w,
-                          __nv_bfloat16* out) {
-  NormArgs a;
+inline RowsArgs rows_args_base(const Engine* e) {
+  RowsArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x;
-  a.tile_ss = ss;
-  a.ss_ld = ss_ld;
   a.H = e->H;
-  a.w = static_cast<const __nv_bfloat16*>(w);
-  a.out = out;
-  a.eps = e->cfg.rms_eps;
   a.SL = e->SL;
+  a.bs = e->bs;
+  a.eps = e->cfg.rms_eps;
+  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  a.valid_mode = kRowsAll;
+  return a;
+}
+
+// Per-layer row pass (partials + residual + RMSNorm): four CTAs per row when the width allows it
+inline cudaError_t launch_finalize(Engine* e, const RowsArgs& a, int rows, cudaStream_t st) {
+  const bool ok = a.ws != nullptr && a.embed == nullptr && a.norm_w != nullptr &&
+                  e->H % (4 * kRowCtas) == 0 && e->H / kRowCtas <= kRowClThreads * 4 * kRowClGroups;
+  if (ok)
+    return launch_cluster_pdl(finalize_rows_cluster_kernel, dim3(kRowCtas, rows), dim3(kRowClThreads),
+                              dim3(kRowCtas, 1, 1), 0, st, e->pdl, a);
+  return launch_pdl(finalize_rows_kernel, dim3(rows), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a);
+}
+
+// fc GEMM + hidden_norm over the pending context rows -> a_in rows [0, RS)   (dflash.py:177)
+inline RowsArgs ctx_finalize_args(Engine* e) {
+  RowsArgs a = rows_args_base(e);
+  a.ws = e->fc.args.ws;
+  a.sm = slot_map_of(e->fc);
+  a.valid_mode = kRowsCtx;
+  a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
+  a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
+  return a;
+}
+
+inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_only) {
+  QkvPostArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ws = p.args.ws;
+  a.sm = slot_map_of(p);
+  a.R = e->R; a.SL = e->SL; a.bs = e->bs; a.Hq = e->Hq; a.Hkv = e->Hkv;
+  a.q_cols = kv_only ? 0 : e->Hq * 128;
+  a.row0 = 0;
+  a.rows = kv_only ? e->RS : 2 * e->RS;
+  a.start = e->buf<int>(DFLASH_BUF_START);
+  a.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+  a.blk_len = e->buf<int>(DFLASH_BUF_BLK_LEN);
+  a.q_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].q_norm);
+  a.k_norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].k_norm);
+  {
+    const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(e->layers[l].bqkv);
+    a.bias = b == nullptr ? nullptr : (kv_only ? b + e->Hq * 128 : b);
+  }
+  a.inv_freq = e->w.inv_freq;
+  a.rope_scale = e->cfg.rope_scale;
+  a.eps = e->cfg.rms_eps;
+  a.q_out = e->buf<__nv_bfloat16>(DFLASH_BUF_Q);
+  const size_t per = static_cast<size_t>(e->R) * e->Hkv * e->cfg.max_seq * 128;
+  a.k_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 0) * per;
+  a.v_cache = e->buf<__nv_bfloat16>(DFLASH_BUF_KV) + (static_cast<size_t>(l) * 2 + 1) * per;
+  a.S_max = e->cfg.max_seq;
   return a;
 }
 
 // One draft step: ctx injection -> block embedding -> L layers -> final norm -> lm_head + argmax.
-// Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247). 2 + 8 L + 1 launches:
-//   fc GEMM [bf16 rows + sums of squares]            rows_pre [hidden_norm of the ctx rows | embed + ln1 of the block]
-//   per layer: qkv GEMM [q/k norm, RoPE, cache write] - attention split - merge - o GEMM [+ residual] - norm -
-//              gate/up GEMM [SwiGLU] - down GEMM [+ residual] - norm
-//   lm_head GEMM [argmax, drafted tokens]
+// Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247). 2 + 9 L + 1 launches:
+//   fc GEMM           row kernel [hidden_norm of the ctx rows | embed + ln1 of the block]
+//   per layer: qkv GEMM - qkv_post [q/k norm, RoPE, cache write] - attention split - merge - o GEMM -
+//              row kernel [+ residual, ln2] - gate/up GEMM [SwiGLU epilogue] - down GEMM - row kernel [+ residual, norm]
+//   lm_head GEMM [argmax; its last CTA reduces the candidates to the drafted tokens]
 // n_candidates > 1: top-4 lm_head epilogue + candidate blocks (fixed_prefix_rank) instead of the plain argmax tail
 inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st,
                               int n_candidates = 1, int fixed_prefix_len = 0, float draft_temperature = 0.f,
                               unsigned long long draft_seed = 0) {
-  const int RS = e->RS, RSp = e->ss_ld_step;
+  const int RS = e->RS;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  const float* ss_fc = e->buf<float>(DFLASH_BUF_TILE_SS);
-  const float* ss_x = ss_fc + static_cast<size_t>(kMaxRowTiles) * RSp;
   // ctx injection GEMM first (it only reads the features gathered by the previous verify step), then ONE row kernel
-  // for both the context rows (hidden_norm -> a_in ctx rows) and the block rows
+  // for both the context finalize (fc -> hidden_norm -> a_in ctx rows) and the block rows
   // (embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows)
   DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
   {
-    NormArgs c = norm_args(e, e->buf<__nv_bfloat16>(DFLASH_BUF_Y_CTX), ss_fc, RSp, e->w.hidden_norm, a_in);
-    c.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
-    EmbedArgs b;
-    memset(&b, 0, sizeof(b));
+    RowsArgs a = rows_args_base(e);
     if (noise_embedding != nullptr) {
-      b.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
-      b.ids = nullptr;
+      a.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
+      a.ids = nullptr;
     } else {
-      b.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
-      b.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+      a.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
+      a.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
     }
-    b.ids_ld = e->bs;
-    b.pad_token = e->cfg.mask_token_id;
-    b.bs = e->bs; b.H = e->H; b.SL = e->SL;
-    b.resid = x;
-    b.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
-    b.out = a_in + static_cast<size_t>(RS) * e->H;
-    b.eps = e->cfg.rms_eps;
-    DFL_CUDA(launch_pdl(rows_pre_kernel, dim3(2 * RS), dim3(kNormThreads), 0, st, e->pdl, c, b, rope_table_args(e), RS),
-             "ctx norm + embed + ln1 + rope table");
+    a.ids_ld = e->bs;
+    a.pad_token = e->cfg.mask_token_id;
+    a.resid = x;
+    a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
+    a.out = a_in + static_cast<size_t>(RS) * e->H;
+    const RowsArgs c = ctx_finalize_args(e);
+    DFL_CUDA(launch_pdl(finalize_rows2_kernel, dim3(2 * RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st,
+                        e->pdl, c, a, RS), "ctx finalize + embed + ln1");
   }
   AttnArgs aa;
   memset(&aa, 0, sizeof(aa));
@@ -472,23 +490,43 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   const int group = e->Hq / e->Hkv;
   for (int l = 0; l < e->L; ++l) {
     DFL_CUDA(launch_gemm(e->qkv[l], st, e->pdl), "qkv gemm");
-    aa.k_cache = e->qkv[l].args.qkv.k_cache;
-    aa.v_cache = e->qkv[l].args.qkv.v_cache;
+    QkvPostArgs qa = qkv_post_args(e, l, e->qkv[l], false);
+    const int items = qa.rows * (e->Hq + 2 * e->Hkv);
+    aa.k_cache = qa.k_cache;
+    aa.v_cache = qa.v_cache;
+    DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st,
+                        e->pdl, qa), "qkv post");
     DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
                         kAttnSmem, st, e->pdl, aa), "attention");
     DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0,
                         st, e->pdl, aa), "attention combine");
     DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
-    DFL_CUDA(launch_pdl(norm_rows_kernel, dim3(RS), dim3(kNormThreads), 0, st, e->pdl,
-                        norm_args(e, x, ss_x, RSp, e->layers[l].ln2, e->buf<__nv_bfloat16>(DFLASH_BUF_A2))),
-             "post-attention norm");
-    DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm");
+    {
+      RowsArgs a = rows_args_base(e);
+      a.ws = e->o[l].args.ws;
+      a.sm = slot_map_of(e->o[l]);
+      a.bias = static_cast<const __nv_bfloat16*>(e->layers[l].bo);
+      a.resid = x;
+      a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l].ln2);
+      a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A2);
+      DFL_CUDA(launch_finalize(e, a, RS, st), "o finalize");
+    }
+    DFL_CUDA(launch_gemm(e->gu[l], st, e->pdl), "gate/up gemm + swiglu");
     DFL_CUDA(launch_gemm(e->d[l], st, e->pdl), "down gemm");
-    const bool last = l + 1 == e->L;
-    DFL_CUDA(launch_pdl(norm_rows_kernel, dim3(RS), dim3(kNormThreads), 0, st, e->pdl,
-                        norm_args(e, x, ss_x, RSp, last ? e->w.final_norm : e->layers[l + 1].ln1,
-                                  last ? e->buf<__nv_bfloat16>(DFLASH_BUF_HN) : a_in + static_cast<size_t>(RS) * e->H)),
-             "layer-output norm");
+    {
+      RowsArgs a = rows_args_base(e);
+      a.ws = e->d[l].args.ws;
+      a.sm = slot_map_of(e->d[l]);
+      a.resid = x;
+      if (l + 1 < e->L) {
+        a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[l + 1].ln1);
+        a.out = a_in + static_cast<size_t>(RS) * e->H;
+      } else {
+        a.norm_w = static_cast<const __nv_bfloat16*>(e->w.final_norm);
+        a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_HN);
+      }
+      DFL_CUDA(launch_finalize(e, a, RS, st), "down finalize");
+    }
   }
   if (!run_lm_head) return DFLASH_OK;
   if (n_candidates > 1) {
@@ -624,7 +662,6 @@ inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int n_ro
     set_error("prefill: bad request %d, rows %d or position %d (max_seq %d)", r, n_rows, pos0, e->cfg.max_seq);
     return DFLASH_ERR_ARG;
   }
-  const float* ss_pf = e->buf<float>(DFLASH_BUF_TILE_SS) + 2 * static_cast<size_t>(kMaxRowTiles) * e->ss_ld_step;
   for (int c0 = 0; c0 < n_rows; c0 += kPrefillRows) {
     const int n = n_rows - c0 < kPrefillRows ? n_rows - c0 : kPrefillRows;
     int pi = 0;
@@ -641,24 +678,25 @@ inline int enqueue_prefill(Engine* e, int r, const void* const* hidden, int n_ro
     GemmPlan fc = e->fc_pf[pi];
     fc.args.m_valid = n;
     DFL_CUDA(launch_gemm(fc, st, e->pdl), "prefill fc gemm");
-    DFL_CUDA(launch_pdl(norm_rows_kernel, dim3(n), dim3(kNormThreads), 0, st, e->pdl,
-                        norm_args(e, e->buf<__nv_bfloat16>(DFLASH_BUF_PF_Y), ss_pf, kPrefillRows, e->w.hidden_norm,
-                                  e->buf<__nv_bfloat16>(DFLASH_BUF_PF_A))),
-             "prefill hidden_norm");
-    {
-      RopeTableArgs t = rope_table_args(e);
-      t.row_pos += rope_pf_row0(e);
-      t.rope += static_cast<size_t>(rope_pf_row0(e)) * 128;
-      t.pf_rows = n;
-      t.pf_pos0 = pos0 + c0;
-      DFL_CUDA(launch_pdl(rope_table_kernel, dim3(n), dim3(64), 0, st, e->pdl, t), "prefill rope table");
-    }
+    RowsArgs a = rows_args_base(e);
+    a.ws = fc.args.ws;
+    a.sm = slot_map_of(fc);
+    a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
+    a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_PF_A);
+    DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(n), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a),
+             "prefill fc finalize");
     for (int l = 0; l < e->L; ++l) {
       GemmPlan kp = e->kv_pf[l * 5 + pi];
       kp.args.m_valid = n;
-      kp.args.qkv.pf_rows = n;
-      kp.args.qkv.pf_req = r;
       DFL_CUDA(launch_gemm(kp, st, e->pdl), "prefill kv gemm");
+      QkvPostArgs qa = qkv_post_args(e, l, kp, true);
+      qa.rows = n;
+      qa.pf_rows = n;
+      qa.pf_req = r;
+      qa.pf_pos0 = pos0 + c0;
+      const int items = n * (2 * e->Hkv);
+      DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st,
+                          e->pdl, qa), "prefill kv post");
     }
   }
   SetStateArgs sa;

@@ -1,8 +1,11 @@
-// The small kernels left between the streaming GEMMs. Everything that works on a finished output tile now runs in
-// the GEMM's own epilogue (epilogues.cuh); what remains needs a whole activation row: the RMSNorm scale
-// (Qwen3RMSNorm: fp32 inside, -> bf16, * weight) over the bf16 rows and per-tile sums of squares the GEMM left, and
-// the block embedding. Latency-bound (<= 0.3 MB each): 128-bit accesses, one L2 round trip, no block-wide barrier
-// in the norm pass.
+// Small fused kernels around the skinny GEMMs: they consume the fp32 split-K partials of fc / qkv / o / down, apply
+// the reference's bf16 rounding points (Linear output (+ bias) -> bf16, RMSNorm in fp32 -> bf16 -> * weight,
+// residual add in bf16, RoPE in bf16) and produce the next GEMM's activations. (SwiGLU runs in the gate/up GEMM's
+// own epilogue, epilogues.cuh; the drafted tokens are reduced by the lm_head GEMM's last CTA.)
+//
+// All of them are latency-bound (a few hundred KB each): 128-bit accesses, rolled loops (small code:
+// the first version unrolled 32x with 64-bit divisions inline and spent ~45 us in instruction fetch),
+// slot counts per 128-column tile computed once with 32-bit arithmetic.
 #pragma once
 #include "gemm_host.cuh"
 
@@ -119,132 +122,406 @@ inline cudaError_t launch_reduce_candidates(const float* cand_val, const int* ca
 }
 
 // =============================================================================================
-// RMSNorm pass over rows whose bf16 values and per-tile sums of squares were written by a kModeRows GEMM:
-//   out = w * bf16(x * rsqrt(mean(x^2) + eps))            (Qwen3RMSNorm, model/dflash.py:115,141,177,189)
-// One CTA per row, 16 bytes per thread per iteration; every warp adds the (<= 64) per-tile sums itself in a fixed
-// order, so the pass is one L2 round trip with no block barrier.
-struct NormArgs {
-  const __nv_bfloat16* x;   // [rows][H]
-  const float* tile_ss;     // [H / 128][ss_ld]
-  int ss_ld;
+// Row layout shared by all step kernels. R requests, SL row slots per request (bs <= SL).
+//   activation matrix a_in [2*R*SL, H]: rows [0, R*SL) = context rows (request r, slot j valid iff
+//   j < ctx_len[r]); rows [R*SL, 2*R*SL) = block rows (request r, slot i valid iff i < bs).
+// Absolute positions: context row j -> start[r] - ctx_len[r] + j ; block row i -> start[r] + i
+// (model/dflash.py:241: position_ids[:, cache_len : start + block_size]).
+// =============================================================================================
+
+enum RowValid : int { kRowsAll = 0, kRowsCtx = 1 };
+
+struct RowsArgs {
+  // source A: split-K partials of the producing GEMM (row m of ws = row m here)
+  const float* ws;
+  SlotMap sm;
+  const __nv_bfloat16* bias;  // optional Linear bias [H] added to the fp32 sum (config.attention_bias: o_proj)
+  // source B (if embed != null): embedding gather, token = ids[(row / SL) * ids_ld + row % SL]
+  const __nv_bfloat16* embed;
+  const long long* ids;
+  int ids_ld;
+  long long pad_token;  // used for slots >= bs
+  int bs;
   int H;
-  const __nv_bfloat16* w;   // [H]
-  __nv_bfloat16* out;       // [rows][H]
-  float eps;
-  const int* ctx_len;       // optional: row (r, j) = (row / SL, row % SL) is live iff j < ctx_len[r]
   int SL;
+  int valid_mode;
+  const int* ctx_len;
+  __nv_bfloat16* resid;   // optional residual stream [rows, H] (in/out), or written (embed mode)
+  const __nv_bfloat16* norm_w;  // optional RMSNorm weight [H]
+  __nv_bfloat16* out;     // [rows, H]
+  float eps;
 };
 
-constexpr int kNormThreads = 512;
+#ifndef DFLASH_ROWS_THREADS
+#define DFLASH_ROWS_THREADS 512
+#endif
+constexpr int kRowsThreads = DFLASH_ROWS_THREADS;
+constexpr int kRowsMaxTiles = 64;  // H <= 8192
 
-__device__ __forceinline__ void norm_row_body(const NormArgs& a, int row, int tid) {
-  const int lane = tid & 31;
-  const int n0 = tid * 8;
-  // the norm weights do not depend on the producing GEMM: requested before griddepcontrol.wait
-  uint4 wv = make_uint4(0, 0, 0, 0);
-  if (n0 < a.H) wv = *reinterpret_cast<const uint4*>(a.w + n0);
-  DFL_WAIT_THEN_TRIGGER();
-  if (a.ctx_len != nullptr && (row % a.SL) >= a.ctx_len[row / a.SL]) return;
+// One CTA per row:  v = bf16(sum of partials)           (nn.Linear output dtype)
+//                   v = bf16(resid + v); resid = v       (residual add, model/dflash.py:140,144)
+//                   out = w * bf16(v * rsqrt(mean(v^2) + eps))   (Qwen3RMSNorm, fp32 inside)
+// rowbuf: 6*H bytes of shared memory (the row as H floats + H bf16 norm weights); red: NT/32 floats; ns_tab:
+// kRowsMaxTiles ints. NT threads (tid in [0, NT)) work on one row and meet at named barrier bar_id.
+// NS_READY: the caller has already filled ns_tab (and synchronised) -- the stand-alone kernel does that before
+// griddepcontrol.wait, since the slot counts do not depend on the producing GEMM's data.
+template <int NT, bool NS_READY = false>
+__device__ __forceinline__ void finalize_row_body(const RowsArgs& a, int row, int tid, float* rowbuf, float* red,
+                                                  int* ns_tab, int bar_id) {
+  if (a.valid_mode == kRowsCtx) {
+    const int r = row / a.SL, j = row % a.SL;
+    if (j >= a.ctx_len[r]) return;
+  }
   const long long roff = static_cast<long long>(row) * a.H;
-  uint4 xv = make_uint4(0, 0, 0, 0);
-  if (n0 < a.H) xv = __ldcg(reinterpret_cast<const uint4*>(a.x + roff + n0));
-  const int nt = a.H / 128;
-  float s = 0.f;
-  for (int t = lane; t < nt; t += 32) s += __ldcg(a.tile_ss + static_cast<long long>(t) * a.ss_ld + row);
-  const float tot = warp_sum(s);
-  const float rstd = 1.0f / sqrtf(tot / static_cast<float>(a.H) + a.eps);
-  for (int n = n0; n < a.H; n += kNormThreads * 8) {
-    if (n != n0) {
-      wv = *reinterpret_cast<const uint4*>(a.w + n);
-      xv = __ldcg(reinterpret_cast<const uint4*>(a.x + roff + n));
+  __nv_bfloat16* wbuf = reinterpret_cast<__nv_bfloat16*>(rowbuf + a.H);  // H bf16 norm weights behind the H floats
+  const bool from_embed = a.embed != nullptr;
+  long long tok = 0;
+  if (from_embed) {
+    const int r = row / a.SL, i = row % a.SL;
+    if (a.ids == nullptr) tok = row;  // `embed` already is a [rows, H] embedding matrix (forward(noise_embedding=))
+    else tok = (i < a.bs) ? a.ids[static_cast<long long>(r) * a.ids_ld + i] : a.pad_token;
+  } else if (!NS_READY) {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = tid; t < nt; t += NT) ns_tab[t] = tile_slots32(t, a.sm);
+    group_sync(bar_id, NT);
+  }
+  float ss = 0.f;
+  constexpr int U = 4;  // iterations whose loads are issued together (latency-bound: ~1 us per L2 round trip)
+  for (int n0 = tid * 4; n0 < a.H; n0 += NT * 4 * U) {
+    float4 x[U];
+    uint2 rs[U], wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int n = n0 + u * NT * 4;
+      if (n < a.H) {
+        if (a.norm_w != nullptr) wv[u] = *reinterpret_cast<const uint2*>(a.norm_w + n);  // for pass 2, fetched now
+        if (from_embed) {
+          rs[u] = *reinterpret_cast<const uint2*>(a.embed + tok * a.H + n);
+        } else {
+          x[u] = sum_slots_4(a.ws, a.sm, row, n, ns_tab[n / kTileN]);
+          if (a.bias != nullptr) {
+            const float4 b = unpack4_bf16(*reinterpret_cast<const uint2*>(a.bias + n));
+            x[u].x += b.x; x[u].y += b.y; x[u].z += b.z; x[u].w += b.w;
+          }
+          if (a.resid != nullptr) rs[u] = __ldcg(reinterpret_cast<const uint2*>(a.resid + roff + n));
+        }
+      }
     }
-    const float4 x0 = unpack4_bf16(make_uint2(xv.x, xv.y)), x1 = unpack4_bf16(make_uint2(xv.z, xv.w));
-    const float4 w0 = unpack4_bf16(make_uint2(wv.x, wv.y)), w1 = unpack4_bf16(make_uint2(wv.z, wv.w));
-    const uint2 o0 = pack4_bf16(w0.x * bf16_round(x0.x * rstd), w0.y * bf16_round(x0.y * rstd),
-                                w0.z * bf16_round(x0.z * rstd), w0.w * bf16_round(x0.w * rstd));
-    const uint2 o1 = pack4_bf16(w1.x * bf16_round(x1.x * rstd), w1.y * bf16_round(x1.y * rstd),
-                                w1.z * bf16_round(x1.z * rstd), w1.w * bf16_round(x1.w * rstd));
-    *reinterpret_cast<uint4*>(a.out + roff + n) = make_uint4(o0.x, o0.y, o1.x, o1.y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int n = n0 + u * NT * 4;
+      if (n >= a.H) continue;
+      float4 v;
+      if (from_embed) {
+        v = unpack4_bf16(rs[u]);
+        if (a.resid != nullptr) *reinterpret_cast<uint2*>(a.resid + roff + n) = rs[u];
+      } else {
+        v = x[u];
+        v.x = bf16_round(v.x); v.y = bf16_round(v.y); v.z = bf16_round(v.z); v.w = bf16_round(v.w);
+        if (a.resid != nullptr) {
+          const float4 rsd = unpack4_bf16(rs[u]);
+          v.x = bf16_round(rsd.x + v.x); v.y = bf16_round(rsd.y + v.y);
+          v.z = bf16_round(rsd.z + v.z); v.w = bf16_round(rsd.w + v.w);
+          *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(v.x, v.y, v.z, v.w);
+        }
+      }
+      if (a.norm_w == nullptr) {
+        *reinterpret_cast<uint2*>(a.out + roff + n) = pack4_bf16(v.x, v.y, v.z, v.w);
+      } else {
+        *reinterpret_cast<float4*>(rowbuf + n) = v;
+        *reinterpret_cast<uint2*>(wbuf + n) = wv[u];
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    }
+  }
+  if (a.norm_w == nullptr) return;
+  DFL_TRACE(4);
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  group_sync(bar_id, NT);
+  DFL_TRACE(5);
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) tot += red[w];
+  const float rstd = 1.0f / sqrtf(tot / static_cast<float>(a.H) + a.eps);
+  for (int n = tid * 4; n < a.H; n += NT * 4) {
+    const float4 x = *reinterpret_cast<const float4*>(rowbuf + n);
+    const float4 w = unpack4_bf16(*reinterpret_cast<const uint2*>(wbuf + n));
+    *reinterpret_cast<uint2*>(a.out + roff + n) =
+        pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
+                   w.w * bf16_round(x.w * rstd));
   }
 }
 
-__global__ void __launch_bounds__(kNormThreads) norm_rows_kernel(const NormArgs a) {
-  norm_row_body(a, blockIdx.x, threadIdx.x);
+__global__ void __launch_bounds__(kRowsThreads) finalize_rows_kernel(const RowsArgs a) {
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float red[kRowsThreads / 32];
+  __shared__ int ns_tab[kRowsMaxTiles];
+  // everything that does not depend on the producing GEMM happens while this kernel waits for it
+  if (a.embed == nullptr) {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
+  }
+  __syncthreads();
+  // wait first, trigger second: the GEMM behind this kernel then becomes resident exactly when this
+  // kernel starts its real work
+  DFL_WAIT_THEN_TRIGGER();
+  finalize_row_body<kRowsThreads, true>(a, blockIdx.x, threadIdx.x, rowbuf, red, ns_tab, 0);
   DFL_TRACE(2);
 }
 
-// =============================================================================================
-// Block rows: embedding gather -> residual stream, then the first input_layernorm
-//   x = embed_tokens(block_ids)  (model/dflash.py:237), out = ln1_0(x)  (:115)
-struct EmbedArgs {
-  const __nv_bfloat16* embed;  // [vocab][H], or (ids == null) a [rows][H] matrix of already-embedded rows
-  const long long* ids;        // [R][ids_ld]
-  int ids_ld;
-  long long pad_token;         // used for slots >= bs
-  int bs, H, SL;
-  __nv_bfloat16* resid;        // [rows][H] residual stream (written)
-  const __nv_bfloat16* norm_w; // [H]
-  __nv_bfloat16* out;          // [rows][H]
-  float eps;
-};
+// The same row pass with kRowCtas CTAs per row (one thread-block cluster): a lone CTA has to pull ~110 KB of partials
+// through one SM's load path (3-4 us in the step timeline, scripts/step_trace.py); four SMs share it here. Each CTA
+// owns a quarter of the columns, keeps its values in registers, and the row's sum of squares is exchanged through
+// distributed shared memory (every CTA pushes its partial sum into all peers, one cluster barrier, fixed summation
+// order). Partials + optional residual + RMSNorm only (what the per-layer launches need).
+#ifndef DFLASH_ROW_CTAS
+#define DFLASH_ROW_CTAS 4
+#endif
+constexpr int kRowCtas = DFLASH_ROW_CTAS;
+constexpr int kRowClThreads = 256;
+constexpr int kRowClGroups = 2;  // float4 groups per thread: H / kRowCtas <= 256 * 4 * 2 (H <= 8192)
 
-// One CTA (kNormThreads threads) per row; the row's sum of squares needs one block reduction here.
-__device__ __forceinline__ void embed_row_body(const EmbedArgs& a, int row, int tid, float* red) {
-  const int n0 = tid * 8;
-  uint4 wv = make_uint4(0, 0, 0, 0);
-  if (n0 < a.H) wv = *reinterpret_cast<const uint4*>(a.norm_w + n0);
+__global__ void __launch_bounds__(kRowClThreads) finalize_rows_cluster_kernel(const RowsArgs a) {
+  __shared__ int ns_tab[kRowsMaxTiles];
+  __shared__ float red[kRowClThreads / 32];
+  __shared__ float peer_ss[kRowCtas];
+  const int rank = static_cast<int>(cluster_cta_rank());
+  const int row = blockIdx.y, tid = threadIdx.x;
+  const int cols = a.H / kRowCtas, c0 = rank * cols;
+  {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = tid; t < nt; t += kRowClThreads) ns_tab[t] = tile_slots32(t, a.sm);
+  }
+  __syncthreads();
   DFL_WAIT_THEN_TRIGGER();
-  const int r = row / a.SL, i = row % a.SL;
-  long long tok;
-  if (a.ids == nullptr) tok = row;  // forward(noise_embedding=...): the rows are given
-  else tok = (i < a.bs) ? a.ids[static_cast<long long>(r) * a.ids_ld + i] : a.pad_token;
+  if (a.valid_mode == kRowsCtx) {  // the whole cluster takes the same branch (no barrier is left half-entered)
+    const int r = row / a.SL, j = row % a.SL;
+    if (j >= a.ctx_len[r]) return;
+  }
   const long long roff = static_cast<long long>(row) * a.H;
-  // H <= 8192: at most two 16-byte groups per thread, kept in registers across the reduction
-  uint4 xv[2];
-  float ss = 0.f;
+  float4 v[kRowClGroups];
+  uint2 rs[kRowClGroups], wv[kRowClGroups];
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int n = n0 + g * kNormThreads * 8;
-    xv[g] = make_uint4(0, 0, 0, 0);
-    if (n < a.H) {
-      xv[g] = *reinterpret_cast<const uint4*>(a.embed + tok * a.H + n);
-      *reinterpret_cast<uint4*>(a.resid + roff + n) = xv[g];
-      const float4 x0 = unpack4_bf16(make_uint2(xv[g].x, xv[g].y)), x1 = unpack4_bf16(make_uint2(xv[g].z, xv[g].w));
-      ss += x0.x * x0.x + x0.y * x0.y + x0.z * x0.z + x0.w * x0.w + x1.x * x1.x + x1.y * x1.y + x1.z * x1.z + x1.w * x1.w;
+  for (int g = 0; g < kRowClGroups; ++g) {
+    const int n = c0 + tid * 4 + g * kRowClThreads * 4;
+    if (n < c0 + cols) {
+      wv[g] = *reinterpret_cast<const uint2*>(a.norm_w + n);
+      v[g] = sum_slots_4(a.ws, a.sm, row, n, ns_tab[n / kTileN]);
+      if (a.bias != nullptr) {
+        const float4 b = unpack4_bf16(*reinterpret_cast<const uint2*>(a.bias + n));
+        v[g].x += b.x; v[g].y += b.y; v[g].z += b.z; v[g].w += b.w;
+      }
+      if (a.resid != nullptr) rs[g] = __ldcg(reinterpret_cast<const uint2*>(a.resid + roff + n));
     }
   }
+  float ss = 0.f;
+#pragma unroll
+  for (int g = 0; g < kRowClGroups; ++g) {
+    const int n = c0 + tid * 4 + g * kRowClThreads * 4;
+    if (n >= c0 + cols) continue;
+    float4& x = v[g];
+    x.x = bf16_round(x.x); x.y = bf16_round(x.y); x.z = bf16_round(x.z); x.w = bf16_round(x.w);
+    if (a.resid != nullptr) {
+      const float4 rsd = unpack4_bf16(rs[g]);
+      x.x = bf16_round(rsd.x + x.x); x.y = bf16_round(rsd.y + x.y);
+      x.z = bf16_round(rsd.z + x.z); x.w = bf16_round(rsd.w + x.w);
+      *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
+    }
+    ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+  }
+  DFL_TRACE(4);
   ss = warp_sum(ss);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
   __syncthreads();
+  if (tid < kRowCtas) {  // thread p pushes this CTA's partial sum into CTA p's peer_ss[rank]
+    float part = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowClThreads / 32; ++w) part += red[w];
+    dsmem_st_f32(dsmem_map(smem_u32(&peer_ss[rank]), static_cast<uint32_t>(tid)), part);
+  }
+  cluster_sync_all();
+  DFL_TRACE(5);
   float tot = 0.f;
 #pragma unroll
-  for (int w = 0; w < kNormThreads / 32; ++w) tot += red[w];
+  for (int p = 0; p < kRowCtas; ++p) tot += peer_ss[p];
   const float rstd = 1.0f / sqrtf(tot / static_cast<float>(a.H) + a.eps);
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int n = n0 + g * kNormThreads * 8;
-    if (n >= a.H) continue;
-    if (g == 1) wv = *reinterpret_cast<const uint4*>(a.norm_w + n);
-    const float4 x0 = unpack4_bf16(make_uint2(xv[g].x, xv[g].y)), x1 = unpack4_bf16(make_uint2(xv[g].z, xv[g].w));
-    const float4 w0 = unpack4_bf16(make_uint2(wv.x, wv.y)), w1 = unpack4_bf16(make_uint2(wv.z, wv.w));
-    const uint2 o0 = pack4_bf16(w0.x * bf16_round(x0.x * rstd), w0.y * bf16_round(x0.y * rstd),
-                                w0.z * bf16_round(x0.z * rstd), w0.w * bf16_round(x0.w * rstd));
-    const uint2 o1 = pack4_bf16(w1.x * bf16_round(x1.x * rstd), w1.y * bf16_round(x1.y * rstd),
-                                w1.z * bf16_round(x1.z * rstd), w1.w * bf16_round(x1.w * rstd));
-    *reinterpret_cast<uint4*>(a.out + roff + n) = make_uint4(o0.x, o0.y, o1.x, o1.y);
+  for (int g = 0; g < kRowClGroups; ++g) {
+    const int n = c0 + tid * 4 + g * kRowClThreads * 4;
+    if (n >= c0 + cols) continue;
+    const float4 w = unpack4_bf16(wv[g]);
+    *reinterpret_cast<uint2*>(a.out + roff + n) =
+        pack4_bf16(w.x * bf16_round(v[g].x * rstd), w.y * bf16_round(v[g].y * rstd), w.z * bf16_round(v[g].z * rstd),
+                   w.w * bf16_round(v[g].w * rstd));
   }
+  DFL_TRACE(2);
 }
 
-// The step's first small kernel: CTAs [0, rows0) finish the context injection (hidden_norm over the fc GEMM's bf16
-// rows, model/dflash.py:177), the rest embed the block and apply layer 0's input_layernorm. CTA b also fills row b of
-// the step's position / rotary table (Qwen3RotaryEmbedding, model/dflash.py:178), which every layer's QKV epilogue
-// reads: request state is only read after griddepcontrol.wait (the verify kernel of the previous cycle wrote it).
-__global__ void __launch_bounds__(kNormThreads) rows_pre_kernel(const NormArgs c, const EmbedArgs e, const RopeTableArgs t,
-                                                               const int rows0) {
-  __shared__ float red[kNormThreads / 32];
-  if (static_cast<int>(blockIdx.x) < rows0) norm_row_body(c, blockIdx.x, threadIdx.x);
-  else embed_row_body(e, blockIdx.x - rows0, threadIdx.x, red);
-  rope_table_row(t, blockIdx.x, threadIdx.x);
+// Two independent row passes in one launch (CTAs [0, rows0) run a0, the rest run a1): the step's first small
+// kernel does both the context finalize (fc -> hidden_norm) and the block embedding + first input_layernorm.
+__global__ void __launch_bounds__(kRowsThreads) finalize_rows2_kernel(const RowsArgs a0, const RowsArgs a1,
+                                                                     const int rows0) {
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float red[kRowsThreads / 32];
+  __shared__ int ns_tab[kRowsMaxTiles];
+  const bool first = static_cast<int>(blockIdx.x) < rows0;
+  const RowsArgs& a = first ? a0 : a1;
+  if (a.embed == nullptr) {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
+  }
+  __syncthreads();
+  DFL_WAIT_THEN_TRIGGER();
+  finalize_row_body<kRowsThreads, true>(a, first ? blockIdx.x : blockIdx.x - rows0, threadIdx.x, rowbuf, red, ns_tab, 0);
+  DFL_TRACE(2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// QKV post-processing: per (row, head) warp. q/k: per-head RMSNorm over D=128 then RoPE
+// (half-split rotate, cos/sin rounded to bf16, products and sum rounded to bf16:
+// model/dflash.py:22-28,70-82); v: bf16 round. K/V go straight into the static draft cache at
+// their absolute position, q into the query buffer.
+struct QkvPostArgs {
+  const float* ws;
+  SlotMap sm;
+  int R, SL, bs;
+  int Hq, Hkv;      // D == 128
+  int q_cols;       // Hq*128, or 0 when the GEMM covered only the K/V weight rows (prefill)
+  int row0, rows;   // rows of the activation matrix covered by this launch
+  const int* start;
+  const int* ctx_len;
+  const int* blk_len;
+  const __nv_bfloat16* q_norm_w;
+  const __nv_bfloat16* k_norm_w;
+  const __nv_bfloat16* bias;  // optional [q_cols + 2*Hkv*128] = [q_proj.bias; k_proj.bias; v_proj.bias] (attention_bias)
+  const float* inv_freq;  // [64]
+  float rope_scale;
+  float eps;
+  __nv_bfloat16* q_out;    // [R*SL][Hq][128]
+  __nv_bfloat16* k_cache;  // [R][Hkv][S_max][128] (this layer)
+  __nv_bfloat16* v_cache;
+  int S_max;
+  // prompt pass (pf_rows > 0): every row is a context row of request pf_req at position pf_pos0 + row
+  int pf_rows, pf_req, pf_pos0;
+};
+
+// one (activation row, head column block hh) item per warp. Split in two so that the stand-alone kernel can run the
+// part that only reads request state, weights and the rope table BEFORE griddepcontrol.wait (request state is written
+// by the previous step's accept kernel, never by the GEMM in front of this kernel).
+struct QkvItem {
+  int kind;        // 0 q, 1 k, 2 v, -1 nothing to do
+  int ws_row, hh;
+  __nv_bfloat16* dst;
+  float4 wv;       // norm weights of this lane's 4 elements
+  float cs[4], sn[4];
+};
+
+__device__ __forceinline__ QkvItem qkv_post_prepare(const QkvPostArgs& a, int row, int hh, int lane) {
+  QkvItem it;
+  it.kind = -1;
+  const int heads_q = a.q_cols / 128;
+  const int RS = a.R * a.SL;
+  const bool is_block = a.pf_rows == 0 && row >= RS;
+  const int rl = is_block ? row - RS : row;
+  const int r = a.pf_rows > 0 ? a.pf_req : rl / a.SL, slot = rl % a.SL;
+  int pos;
+  if (a.pf_rows > 0) {
+    if (row >= a.pf_rows) return it;
+    pos = a.pf_pos0 + row;
+  } else if (is_block) {
+    if (slot >= a.blk_len[r]) return it;
+    pos = a.start[r] + slot;
+  } else {
+    const int c = a.ctx_len[r];
+    if (slot >= c) return it;
+    pos = a.start[r] - c + slot;
+  }
+  const int kind = hh < heads_q ? 0 : (hh < heads_q + a.Hkv ? 1 : 2);  // q, k, v
+  if (kind == 0 && !is_block) return it;  // context rows carry no queries
+  if (pos < 0 || pos >= a.S_max) return it;
+  const int head = kind == 0 ? hh : (kind == 1 ? hh - heads_q : hh - heads_q - a.Hkv);
+  it.ws_row = row - a.row0;
+  it.hh = hh;
+  if (kind == 0) {
+    it.dst = a.q_out + (static_cast<long long>(rl) * a.Hq + head) * 128;
+  } else {
+    __nv_bfloat16* base = kind == 1 ? a.k_cache : a.v_cache;
+    it.dst = base + ((static_cast<long long>(r) * a.Hkv + head) * a.S_max + pos) * 128;
+  }
+  it.kind = kind;
+  if (kind == 2) return it;
+  const __nv_bfloat16* w = kind == 0 ? a.q_norm_w : a.k_norm_w;
+  it.wv = unpack4_bf16(*reinterpret_cast<const uint2*>(w + lane * 4));
+  // RoPE: element d pairs with d +- 64 -> held by lane ^ 16; frequency index = d mod 64
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int f = (lane & 15) * 4 + t;
+    const float ang = static_cast<float>(pos) * a.inv_freq[f];
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    it.cs[t] = bf16_round(cs * a.rope_scale);
+    it.sn[t] = bf16_round(sn * a.rope_scale);
+  }
+  return it;
+}
+
+__device__ __forceinline__ void qkv_post_apply(const QkvPostArgs& a, const QkvItem& it, int lane) {
+  if (it.kind < 0) return;
+  // head hh covers output columns [hh*128, hh*128+128) = exactly stream-K tile hh
+  float4 xv = sum_slots_4(a.ws, a.sm, it.ws_row, it.hh * 128 + lane * 4, tile_slots32(it.hh, a.sm));
+  if (a.bias != nullptr) {
+    const float4 b = unpack4_bf16(*reinterpret_cast<const uint2*>(a.bias + it.hh * 128 + lane * 4));
+    xv.x += b.x; xv.y += b.y; xv.z += b.z; xv.w += b.w;
+  }
+  float x[4] = {bf16_round(xv.x), bf16_round(xv.y), bf16_round(xv.z), bf16_round(xv.w)};  // d = 4*lane + t
+  if (it.kind == 2) {
+    *reinterpret_cast<uint2*>(it.dst + lane * 4) = pack4_bf16(x[0], x[1], x[2], x[3]);
+    return;
+  }
+  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+  ss = warp_sum(ss);
+  const float rstd = 1.0f / sqrtf(ss * (1.0f / 128.0f) + a.eps);
+  x[0] = bf16_round(it.wv.x * bf16_round(x[0] * rstd));
+  x[1] = bf16_round(it.wv.y * bf16_round(x[1] * rstd));
+  x[2] = bf16_round(it.wv.z * bf16_round(x[2] * rstd));
+  x[3] = bf16_round(it.wv.w * bf16_round(x[3] * rstd));
+  float o[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float other = __shfl_xor_sync(0xffffffffu, x[t], 16);
+    // first half (lane < 16): x*cos + (-x_hi)*sin ; second half: x*cos + x_lo*sin
+    const float rot = (lane < 16) ? -other : other;
+    o[t] = bf16_round(bf16_round(x[t] * it.cs[t]) + bf16_round(rot * it.sn[t]));
+  }
+  *reinterpret_cast<uint2*>(it.dst + lane * 4) = pack4_bf16(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, int hh, int lane) {
+  const QkvItem it = qkv_post_prepare(a, row, hh, lane);
+  qkv_post_apply(a, it, lane);
+  DFL_TRACE(2);
+}
+
+// item in [0, rows * (q_cols/128 + 2*Hkv))
+__device__ __forceinline__ void qkv_post_item(const QkvPostArgs& a, int item, int lane) {
+  const int heads_per_row = a.q_cols / 128 + 2 * a.Hkv;
+  qkv_post_rowhead(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
+}
+
+__global__ void __launch_bounds__(32 * kItemWarps) qkv_post_kernel(const QkvPostArgs a) {
+  const int item = blockIdx.x * kItemWarps + (threadIdx.x >> 5);
+  const int heads_per_row = a.q_cols / 128 + 2 * a.Hkv;
+  const int lane = threadIdx.x & 31;
+  QkvItem it;
+  it.kind = -1;
+  // positions, rope table and norm weights while the QKV GEMM in front of this kernel is still running. The request
+  // state read here was written by the previous cycle's verify kernel, which has completed: the row kernel at the top
+  // of the step waits (griddepcontrol.wait) for the fc GEMM, whose own wait covers the verify kernel, before it
+  // releases anything behind it.
+  if (item < a.rows * heads_per_row) it = qkv_post_prepare(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
+  DFL_WAIT_THEN_TRIGGER();
+  qkv_post_apply(a, it, lane);
   DFL_TRACE(2);
 }
 

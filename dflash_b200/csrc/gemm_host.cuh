@@ -110,9 +110,7 @@ inline cudaError_t launch_gemm_any_mb(const GemmPlan& p, cudaStream_t stream, bo
 }
 
 inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl) {
-  if (p.mode == kModeRows) return launch_gemm_any_mb<kModeRows>(p, stream, pdl);
   if (p.mode == kModeSwiglu) return launch_gemm_any_mb<kModeSwiglu>(p, stream, pdl);
-  if (p.mode == kModeQkv) return launch_gemm_any_mb<kModeQkv>(p, stream, pdl);
   if (p.mode == kModeSample) {
     switch (p.mb) {
       case 16: return launch_gemm_t<16, kModeSample>(p, stream, pdl);

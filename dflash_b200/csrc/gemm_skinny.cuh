@@ -37,13 +37,11 @@ enum GemmMode : int {
                       // (multi-candidate drafting: benchmark_candidate_solutions.py:181-249)
   kModeSample = 4,    // whole tiles per CTA; per-CTA argmax of  logit / T + Gumbel noise  per activation row = a draw
                       // from softmax(logits / T) (Gumbel-max, the construction the posterior sampler uses too)
-  // Fused row epilogues (epilogues.cuh): stream-K as kModePartials, but a split tile is FINISHED inside the GEMM -- the
-  // CTA that owns the tile's first k-blocks (always the last segment of its range) adds the partial accumulators the
-  // other CTAs of the tile left in `part`, in slot order, and runs the epilogue on the finished tile. Tiles that one
-  // CTA owns entirely never leave TMEM/registers. No fp32 partial plane, no consumer kernel.
-  kModeRows = 5,      // bf16 Linear output (+bias) [+ residual] and per-tile sums of squares (fc, o_proj, down_proj)
-  kModeSwiglu = 6,    // tile = 64 gate rows + 64 up rows of the same columns -> bf16 silu(gate) * up
-  kModeQkv = 7,       // tile = one head: q/k RMSNorm + RoPE, K/V written at their cache position, q to the query buffer
+  // Fused SwiGLU epilogue (epilogues.cuh): stream-K as kModePartials, but a split tile is FINISHED inside the GEMM --
+  // the CTA that owns the tile's first k-blocks (always the last segment of its range) adds the partial accumulators
+  // the other CTAs of the tile left in `part`, in slot order, and runs the epilogue on the finished tile. Tiles that
+  // one CTA owns entirely never leave TMEM/registers. No fp32 partial plane, no consumer kernel.
+  kModeSwiglu = 5,    // tile = 64 gate rows + 64 up rows of the same columns -> bf16 silu(gate) * up
 };
 constexpr int kTopK = 4;
 
@@ -66,9 +64,7 @@ struct GemmArgs {
   // Fused modes: exchange of partial accumulators between the CTAs of a split tile
   float* part;            // [groups * ranges][MB/4][128][4] fp32: the partial of CTA (group, range)'s FIRST segment
   unsigned int* flags;    // [groups][n_tiles] arrivals of a tile's non-finishing CTAs (reset by the finisher)
-  RowsEpi rows;           // kModeRows
   SwigluEpi sw;           // kModeSwiglu
-  QkvPostArgs qkv;        // kModeQkv
   // kModeArgmax / kModeSample inside the engine: the LAST CTA to finish also reduces the per-CTA candidates to the
   // drafted tokens (block_ids[:, 1:bs], model/dflash.py:247) -- no separate reduce launch. Off when tok_counter is null.
   unsigned int* tok_counter;
@@ -126,7 +122,7 @@ __host__ __device__ inline int tile_num_slots(int t, int k_blocks, long long T, 
 #define DFLASH_GEMM_SMEM_KB_WIDE 196
 #endif
 
-constexpr bool mode_is_fused(int mode) { return mode >= kModeRows; }
+constexpr bool mode_is_fused(int mode) { return mode == kModeSwiglu; }
 constexpr bool mode_is_whole_tile(int mode) { return mode >= kModeArgmax && mode <= kModeSample; }
 
 template <int MB, int MODE = 0>
@@ -350,26 +346,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       __shared__ __align__(16) float s_t[kCh * kTileN];  // tile[m][n] of the current chunk of activation rows
       const long long part_stride = static_cast<long long>(kTileN) * MB;  // floats per CTA partial
       float* my_part = a.part + (static_cast<long long>(blockIdx.x) * G + cta) * part_stride;
-      // Per-row operands of the epilogue that do not depend on the accumulator (residual values; row position and
-      // rotary table entries) are requested BEFORE the wait for the accumulator: at the end of the kernel the
-      // epilogue of the last tile is exposed, and an L2 round trip per row there costs more than the math.
-      uint2 pre_rs[MODE == kModeRows ? kRpw : 1];
-      QkvRowPre pre_q[MODE == kModeQkv ? kRpw : 1];
-      float4 norm_wv = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto prefetch_rows = [&](int tile, int c) {
-#pragma unroll
-        for (int i = 0; i < kRpw; ++i) {
-          const int m = c * kCh + quarter + 4 * i;
-          const int row = a.x_row0 + m0 + (m < mv ? m : 0);
-          if constexpr (MODE == kModeRows) {
-            if (a.rows.resid != nullptr)
-              pre_rs[i] = __ldcg(reinterpret_cast<const uint2*>(a.rows.resid + static_cast<long long>(row) * a.rows.ld +
-                                                                tile * kTileN + lane * 4));
-          } else if constexpr (MODE == kModeQkv) {
-            pre_q[i] = qkv_row_prefetch(a.qkv, row, lane);
-          }
-        }
-      };
       long long u = u0;
       while (u < u1) {
         const int tile = static_cast<int>(u / a.k_blocks);
@@ -381,48 +357,42 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const bool writer = slot > 0;                  // the tile began in an earlier CTA: leave a partial for it
         const bool finisher = slot == 0 && nslots > 1; // the tile continues in later CTAs: they left partials for us
         unsigned int* flag = a.flags + static_cast<long long>(blockIdx.x) * a.n_tiles + tile;
-        if (!writer) {
-          prefetch_rows(tile, 0);
-          if constexpr (MODE == kModeQkv) {
-            const int kind = qkv_kind(a.qkv, tile);
-            if (kind < 2)
-              norm_wv = unpack4_bf16(*reinterpret_cast<const uint2*>((kind == 0 ? a.qkv.q_norm_w : a.qkv.k_norm_w) + lane * 4));
-          }
-        }
-        mbar_wait(&tfull[acc], acc_phase);
-        if (tr && seg_end >= u1 && threadIdx.x == 0) tr[5] = global_ns();
-        if (seg_end >= u1) DFL_TRACE(4);
-        tc_fence_after();
+        constexpr int kSlotBatch = 64 / kCh;  // other CTAs' partials in flight together (register budget)
+        float4 p[kSlotBatch][kCh / 4];
+        // partial layout: [m / 4][n][4] -> a warp's float4 accesses are 512 contiguous bytes
+        auto part_ofs = [&](int c) { return (static_cast<long long>(c * (kCh / 4)) * kTileN + row_in_tile) * 4; };
+        auto load_partials = [&](int c, int s0) {  // slots [s0, s0 + kSlotBatch) of chunk c
+#pragma unroll
+          for (int b = 0; b < kSlotBatch; ++b)
+            if (s0 + b < nslots) {
+              const float* op = my_part + static_cast<long long>(s0 + b) * part_stride + part_ofs(c);
+#pragma unroll
+              for (int i = 0; i < kCh / 4; ++i)
+                p[b][i] = __ldcg(reinterpret_cast<const float4*>(op + static_cast<long long>(i) * kTileN * 4));
+            }
+        };
         if (finisher) {
-          // The other CTAs of this tile computed their share at the START of their ranges, or are whole-range middle
-          // slots that end when we do.
+          // The other CTAs of this tile computed their share at the START of their ranges (gate/up: a tile spans two
+          // CTAs), so their partials are normally long there: wait for them and request them BEFORE the wait for
+          // this CTA's own accumulator -- at the end of the kernel the last tile's epilogue is exposed.
           if (epi_tid == 0) {
             while (ld_acquire_u32(flag) < static_cast<unsigned int>(nslots - 1)) { }
             *flag = 0u;  // next use is a later launch of this plan
           }
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          DFL_TRACE(5);
+          load_partials(0, 1);
         }
+        mbar_wait(&tfull[acc], acc_phase);
+        if (tr && seg_end >= u1 && threadIdx.x == 0) tr[5] = global_ns();
+        if (seg_end >= u1) DFL_TRACE(4);
+        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < MB / kCh; ++c) {
           float v[kCh];
 #pragma unroll
           for (int q = 0; q < kCh / 16; ++q)
             tmem_ld16(tmem_base + lane_addr + static_cast<uint32_t>(acc * MB + c * kCh + q * 16), v + q * 16);
-          // partial layout: [m / 4][n][4] -> a warp's float4 accesses are 512 contiguous bytes
-          const long long pofs = (static_cast<long long>(c * (kCh / 4)) * kTileN + row_in_tile) * 4;
-          constexpr int kSlotBatch = 64 / kCh;  // other CTAs' partials in flight together (register budget)
-          float4 p[kSlotBatch][kCh / 4];
-          if (finisher) {  // first batch of the other slots' partials: requested before the TMEM load completes
-#pragma unroll
-            for (int b = 0; b < kSlotBatch; ++b)
-              if (1 + b < nslots) {
-                const float* op = my_part + static_cast<long long>(1 + b) * part_stride + pofs;
-#pragma unroll
-                for (int i = 0; i < kCh / 4; ++i)
-                  p[b][i] = __ldcg(reinterpret_cast<const float4*>(op + static_cast<long long>(i) * kTileN * 4));
-              }
-          }
+          const long long pofs = part_ofs(c);
           tmem_ld_wait();
           if (c == MB / kCh - 1) {
             tc_fence_before();
@@ -437,16 +407,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           }
           if (finisher) {
             for (int s0 = 1; s0 < nslots; s0 += kSlotBatch) {  // slot order: the summation order is fixed
-              if (s0 > 1) {
-#pragma unroll
-                for (int b = 0; b < kSlotBatch; ++b)
-                  if (s0 + b < nslots) {
-                    const float* op = my_part + static_cast<long long>(s0 + b) * part_stride + pofs;
-#pragma unroll
-                    for (int i = 0; i < kCh / 4; ++i)
-                      p[b][i] = __ldcg(reinterpret_cast<const float4*>(op + static_cast<long long>(i) * kTileN * 4));
-                  }
-              }
+              if (s0 > 1) load_partials(c, s0);
 #pragma unroll
               for (int b = 0; b < kSlotBatch; ++b)
                 if (s0 + b < nslots) {
@@ -464,19 +425,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           for (int i = 0; i < kRpw; ++i) {
             const int j = quarter + 4 * i;
             const int m = c * kCh + j;
-            if (m < mv) {
-              const int row = a.x_row0 + m0 + m;  // row of the activation matrix == row of the output
-              if constexpr (MODE == kModeRows) {
-                rows_epi_apply(a.rows, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]), pre_rs[i], tile, row, lane);
-              } else if constexpr (MODE == kModeSwiglu) {
-                swiglu_epi_apply(a.sw, &s_t[j * kTileN], tile, row, lane);
-              } else {
-                qkv_post_apply(a.qkv, pre_q[i], norm_wv, *reinterpret_cast<const float4*>(&s_t[j * kTileN + lane * 4]),
-                               row, tile, lane);
-              }
-            }
+            // row of the activation matrix == row of the output
+            if (m < mv) swiglu_epi_apply(a.sw, &s_t[j * kTileN], tile, a.x_row0 + m0 + m, lane);
           }
-          if (c + 1 < MB / kCh) prefetch_rows(tile, c + 1);
+          if (finisher && c + 1 < MB / kCh) load_partials(c + 1, 1);
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
         }
         if (writer) {

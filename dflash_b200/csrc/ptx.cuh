@@ -190,28 +190,18 @@ __device__ __forceinline__ void dfl_trace_any(int phase) {  // call from ONE thr
 #endif
 
 // Small kernels in front of a GEMM: wait for the producer first, release the dependent GEMM second, so that the GEMM
-// becomes resident exactly when this kernel starts its real work (measured against trigger-first: DESIGN.md §7).
-#ifdef DFLASH_TRIGGER_FIRST
-#define DFL_WAIT_THEN_TRIGGER() do { DFL_TRACE(0); pdl_trigger(); pdl_wait(); DFL_TRACE(1); } while (0)
-#else
+// becomes resident exactly when this kernel starts its real work (measured against trigger-first: DESIGN.md section 7).
+// The ordering is also what makes request state read before a later kernel's own wait safe: a kernel behind this one
+// cannot start before this kernel's wait has returned.
 #define DFL_WAIT_THEN_TRIGGER() do { DFL_TRACE(0); pdl_wait(); pdl_trigger(); DFL_TRACE(1); } while (0)
-#endif
 
-// the verify-side kernels and the token reduce (experiment switch: same ordering question)
-#ifdef DFLASH_VERIFY_WAIT_FIRST
-#define DFL_VERIFY_SYNC() do { DFL_TRACE(0); pdl_wait(); pdl_trigger(); DFL_TRACE(1); } while (0)
-#else
+// the verify-side kernels: release the dependent first (measured: no difference either way)
 #define DFL_VERIFY_SYNC() do { DFL_TRACE(0); pdl_trigger(); pdl_wait(); DFL_TRACE(1); } while (0)
-#endif
 
-// block sizes of the small kernels (tuning switches; measured defaults)
-#ifndef DFLASH_SWIGLU_THREADS
-#define DFLASH_SWIGLU_THREADS 256
-#endif
-#ifndef DFLASH_WARPITEM_WARPS   // warps (= items) per CTA of the warp-per-item kernels qkv_post / attn_combine
+// block size of the warp-per-item kernels qkv_post / attn_combine (tuning switch; measured default)
+#ifndef DFLASH_WARPITEM_WARPS
 #define DFLASH_WARPITEM_WARPS 8
 #endif
-constexpr int kSwigluThreads = DFLASH_SWIGLU_THREADS;
 constexpr int kItemWarps = DFLASH_WARPITEM_WARPS;
 
 // named barrier over `nthreads` threads of the CTA (id 0 with blockDim.x threads == __syncthreads)

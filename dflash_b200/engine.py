@@ -40,15 +40,14 @@ class CWeights(Structure):
 BUFFERS = [
     ("x", torch.bfloat16), ("a_in", torch.bfloat16), ("ctx_feat", torch.bfloat16), ("q", torch.bfloat16),
     ("attn_out", torch.bfloat16), ("a2", torch.bfloat16), ("hmid", torch.bfloat16), ("hn", torch.bfloat16),
-    ("kv", torch.bfloat16), ("y_ctx", torch.bfloat16), ("tile_ss", torch.float32), ("part", torch.float32),
-    ("flags", torch.int32), ("counters", torch.int32), ("row_pos", torch.int32), ("rope", torch.float32),
-    ("attn_po", torch.float32), ("attn_ml", torch.float32),
+    ("kv", torch.bfloat16), ("ws", torch.float32), ("part", torch.float32), ("flags", torch.int32),
+    ("counters", torch.int32), ("attn_po", torch.float32), ("attn_ml", torch.float32),
     ("cand_val", torch.float32), ("cand_idx", torch.int32), ("post_val", torch.float32), ("post_idx", torch.int32),
     ("draft_tokens", torch.int64), ("block_ids", torch.int64), ("posterior", torch.int64),
     ("output_ids", torch.int64), ("start", torch.int32), ("ctx_len", torch.int32), ("done", torch.int32),
     ("n_cycles", torch.int32), ("blk_len", torch.int32), ("max_len", torch.int32), ("acc_hist", torch.int32),
     ("rng_step", torch.int64), ("draft_logits", torch.bfloat16), ("pf_feat", torch.bfloat16), ("pf_a", torch.bfloat16),
-    ("pf_y", torch.bfloat16), ("topk_idx", torch.int32), ("topk_val", torch.float32), ("cand_ids", torch.int64),
+    ("topk_idx", torch.int32), ("topk_val", torch.float32), ("cand_ids", torch.int64),
     ("cand_scores", torch.float32), ("chosen", torch.int32),
 ]
 
@@ -242,9 +241,10 @@ class DraftEngine:
         self.SL = 16 if bs <= 16 else 32
         self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
         # launches per draft step of the schedule actually enqueued (engine.cuh): fc GEMM, one row kernel (context
-        # hidden_norm + block embedding + first layernorm), per layer {qkv GEMM, attention, merge, o GEMM, norm,
-        # gate/up GEMM, down GEMM, norm}, lm_head GEMM (argmax + drafted tokens); the verify step is one kernel
-        self.kernels_per_draft_step = 2 + 8 * cfg.num_hidden_layers + 1
+        # finalize + block embedding + first layernorm), per layer {qkv GEMM, qkv_post, attention, merge, o GEMM, row
+        # kernel, gate/up GEMM (SwiGLU epilogue), down GEMM, row kernel}, lm_head GEMM (argmax + drafted tokens); the
+        # verify step is one kernel
+        self.kernels_per_draft_step = 2 + 9 * cfg.num_hidden_layers + 1
         self.kernels_per_verify_step = 1
         self._graph = None
 

@@ -14,6 +14,7 @@ from typing import List, Optional
 import torch
 from torch import nn
 from transformers import DynamicCache
+from transformers.cache_utils import Cache
 from transformers.models.qwen3.modeling_qwen3 import (Qwen3Config, Qwen3MLP, Qwen3PreTrainedModel, Qwen3RMSNorm,
                                                       Qwen3RotaryEmbedding)
 
@@ -54,19 +55,36 @@ class Qwen3DFlashDecoderLayer(nn.Module):
         self.post_attention_layernorm = Qwen3RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
 
-class DFlashStaticCache:
-    """Handle on the engine's static draft KV cache with the three `Cache` methods the decode loop uses
-    (`get_seq_length`, `crop`, and the implicit append done by `forward`): model/dflash.py:215,241,246.
-    The K/V rows live in the engine workspace; cropping is a length write."""
+class DFlashStaticCache(Cache):
+    """A `transformers.Cache` that is only a handle on the engine's static draft KV cache: the three methods the
+    decode loop uses (`get_seq_length`, `crop`, and the implicit append done by `forward`: model/dflash.py:215,241,246)
+    work on a length; the K/V rows live in the engine workspace, so cropping is a length write."""
 
     def __init__(self):
+        super().__init__(layers=[])
         self.length = 0
 
     def get_seq_length(self, layer_idx: int = 0) -> int:
         return self.length
 
     def crop(self, max_length: int):
-        self.length = min(self.length, int(max_length))
+        n = int(max_length)
+        self.length = max(0, self.length + n) if n < 0 else min(self.length, n)
+
+    def reset(self):
+        self.length = 0
+
+    def update(self, key_states, value_states, layer_idx, *args, **kwargs):
+        raise RuntimeError("DFlashStaticCache holds no tensors: the draft K/V rows are written by the CUDA engine")
+
+
+def _grow_foreign_cache(cache, n_rows: int, n_layers: int, device):
+    """A caller-owned HF cache (e.g. the `DynamicCache()` of benchmark.py:60,122-129) only has to report the right
+    length to its owner (`get_seq_length()` / `crop()`); the K/V rows themselves stay in the engine. Append `n_rows`
+    empty positions per layer: [1, 1, n_rows, 1] placeholders, a few bytes each."""
+    z = torch.zeros(1, 1, int(n_rows), 1, dtype=torch.bfloat16, device=device)
+    for layer_idx in range(n_layers):
+        cache.update(z, z, layer_idx)
 
 
 class DFlashDraftModel(Qwen3PreTrainedModel):
@@ -120,14 +138,18 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
                 noise_embedding: Optional[torch.Tensor] = None, target_hidden: Optional[torch.Tensor] = None,
                 past_key_values=None, use_cache: bool = False, **kwargs) -> torch.Tensor:
         """model/dflash.py:166-190. Returns the final-normed hidden states [1, q_len, H] (no lm_head).
-        `past_key_values` is a `DFlashStaticCache` (or None for a fresh context starting at position 0).
-        Side effect, as in the reference: the cache grows by ctx_len + q_len rows (the caller crops)."""
+        `past_key_values`: None (a fresh context starting at position 0), a `DFlashStaticCache`, or any HF `Cache` the
+        caller owns (`DynamicCache()` as in benchmark.py:60,122-129): its length is adopted and kept in step, the K/V
+        rows themselves live in the engine (one sequence at a time: a cache that was not grown by this model must be
+        empty). Side effect, as in the reference: the cache grows by ctx_len + q_len rows (the caller crops)."""
         if attention_mask is not None:
             raise NotImplementedError("the DFlash draft attends without a mask (model/dflash.py:244)")
         if noise_embedding.shape[0] != 1:
             raise RuntimeError("DFlashDraftModel.forward: batch size 1 only (as spec_generate, model/dflash.py:206-211)")
-        if isinstance(past_key_values, DynamicCache):
-            raise NotImplementedError("pass a dflash_b200.DFlashStaticCache: the draft K/V live in the CUDA engine")
+        foreign = past_key_values is not None and not isinstance(past_key_values, DFlashStaticCache)
+        if foreign and past_key_values.get_seq_length() > 0 and getattr(self, "_foreign_cache_id", None) != id(past_key_values):
+            raise RuntimeError("DFlashDraftModel.forward: this cache holds K/V rows written by another model; the CUDA "
+                               "engine keeps the draft K/V of one sequence (start from an empty cache)")
         dev = noise_embedding.device
         q_len, c = noise_embedding.shape[1], target_hidden.shape[1]
         cache_len = 0 if past_key_values is None else past_key_values.get_seq_length()
@@ -160,7 +182,10 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         noise = torch.zeros(e.SL, H, dtype=bf, device=dev)
         noise[:q_len] = noise_embedding[0].to(bf)
         e.draft_step(noise_embedding=noise, lm_head=False)
-        if past_key_values is not None:
+        if foreign:
+            _grow_foreign_cache(past_key_values, c + q_len, self.config.num_hidden_layers, dev)
+            self._foreign_cache_id = id(past_key_values)
+        elif past_key_values is not None:
             past_key_values.length = start + q_len
         return e.hn[:q_len].clone().unsqueeze(0).to(noise_embedding.dtype)
 
@@ -180,10 +205,11 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         """model/dflash.py:192-277, same signature and return value (`LongTensor[1, P + n_out]`).
         Keyword-only extras: `clamp_tail` = benchmark.py:104-105 behaviour, `forced_k` = harness hook that
         forces the first k draft tokens of each cycle to be accepted, `seed` for T > 0,
-        `graph_target` (default: `self.graph_target`, False) runs the target's verify forward from a CUDA graph
+        `graph_target` (default: `self.graph_target`, "auto") runs the target's verify forward from a CUDA graph
         over a static KV cache (`dflash_b200/target_graph.py`) — the target module itself is
         untouched, and the whole cycle then needs no host round trip, so the host may poll the device state only
-        every `sync_every` cycles."""
+        every `sync_every` cycles. "auto" falls back to the reference's eager call when the target cannot be
+        captured; False forces the eager call."""
         self.eval()
         if input_ids.shape[0] != 1:
             raise RuntimeError("spec_generate: batch size 1 only (the expanded size of the tensor must match: "
@@ -198,19 +224,41 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         position_ids = torch.arange(max_length + bs, device=dev).unsqueeze(0)
         if seed is None:
             seed = int(torch.randint(0, 2**62, (1,)).item()) if temperature >= 1e-5 else 0
+        # Target verify forward: replayed from a CUDA graph over a static KV cache whenever the target can be captured
+        #  -- same module, same arithmetic, no host round trip in the cycle. `graph_target=False`
+        # (or `model.graph_target = False`) keeps the reference's eager call with a DynamicCache; the default "auto"
+        # falls back to it when capture fails (e.g. attn_implementation="eager", data-dependent expert routing).
         if graph_target is None:
-            graph_target = bool(getattr(self, "graph_target", False))
+            graph_target = getattr(self, "graph_target", "auto")
+        auto = graph_target == "auto"
+        if auto and getattr(self, "_graph_target_failed", None) == id(target):
+            graph_target = False
         gt = None
+        logits0 = hidden0 = None
         if graph_target:
             from .target_graph import GraphedVerifyTarget
             key = (id(target), bs, e.buf["start"].data_ptr())
-            gt = getattr(self, "_graphed_target", None)
-            if gt is None or getattr(self, "_graphed_target_key", None) != key or gt.max_cache_len < max_length + bs:
-                cap = max(1024, 1 << (max_length + bs - 1).bit_length())
-                gt = GraphedVerifyTarget(target, bs, cap, self.target_layer_ids, e.buf["start"], e.block_ids)
-                self._graphed_target, self._graphed_target_key = gt, key
-            logits0, hidden0 = gt.prefill(input_ids)
-        else:
+            try:
+                gt = getattr(self, "_graphed_target", None)
+                if gt is None or getattr(self, "_graphed_target_key", None) != key or gt.max_cache_len < max_length + bs:
+                    cap = max(1024, 1 << (max_length + bs - 1).bit_length())
+                    gt = GraphedVerifyTarget(target, bs, cap, self.target_layer_ids, e.buf["start"], e.block_ids)
+                    self._graphed_target, self._graphed_target_key = gt, key
+                logits0, hidden0 = gt.prefill(input_ids)
+                if gt.graph is None:
+                    e.buf["start"][0] = P  # capture replays the forward on the live state: any in-range start will do
+                    gt.capture()
+            except Exception as ex:  # noqa: BLE001 -- capture failures surface as many exception types
+                if not auto:
+                    raise
+                import warnings
+                warnings.warn(f"dflash_b200: the target's verify forward could not be captured in a CUDA graph "
+                              f"({type(ex).__name__}: {ex}); calling it eagerly as the reference does")
+                self._graph_target_failed = id(target)
+                self._graphed_target = None
+                gt = None
+                torch.cuda.synchronize(dev)
+        if gt is None:
             # the selected residual streams come from forward hooks (ContextTap), not output_hidden_states=True:
             # same tensors, without the target keeping all L + 1 of them
             cache_t = DynamicCache()

@@ -101,14 +101,10 @@ enum dflash_buffer_id {
   DFLASH_BUF_HMID,         /* bf16 [R*SL, intermediate] */
   DFLASH_BUF_HN,           /* bf16 [R*SL, hidden] final-normed hidden = DFlashDraftModel.forward output */
   DFLASH_BUF_KV,           /* bf16 [n_layers, 2, R, Hkv, max_seq, 128] static draft KV cache */
-  DFLASH_BUF_Y_CTX,        /* bf16 [R*SL, hidden] fc output of the pending context rows (before hidden_norm) */
-  DFLASH_BUF_TILE_SS,      /* fp32 [3][64][rows]: per 128-column tile sums of squares of the fc rows, the residual
-                              rows and the prompt-pass rows (the RMSNorm pass adds them in tile order) */
-  DFLASH_BUF_PART,         /* fp32 partial accumulators exchanged between the CTAs of a split output tile */
-  DFLASH_BUF_FLAGS,        /* uint32 arrival counters per (GEMM, column group, tile); zero between launches */
+  DFLASH_BUF_WS,           /* fp32 split-K partial planes of fc / qkv / o / down (consumed by the row kernels) */
+  DFLASH_BUF_PART,         /* fp32 partial accumulators exchanged between the CTAs of a split gate/up tile */
+  DFLASH_BUF_FLAGS,        /* uint32 arrival counters per (layer, column group, gate/up tile); zero between launches */
   DFLASH_BUF_COUNTERS,     /* uint32 [R + 2] arrival counters of the verify kernel and of the token reduce */
-  DFLASH_BUF_ROW_POS,      /* int32 [2*R*SL + 256] absolute position of every activation row of the step (-1 = dead) */
-  DFLASH_BUF_ROPE,         /* fp32 [2*R*SL + 256, 128] rotary table of those rows: cos[64] | sin[64], bf16-rounded */
   DFLASH_BUF_ATTN_PO,
   DFLASH_BUF_ATTN_ML,
   DFLASH_BUF_CAND_VAL,
@@ -130,7 +126,6 @@ enum dflash_buffer_id {
   DFLASH_BUF_DRAFT_LOGITS, /* bf16 [R*SL, vocab] when keep_draft_logits */
   DFLASH_BUF_PF_FEAT,      /* bf16 [256, n_sel*hidden] prompt pass: gathered target features */
   DFLASH_BUF_PF_A,         /* bf16 [256, hidden] prompt pass: hidden_norm(fc(features)) */
-  DFLASH_BUF_PF_Y,         /* bf16 [256, hidden] prompt pass: fc(features) */
   DFLASH_BUF_TOPK_IDX,     /* int32 [R*SL, 4] top-4 vocab indices of every block row's draft logits */
   DFLASH_BUF_TOPK_VAL,     /* fp32 [R*SL, 4] their bf16-rounded logits */
   DFLASH_BUF_CAND_IDS,     /* int64 [R, 4, block_size] candidate blocks (feeds the target's batched verify forward) */
@@ -241,24 +236,14 @@ int dflash_gemm_skinny(const void* W, int w_rows_total, int w_row0, int N, int K
                        long long ws_ld, float* out, long long out_ld, int grid, int use_pdl,
                        void* stream);
 
-/* The projection GEMMs of the step with their fused row epilogues, as raw operators. A 128-column output tile that
- * several CTAs share (stream-K) is finished INSIDE the launch: `part` (fp32, grid * 128 * mb elements) carries the
- * partial accumulators, `flags` (uint32, ceil(m_valid/mb) * tiles, zero on entry and on exit) the arrivals.
- *   dflash_gemm_rows:   out[m, n] = bf16(resid[m, n] + bf16(sum_k X[m,k] W[n,k] + bias[n]))  (resid / bias optional;
- *                       out may alias resid) and tile_ss[n / 128][m] = sum of out[m, n]^2 over the tile's columns.
- *                       Replaces fc (model/dflash.py:177), o_proj + residual (:101,140), down_proj + residual (:143-144).
- *   dflash_gemm_swiglu: out[m, i] = bf16(bf16(silu(gate[m, i])) * up[m, i]) with Wgu = [gate_proj; up_proj] stacked
- *                       (rows [0, I) and [I, 2I)); N = I must be a multiple of 64. Replaces Qwen3MLP's
- *                       act_fn(gate_proj(x)) * up_proj(x).
- *   dflash_rms_norm_rows: out[m] = weight * bf16(x[m] * rsqrt(sum_t tile_ss[t][m] / hidden + eps))  (Qwen3RMSNorm over
- *                       rows a dflash_gemm_rows launch produced). */
-int dflash_gemm_rows(const void* W, int N, int K, const void* X, int x_rows_total, int mb, int m_valid,
-                     const void* bias, void* resid, void* out, long long ld, float* tile_ss, int ss_ld, float* part,
-                     unsigned int* flags, int grid, int use_pdl, void* stream);
+/* The gate/up GEMM with its fused SwiGLU epilogue, as a raw operator:
+ *   out[m, i] = bf16(bf16(silu(gate[m, i])) * up[m, i]),  Wgu = [gate_proj; up_proj] stacked (rows [0, I), [I, 2I)),
+ *   I a multiple of 64. A tile = 64 gate rows + 64 up rows of the same columns; a tile that several CTAs share
+ *   (stream-K) is finished INSIDE the launch: `part` (fp32, grid * 128 * mb elements) carries the partial
+ *   accumulators, `flags` (uint32, ceil(m_valid/mb) * I/64, zero on entry and on exit) the arrivals.
+ * Replaces Qwen3MLP's act_fn(gate_proj(x)) * up_proj(x) (transformers, via model/dflash.py:143). */
 int dflash_gemm_swiglu(const void* Wgu, int I, int K, const void* X, int x_rows_total, int mb, int m_valid, void* out,
                        long long ld, float* part, unsigned int* flags, int grid, int use_pdl, void* stream);
-int dflash_rms_norm_rows(const void* x, const float* tile_ss, int ss_ld, int hidden, const void* weight, void* out,
-                         int rows, float eps, void* stream);
 
 /* tokens_out[m] = argmax_n bf16(sum_k X[x_row0+m,k] * W[n,k]), ties -> lowest n; optionally also
  * writes the bf16 logits. Replaces target.lm_head(...) + sample(draft_logits)

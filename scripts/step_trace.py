@@ -56,15 +56,15 @@ for _ in range(6):
 torch.cuda.synchronize()
 rec = buf.view(cap, 2).cpu()
 rec = rec[rec[:, 1] != 0]
-names = {(512, 32, 1): "rows_pre", (512, 16, 1): "norm", (128, 16, 8): "attn_split", (256, 64, 1): "attn_combine",
-         (256, 32, 16): "verify", (192, 1, 148): "gemm", (192, 1, 132): "gemm_lm"}
+names = {(512, 32, 1): "finalize2", (256, 4, 16): "finalize_cl", (256, 192, 1): "qkv_post", (128, 16, 8): "attn_split",
+         (256, 64, 1): "attn_combine", (256, 32, 16): "verify", (192, 1, 148): "gemm", (192, 1, 132): "gemm_lm"}
 ev = []
 for tag, t in rec.tolist():
     phase, bd, gx, gy = tag & 15, (tag >> 4) & 0xFFF, (tag >> 16) & 0xFFFFFF, (tag >> 40) & 0xFFFFFF
     ev.append((t, names.get((bd, gx, gy), f"?{bd},{gx},{gy}"), phase))
 ev.sort()
 # one step = from a finalize2 entry to the next
-starts = [i for i, e in enumerate(ev) if e[1] == "rows_pre" and e[2] == 0]
+starts = [i for i, e in enumerate(ev) if e[1] == "finalize2" and e[2] == 0]
 a, b = starts[-3], starts[-2]
 # the fc GEMM of the step starts before finalize2: back up to its entry
 while a > 0 and not (ev[a][1] == "verify" and ev[a][2] == 0):

@@ -192,3 +192,63 @@ def test_forced_tau_schedule_is_window_balanced():
     for w in (8, 16, 32):
         for i in range(0, len(ks) - w + 1, w):
             assert abs(sum(k + 1 for k in ks[i:i + w]) / w - mean) < 0.75
+
+
+def test_automodel_from_pretrained_returns_the_product_class(tmp_path):
+    """README.md:76-81: `AutoModel.from_pretrained(<draft>, trust_remote_code=True)`. A checkpoint directory with the
+    installed remote-code module loads as this package's class, weights and DFlash attributes intact."""
+    import torch
+    from transformers import AutoModel
+    from dflash_b200 import DFlashDraftModel
+    from dflash_b200.hf import install_remote_code
+    from tests.tiny_models import draft_config, seeded_fill_
+    ref = DFlashDraftModel(draft_config(16))
+    seeded_fill_(ref, 7)
+    ref.save_pretrained(tmp_path)
+    mod = install_remote_code(str(tmp_path))
+    assert os.path.basename(mod) == "dflash.py"
+    import json
+    assert json.load(open(tmp_path / "config.json"))["auto_map"]["AutoModel"] == "dflash.DFlashDraftModel"
+    m = AutoModel.from_pretrained(str(tmp_path), trust_remote_code=True)
+    assert type(m).__name__ == "DFlashDraftModel" and isinstance(m, DFlashDraftModel)
+    assert m.block_size == 16 and m.mask_token_id == ref.mask_token_id and m.target_layer_ids == ref.target_layer_ids
+    sd_a, sd_b = ref.state_dict(), m.state_dict()
+    assert sd_a.keys() == sd_b.keys()
+    for k in sd_a:
+        assert torch.equal(sd_a[k], sd_b[k]), k
+    install_remote_code(str(tmp_path))  # idempotent
+
+
+def test_static_cache_is_a_transformers_cache_and_foreign_caches_track_length():
+    import torch
+    from transformers import DynamicCache
+    from transformers.cache_utils import Cache
+    from dflash_b200.model import DFlashStaticCache, _grow_foreign_cache
+    c = DFlashStaticCache()
+    assert isinstance(c, Cache) and c.get_seq_length() == 0
+    c.length = 40
+    c.crop(33)
+    assert c.get_seq_length() == 33
+    c.crop(100)
+    assert c.get_seq_length() == 33
+    with pytest.raises(RuntimeError):
+        c.update(torch.zeros(1, 1, 1, 1), torch.zeros(1, 1, 1, 1), 0)
+    d = DynamicCache()
+    _grow_foreign_cache(d, 37, 2, "cpu")
+    assert d.get_seq_length() == 37
+    d.crop(21)
+    _grow_foreign_cache(d, 5, 2, "cpu")
+    assert d.get_seq_length() == 26
+
+
+def test_shipped_library_has_no_result_changing_switches():
+    """The product build reads no environment variable: timing experiments that change results live in debug builds."""
+    import subprocess
+    from dflash_b200 import _lib
+    out = subprocess.run(["strings", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in ("DFLASH_DEBUG_SKIP", "DFLASH_LATE_W", "DFLASH_MEGA", "DFLASH_FUSED_ATTN", "DFLASH_NO_ROW_CLUSTER",
+                 "DFLASH_NO_CARVEOUT", "DFLASH_LM_GRID"):
+        assert name not in out, name
+    src = "".join(open(os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", f)).read()
+                  for f in os.listdir(os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc")))
+    assert "getenv" not in src

@@ -84,56 +84,6 @@ def _fused_scratch(dev, N_tiles, mb, rows, grid=148):
     return groups, part, flags
 
 
-@pytest.mark.parametrize("N,K,mb,rows,grid", [
-    (4096, 4096, 16, 16, 148), (4096, 12288, 16, 16, 148), (4096, 20480, 16, 11, 148), (2560, 4096, 16, 16, 148),
-    (4096, 4096, 16, 16, 37), (256, 128, 16, 16, 148), (4096, 4096, 32, 32, 148), (2048, 2048, 64, 64, 148),
-    (4096, 4096, 128, 100, 148), (4096, 12288, 256, 256, 148), (4096, 4096, 256, 1024, 148), (2048, 6144, 256, 520, 148)])
-@pytest.mark.parametrize("with_resid", [False, True])
-def test_gemm_rows_fused_epilogue(N, K, mb, rows, grid, with_resid):
-    """kModeRows: split tiles are finished inside the GEMM; out = bf16(resid + bf16(X W^T + bias)), per-tile sums of
-    squares of the bf16 result; then the RMSNorm pass over them (dflash.py:101,140,143-144,177 + Qwen3RMSNorm).
-    Run twice on the same scratch: the arrival counters must be back at zero after a launch."""
-    dev = _cuda()
-    from dflash_b200 import _lib
-    lib = _lib.load()
-    torch.manual_seed(N + K + rows)
-    groups, part, flags = _fused_scratch(dev, N // 128, mb, rows, grid)
-    W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
-    X = torch.randn(groups * mb, K, device=dev).to(torch.bfloat16)
-    bias = (torch.randn(N, device=dev) * 0.5).to(torch.bfloat16) if with_resid else None
-    resid0 = torch.randn(rows, N, device=dev).to(torch.bfloat16) if with_resid else None
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    lin = (X[:rows].float() @ W.float().t())
-    if bias is not None:
-        lin = lin + bias.float()
-    lin_bf = lin.to(torch.bfloat16)
-    exp = (resid0.float() + lin_bf.float()).to(torch.bfloat16) if with_resid else lin_bf
-    for rep in range(2):
-        out = resid0.clone() if with_resid else torch.zeros(rows, N, dtype=torch.bfloat16, device=dev)
-        ss = torch.zeros(N // 128, rows, dtype=torch.float32, device=dev)
-        _lib.check(lib.dflash_gemm_rows(_ptr(W), N, K, _ptr(X), groups * mb, mb, rows,
-                                        None if bias is None else _ptr(bias), _ptr(out) if with_resid else None,
-                                        _ptr(out), N, _ptr(ss), rows, _ptr(part), _ptr(flags), grid, 0, st))
-        torch.cuda.synchronize()
-        assert int(flags.abs().sum()) == 0, "arrival counters not reset"
-        # bf16 rounding of an fp32 sum that differs in the last bits: allow one bf16 ulp on a tiny fraction
-        diff = (out.float() - exp.float()).abs()
-        ulp = (exp.float().abs() + lin_bf.float().abs() + 1e-3) * 2 ** -6  # (a flipped Linear rounding carries over)
-        assert (diff <= ulp).all(), (rep, diff.max().item())
-        assert (diff > 0).float().mean().item() < 0.02
-        ss_ref = out.float().pow(2).view(rows, N // 128, 128).sum(-1).t()
-        assert torch.allclose(ss, ss_ref, rtol=1e-4, atol=1e-5)
-        w = (torch.rand(N, device=dev) + 0.5).to(torch.bfloat16)
-        y = torch.zeros(rows, N, dtype=torch.bfloat16, device=dev)
-        _lib.check(lib.dflash_rms_norm_rows(_ptr(out), _ptr(ss), rows, N, _ptr(w), _ptr(y), rows, 1e-6, st))
-        torch.cuda.synchronize()
-        xf = out.float()
-        yr = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(torch.bfloat16)
-        d = (y.float() - yr.float()).abs()
-        assert (d <= yr.float().abs().clamp_min(1e-3) * 2 ** -6).all(), d.max().item()
-        assert (d > 0).float().mean().item() < 0.01
-
-
 @pytest.mark.parametrize("I,K,mb,rows,grid", [(12288, 4096, 16, 16, 148), (9728, 2560, 16, 16, 148), (6144, 2048, 64, 64, 148),
                                               (1024, 512, 16, 9, 37), (12288, 4096, 256, 1024, 148), (14336, 4096, 128, 128, 148)])
 def test_gemm_swiglu_fused_epilogue(I, K, mb, rows, grid):
@@ -1044,7 +994,7 @@ def test_graphed_target_matches_eager_target(sync_every):
     forced = [3, 0, 7, 15, 1, 5, 2, 11]
     # honest greedy: the output depends only on the target's argmax -> equal to the eager-target run except at
     # near-ties (same module math, but a different attention kernel: static length + mask)
-    ref = draft.spec_generate(target, prompt, 40, None, 0.0)
+    ref = draft.spec_generate(target, prompt, 40, None, 0.0, graph_target=False)
     out = draft.spec_generate(target, prompt, 40, None, 0.0, graph_target=True, sync_every=sync_every)
     assert out.shape == ref.shape
     if not torch.equal(out, ref):
@@ -1309,4 +1259,80 @@ def test_spec_generate_block_size_override_is_lossless(bs):
             assert _near_tie(logits[i], pred[i].item(), out[0, i + 1].item()), i
     out_f = draft.spec_generate(target, prompt, 30, None, 0.0, forced_k=[bs - 1, 0, 3])
     assert max(draft.last_acceptance_lengths) == bs and out_f.shape == (1, 63)
+    draft.release_engine()
+
+
+# ------------------------------------------------------------------------------------------------
+# round-2 boundary items
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("graph_target", [False, None])
+def test_fresh_engine_first_cycle_matches_oracle(graph_target):
+    """The first cycle on a FRESH engine (graph capture warm-up included) drafts from [token, mask, mask, ...] exactly
+    as the reference does (model/dflash.py:233-235): acceptance lengths per cycle equal the oracle's. graph_target=None
+    is the default path (graphed target when capturable)."""
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from tests.tiny_models import TINY, draft_state_dict
+    target, draft = _tiny(16, rigged=True)
+    for seed in (11, 12):
+        prompt = torch.randint(0, TINY["vocab"] - 1, (1, 23), generator=torch.Generator().manual_seed(seed)).to(dev)
+        draft.release_engine()  # every prompt starts on a new engine (and a new draft graph)
+        out = draft.spec_generate(target, prompt, 48, None, 0.0, graph_target=graph_target)
+        ref, taus = O.spec_generate(draft_state_dict(draft), O.DraftConfig.from_hf(draft), target, prompt, 48, None, 0.0)
+        if torch.equal(out, ref):
+            assert draft.last_acceptance_lengths == taus, (draft.last_acceptance_lengths, taus)
+        else:  # a target near-tie: cycles shift, the first one cannot
+            assert draft.last_acceptance_lengths[0] == taus[0]
+        again = draft.spec_generate(target, prompt, 48, None, 0.0, graph_target=graph_target)
+        assert torch.equal(again, out)
+    draft.release_engine()
+
+
+def test_same_seed_same_samples_on_cached_engine():
+    """temperature > 0 with a given seed is reproducible on the cached engine (the Philox step restarts per request)."""
+    dev = _cuda()
+    from tests.tiny_models import TINY
+    target, draft = _tiny(16, rigged=True)
+    prompt = torch.randint(0, TINY["vocab"] - 1, (1, 19), generator=torch.Generator().manual_seed(5)).to(dev)
+    a = draft.spec_generate(target, prompt, 40, None, 1.0, seed=1234)
+    draft.spec_generate(target, prompt, 24, None, 1.0, seed=99)  # other work on the same engine in between
+    b = draft.spec_generate(target, prompt, 40, None, 1.0, seed=1234)
+    c = draft.spec_generate(target, prompt, 40, None, 1.0, seed=1235)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    draft.release_engine()
+
+
+def test_forward_with_callers_dynamic_cache_like_benchmark_loop():
+    """benchmark.py:60,122-129 owns a DynamicCache and calls draft.forward(...) / cache.crop(start) itself: the product
+    forward adopts the cache's length (the K/V rows stay in the engine) and returns what the oracle's forward returns."""
+    dev = _cuda()
+    from transformers import DynamicCache
+    from oracle import dflash_oracle as O
+    from tests.tiny_models import TINY, draft_state_dict
+    bs = 16
+    target, draft = _tiny(bs)
+    sd, cfg = draft_state_dict(draft), O.DraftConfig.from_hf(draft)
+    H, nsel = TINY["hidden"], len(draft.target_layer_ids)
+    g = torch.Generator().manual_seed(3)
+    cache_p, cache_o = DynamicCache(), O.DraftCache()
+    start = 0
+    for c in (21, 5, 16, 1):  # prompt-sized context first, then ragged accepted lengths
+        th = (torch.randn(1, c, nsel * H, generator=g) * 0.5).to(dev).to(torch.bfloat16)
+        noise = (torch.randn(1, bs, H, generator=g) * 0.1).to(dev).to(torch.bfloat16)
+        start += c
+        pos = torch.arange(cache_p.get_seq_length(), start + bs, device=dev).unsqueeze(0)
+        assert cache_p.get_seq_length() == cache_o.get_seq_length()
+        out = draft(target_hidden=th, noise_embedding=noise, position_ids=pos, past_key_values=cache_p, use_cache=True,
+                    is_causal=False)
+        ref = O.draft_forward(sd, cfg, th, noise, pos, cache_o)
+        assert cache_p.get_seq_length() == start + bs
+        assert _rel_err(out, ref) < REL_TOL
+        cache_p.crop(start)
+        cache_o.crop(start)
+    other = DynamicCache()
+    other.update(torch.zeros(1, 1, 3, 128, device=dev), torch.zeros(1, 1, 3, 128, device=dev), 0)
+    with pytest.raises(RuntimeError):
+        draft(target_hidden=th, noise_embedding=noise, position_ids=torch.arange(3, 3 + 1 + bs, device=dev).unsqueeze(0),
+              past_key_values=other, use_cache=True)
     draft.release_engine()

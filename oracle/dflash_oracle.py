@@ -158,8 +158,13 @@ class DraftCache:
 ATTN_IMPL = "eager"  # "sdpa" = F.scaled_dot_product_attention, what the reference dispatches to by default
 
 
-def _lin(x, w):
-    return F.linear(x, w)
+def _lin(x, w, b=None):
+    return F.linear(x, w, b)
+
+
+def _proj(sd, pfx, name, x):
+    """nn.Linear of the attention block; its bias exists iff config.attention_bias (model/dflash.py:41-50)."""
+    return _lin(x, sd[pfx + f"self_attn.{name}.weight"], sd.get(pfx + f"self_attn.{name}.bias"))
 
 
 def draft_attention(sd, pfx, cfg: DraftConfig, hidden, target_hidden, cos, sin, cache: Optional[DraftCache], layer):
@@ -167,12 +172,12 @@ def draft_attention(sd, pfx, cfg: DraftConfig, hidden, target_hidden, cos, sin, 
     bsz, q_len = hidden.shape[:-1]
     ctx_len = target_hidden.shape[1]
     D, Hq, Hkv = cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads
-    q = _lin(hidden, sd[pfx + "self_attn.q_proj.weight"]).view(bsz, q_len, -1, D)
+    q = _proj(sd, pfx, "q_proj", hidden).view(bsz, q_len, -1, D)
     q = rms_norm(q, sd[pfx + "self_attn.q_norm.weight"], cfg.rms_norm_eps).transpose(1, 2)
-    k_ctx = _lin(target_hidden, sd[pfx + "self_attn.k_proj.weight"])
-    k_noise = _lin(hidden, sd[pfx + "self_attn.k_proj.weight"])
-    v_ctx = _lin(target_hidden, sd[pfx + "self_attn.v_proj.weight"])
-    v_noise = _lin(hidden, sd[pfx + "self_attn.v_proj.weight"])
+    k_ctx = _proj(sd, pfx, "k_proj", target_hidden)
+    k_noise = _proj(sd, pfx, "k_proj", hidden)
+    v_ctx = _proj(sd, pfx, "v_proj", target_hidden)
+    v_noise = _proj(sd, pfx, "v_proj", hidden)
     k = torch.cat([k_ctx, k_noise], dim=1).view(bsz, ctx_len + q_len, -1, D)
     v = torch.cat([v_ctx, v_noise], dim=1).view(bsz, ctx_len + q_len, -1, D)
     k = rms_norm(k, sd[pfx + "self_attn.k_norm.weight"], cfg.rms_norm_eps).transpose(1, 2)
@@ -184,14 +189,14 @@ def draft_attention(sd, pfx, cfg: DraftConfig, hidden, target_hidden, cos, sin, 
         out = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False,
                                              scale=D ** -0.5, enable_gqa=True)
         out = out.transpose(1, 2).reshape(bsz, q_len, -1)
-        return _lin(out, sd[pfx + "self_attn.o_proj.weight"])
+        return _proj(sd, pfx, "o_proj", out)
     rep = Hq // Hkv
     kk = k.repeat_interleave(rep, dim=1)
     vv = v.repeat_interleave(rep, dim=1)
     scores = torch.matmul(q, kk.transpose(2, 3)) * (D ** -0.5)
     probs = torch.softmax(scores, dim=-1, dtype=torch.float32).to(q.dtype)
     out = torch.matmul(probs, vv).transpose(1, 2).reshape(bsz, q_len, -1)
-    return _lin(out, sd[pfx + "self_attn.o_proj.weight"])
+    return _proj(sd, pfx, "o_proj", out)
 
 
 def draft_forward(sd, cfg: DraftConfig, target_hidden, noise_embedding, position_ids,

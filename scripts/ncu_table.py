@@ -43,3 +43,17 @@ for r in data:
           f"{to_bytes(r, 'dram__bytes_write.sum') / 1e6:.2f} | {f(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
           f"{tens:.1f} | {f(r, 'launch__registers_per_thread'):.0f} | "
           f"{to_bytes(r, 'launch__shared_mem_per_block_dynamic') / 1e3:.1f} |")
+
+# --lm-json <path>: per-launch DRAM traffic of the lm_head GEMM (+ fused argmax) for bench.py's roofline.traffic
+if "--lm-json" in sys.argv:
+    import json
+    out = sys.argv[sys.argv.index("--lm-json") + 1]
+    lm = [r for r in data if re.search(r"gemm_skinny_kernel<\d+, 1>", r[col["Kernel Name"]])]
+    assert lm, "no lm_head GEMM (argmax mode) launch in this report"
+    tr = [to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum") for r in lm]
+    json.dump(dict(kernel="gemm_skinny_kernel<16,argmax> (lm_head)", launches=len(lm),
+                   dram_bytes_per_launch=sum(tr) / len(tr),
+                   dram_read_bytes=sum(to_bytes(r, "dram__bytes_read.sum") for r in lm) / len(lm),
+                   dram_write_bytes=sum(to_bytes(r, "dram__bytes_write.sum") for r in lm) / len(lm),
+                   duration_us_under_ncu=sum(to_us(r, "gpu__time_duration.sum") for r in lm) / len(lm),
+                   source="ncu --set full --clock-control none, " + rep.split("/")[-1]), open(out, "w"), indent=1)

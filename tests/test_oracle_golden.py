@@ -60,6 +60,28 @@ def test_draft_forward_matches_reference(golden, bs):
     torch.testing.assert_close(h1, g["h1"], rtol=2e-4, atol=2e-5)
 
 
+def test_attention_bias_matches_reference():
+    """config.attention_bias = True (model/dflash.py:41-50): biased q/k/v/o projections, forward with a live cache and a
+    whole greedy spec_generate, against vectors from the unmodified reference (tests/golden/make_bias_golden.py)."""
+    import os
+    from dflash_b200 import DFlashDraftModel
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_bias.pt"))
+    bs = 16
+    target, draft = build_pair(DFlashDraftModel, seed=1234, block_size=bs, attention_bias=True)
+    rig_lm_head(target, live=LIVE, seed=99)
+    assert fingerprint(target, draft) == g["fingerprint"], "seeded weights drifted from the golden run"
+    cfg, sd = O.DraftConfig.from_hf(draft), draft_state_dict(draft)
+    assert "layers.0.self_attn.q_proj.bias" in sd and "layers.1.self_attn.o_proj.bias" in sd
+    cache = O.DraftCache()
+    h0 = O.draft_forward(sd, cfg, g["th_old"], g["noise"], torch.arange(0, 5 + bs).unsqueeze(0), cache)
+    cache.crop(5)
+    h1 = O.draft_forward(sd, cfg, g["th_new"], g["noise"], torch.arange(5, 8 + bs).unsqueeze(0), cache)
+    torch.testing.assert_close(h0, g["h0"], rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(h1, g["h1"], rtol=2e-4, atol=2e-5)
+    out, taus = O.spec_generate(sd, cfg, target, g["prompt"], 48, None, 0.0)
+    assert out.tolist() == g["output"].tolist() == g["autoregressive"].tolist()
+
+
 def test_layer_ids_and_helpers():
     assert O.build_target_layer_ids(36, 5) == [1, 9, 17, 25, 33]
     assert O.build_target_layer_ids(36, 1) == [18]

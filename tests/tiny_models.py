@@ -22,9 +22,9 @@ def target_config(dims=TINY):
                        rope_parameters={"rope_type": "default", "rope_theta": dims["rope_theta"]})
 
 
-def draft_config(block_size=16, dims=TINY, target_layer_ids=None):
+def draft_config(block_size=16, dims=TINY, target_layer_ids=None, attention_bias=False):
     from transformers import Qwen3Config
-    cfg = Qwen3Config(vocab_size=dims["vocab"], hidden_size=dims["hidden"], intermediate_size=dims["intermediate"],
+    cfg = Qwen3Config(attention_bias=attention_bias, vocab_size=dims["vocab"], hidden_size=dims["hidden"], intermediate_size=dims["intermediate"],
                       num_hidden_layers=dims["draft_layers"], num_attention_heads=dims["heads"],
                       num_key_value_heads=dims["kv_heads"], head_dim=dims["head_dim"],
                       max_position_embeddings=dims["max_pos"], rms_norm_eps=dims["eps"],
@@ -44,20 +44,22 @@ def seeded_fill_(module_or_sd, seed: int):
     items = module_or_sd.items() if isinstance(module_or_sd, dict) else dict(module_or_sd.named_parameters()).items()
     with torch.no_grad():
         for name, p in sorted(items, key=lambda kv: kv[0]):
-            if p.dim() == 1:
+            if name.endswith(".bias"):
+                v = 0.1 * torch.randn(p.shape, generator=g)
+            elif p.dim() == 1:
                 v = 1.0 + 0.1 * torch.randn(p.shape, generator=g)
             else:
                 v = torch.randn(p.shape, generator=g) * (1.0 / (p.shape[-1] ** 0.5))
             p.copy_(v.to(p.dtype))
 
 
-def build_pair(draft_cls, seed=1234, block_size=16, dims=TINY, dtype=torch.float32, device="cpu"):
+def build_pair(draft_cls, seed=1234, block_size=16, dims=TINY, dtype=torch.float32, device="cpu", attention_bias=False):
     """(target HF Qwen3ForCausalLM, draft draft_cls) with seeded weights, eval mode."""
     from transformers import Qwen3ForCausalLM
     target = Qwen3ForCausalLM(target_config(dims))
-    draft = draft_cls(draft_config(block_size, dims))
+    draft = draft_cls(draft_config(block_size, dims, attention_bias=attention_bias))
     seeded_fill_(target, seed)
-    seeded_fill_(draft, seed + 1)
+    seeded_fill_(draft, seed + 1)  # (with attention_bias the q/k/v/o biases are ~N(0, 0.1^2))
     target = target.to(dtype=dtype, device=device).eval()
     draft = draft.to(dtype=dtype, device=device).eval()
     return target, draft

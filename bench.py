@@ -388,6 +388,31 @@ def full_cycle_bench(dims, draft, eng, embed, lm_head, device, ks, new_tokens=51
                                  wall_s=dt)
     out["speedup_vs_reference_loop"] = {k: out[k]["tokens_per_s"] / out["reference_loop"]["tokens_per_s"]
                                         for k in ("default", "eager_target", "graphed_target")}
+    # batched serving (BASELINE configs[2]-[4] shape): R request streams in one engine, ONE target verify forward per
+    # cycle for all of them (ragged static cache, CUDA graph); the reference's shape of the same work is one eager
+    # target call per request per cycle (graph_target=False), timed at R = 16 on a shorter generation
+    batched = {}
+    for R, n_new, graph in ((16, 256, "auto"), (64, 256, "auto"), (16, 48, False)):
+        gp = torch.Generator(device=device).manual_seed(40 + R)
+        prompts = [torch.randint(0, dims["vocab"] - 1, (1, PROMPT_LEN), device=device, generator=gp) for _ in range(R)]
+        fk = [ks[r % len(ks):] + ks[:r % len(ks)] for r in range(R)]  # every stream its own rotation of the schedule
+        draft.spec_generate_batch(target, prompts, 2 * dims["block_size"], None, 0.0, forced_k=fk, graph_target=graph)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        outs = draft.spec_generate_batch(target, prompts, n_new, None, 0.0, forced_k=fk, graph_target=graph,
+                                         sync_every=4 if graph else 1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n = sum(o.shape[1] - PROMPT_LEN for o in outs)
+        name = f"R{R}_" + ("batched_target" if graph else "per_request_eager_target")
+        batched[name] = dict(tokens_per_s=n / dt, new_tokens=n, streams=R, cycles=draft.last_batch_cycles,
+                             target_forwards=draft.last_batch_target_forwards if graph else draft.last_batch_cycles * R,
+                             ms_per_cycle=dt / max(1, draft.last_batch_cycles) * 1e3, wall_s=dt)
+        draft.release_engine()
+        torch.cuda.empty_cache()
+    batched["speedup_R16_batched_vs_per_request"] = (batched["R16_batched_target"]["tokens_per_s"] /
+                                                     batched["R16_per_request_eager_target"]["tokens_per_s"])
+    out["batched"] = batched
     out["note"] = ("prefill + decode wall clock of spec_generate, batch 1, random-init Qwen3-8B target (bf16, sdpa), "
                    "forced-tau schedule; the target forward is the caller's HF module in every row; `default` = what "
                    "spec_generate does without extra arguments (graphed target when capturable); reference_loop = the "
@@ -565,11 +590,11 @@ def run_cuda_arm(args):
     res_dev = torch.empty(2 + bs, dtype=torch.int64, device=device)
     h2d = stage_host.numel() * 2
     d2h = res_host.numel() * 8
-    # Two graphs (draft / verify) and a copy stream: the step's host inputs -- the target's logits and hidden states
-    # -- are only consumed by the verify half, so their H2D copy overlaps the draft half.
-    draft_graph, verify_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    # ONE graph per step: the H2D copy of the step's host inputs (pinned memory) forks onto a copy stream and joins in
+    # front of the verify half -- the target's logits and hidden states are only consumed there, so the copy overlaps
+    # the draft half -- and the D2H copy of the result is the graph's last node. Per step the host launches one graph
+    # and waits for it.
     copy_stream = torch.cuda.Stream(device=device)
-    copied = torch.cuda.Event()
 
     def verify_enqueue():
         eng.verify_step(tl_dev, hs_dev, temperature=0.0, forced_k=forced)
@@ -577,27 +602,27 @@ def run_cuda_arm(args):
         res_dev[1] = eng.buf["ctx_len"][0]
         res_dev[2:] = eng.posterior[0]
 
+    def whole_step():
+        cur = torch.cuda.current_stream()
+        copy_stream.wait_stream(cur)
+        with torch.cuda.stream(copy_stream):
+            stage_dev.copy_(stage_host, non_blocking=True)
+        eng.draft_step()
+        cur.wait_stream(copy_stream)
+        verify_enqueue()
+        res_host.copy_(res_dev, non_blocking=True)
+
     with torch.cuda.stream(side):
-        eng.draft_step()
-        verify_enqueue()
+        whole_step()
     torch.cuda.synchronize()
-    with torch.cuda.graph(draft_graph, stream=side):
-        eng.draft_step()
-    with torch.cuda.graph(verify_graph, stream=side):
-        verify_enqueue()
+    step_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(step_graph, stream=side):
+        whole_step()
     torch.cuda.synchronize()
 
     def e2e_step():
-        main = torch.cuda.current_stream()
-        copy_stream.wait_stream(main)  # the previous step's verify has consumed tl_dev / hs_dev
-        with torch.cuda.stream(copy_stream):
-            stage_dev.copy_(stage_host, non_blocking=True)
-            copied.record(copy_stream)
-        draft_graph.replay()
-        main.wait_event(copied)
-        verify_graph.replay()
-        res_host.copy_(res_dev, non_blocking=True)
-        main.synchronize()  # the caller reads the accepted length every cycle
+        step_graph.replay()
+        torch.cuda.current_stream().synchronize()  # the caller reads the accepted length every cycle
         return int(res_host[1])
 
     do_reset()

@@ -3,10 +3,11 @@
 The reference decodes one prompt at a time; its "batched" harness (`benchmark_batched.py`) only keeps several
 batch-1 decodes in flight. Here up to 64 request streams live in ONE engine: every cycle the draft step, the
 posterior sampling, the acceptance / commit and the context gather run once for all of them (one weight stream,
-ragged acceptance lengths kept as device state), while the target stays the caller's HF module and is called per
-request exactly as the reference calls it (`model/dflash.py:218-225,249-255`) -- a batched ragged target forward
-is a property of the target's runtime, not of this path. A finished request's slot is refilled with the next
-prompt (its prompt pass does not disturb the streams that are mid-generation).
+ragged acceptance lengths kept as device state). The target stays the caller's unmodified HF module; by default its
+verify forward (`model/dflash.py:249-255`) also runs ONCE per cycle for all streams (`BatchedVerifyTarget`: per-row
+positions, a 4-D mask and a ragged static KV cache derived from the engine's device-side `start[r]`, replayed from a
+CUDA graph), `graph_target=False` calls it per request exactly as the reference does. A finished request's slot is
+refilled with the next prompt (its prompt pass does not disturb the streams that are mid-generation).
 
 Results per prompt obey the same contract as `spec_generate`: `LongTensor[1, P + n_out]`, ends at the first stop
 token, mask ids removed; greedy outputs are the target's own greedy continuation.
@@ -27,15 +28,18 @@ def spec_generate_batch(draft, target, prompts: Sequence[torch.Tensor], max_new_
                         stop_token_ids: Optional[List[int]], temperature: float, *, max_requests: Optional[int] = None,
                         clamp_tail: bool = False, forced_k: Optional[Sequence[Sequence[int]]] = None,
                         seed: Optional[int] = None, noise_fn: Optional[Callable[[int], torch.Tensor]] = None,
-                        graph_target: bool = False, sync_every: int = 1) -> List[torch.Tensor]:
+                        graph_target="auto", sync_every: int = 1) -> List[torch.Tensor]:
     """prompts: LongTensor[1, P_i] each (ragged). Returns one LongTensor[1, P_i + n_i] per prompt, in order.
 
     max_requests: request streams resident in the engine (<= 64; default: enough for all prompts).
     forced_k[i]: harness hook, per-prompt forced-acceptance schedule. noise_fn(cycle) -> fp32
     [R * block_size, V] Exp(1) draws for the posterior race at temperature > 0 (tests); otherwise Philox(seed).
-    graph_target: every slot replays the (unmodified) target's verify forward from its own CUDA graph over a static
-    KV cache whose length is the engine's device-side `start[r]` (`target_graph.py`); the host
-    then only polls `start` / `done` every `sync_every` cycles (finished streams are frozen on the device meanwhile).
+    graph_target ("auto" | True | False): unless False, the (unmodified) target's verify forward runs once per cycle for
+    ALL streams over a ragged static KV cache whose per-stream lengths are the engine's device-side `start[r]`
+    (`target_graph.BatchedVerifyTarget`), replayed from a CUDA graph when the target can be captured; the host then
+    only polls `start` / `done` every `sync_every` cycles (finished streams are frozen on the device meanwhile).
+    "auto" falls back to the per-request eager calls for targets the batched forward does not cover (sliding-window
+    layers); False always uses them. `draft.last_batch_target_forwards` = verify forwards issued.
     Side effect: `draft.last_batch_acceptance_lengths[i]` = tau per cycle of prompt i."""
     draft.eval()
     n = len(prompts)
@@ -51,14 +55,27 @@ def spec_generate_batch(draft, target, prompts: Sequence[torch.Tensor], max_new_
         if p.dim() != 2 or p.shape[0] != 1:
             raise RuntimeError("spec_generate_batch: every prompt is a LongTensor[1, P]")
     max_len_all = Pmax + max_new_tokens
-    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight,
-                      max_seq=max_len_all + 2 * bs + 1, out_len=max_len_all + bs + 1, max_requests=R, block_size=bs,
-                      device=dev)
-    try:
-        return _run(draft, target, eng, list(prompts), max_new_tokens, stop_token_ids, temperature, clamp_tail,
-                    forced_k, seed, noise_fn, graph_target, max(1, int(sync_every)), max_len_all + bs)
-    finally:
+    eng = _batch_engine(draft, target, R, bs, max_len_all, dev)
+    return _run(draft, target, eng, list(prompts), max_new_tokens, stop_token_ids, temperature, clamp_tail,
+                forced_k, seed, noise_fn, graph_target, max(1, int(sync_every)), max_len_all + 2 * bs)
+
+
+def _batch_engine(draft, target, R: int, bs: int, max_len_all: int, dev) -> DraftEngine:
+    """The engine of the previous call is reused when it fits (same target weights, stream count, block size, and at
+    least this capacity): a serving loop calls spec_generate_batch many times. `draft.release_engine()` drops it."""
+    key = (target.model.embed_tokens.weight.data_ptr(), target.lm_head.weight.data_ptr(), R, bs, str(dev))
+    cached = getattr(draft, "_batch_engine_cache", None)
+    if cached is not None:
+        k, eng, _ = cached
+        if k == key and eng.max_seq >= max_len_all + 2 * bs + 1 and eng.handle.value:
+            return eng
         eng.close()
+        draft._batch_engine_cache = None
+    cap = max(1024, 1 << (max_len_all + 2 * bs).bit_length())
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=cap + 1, out_len=cap + 1,
+                      max_requests=R, block_size=bs, device=dev)
+    draft._batch_engine_cache = (key, eng, {})
+    return eng
 
 
 def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_ids, temperature, clamp_tail, forced_k,
@@ -88,19 +105,24 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
     state = torch.empty(2, R, dtype=torch.int32).pin_memory()
     state_dev = torch.empty(2, R, dtype=torch.int32, device=dev)
     next_req = 0
-    gts = [None] * R          # graph_target: one graphed target + static cache per slot
+    bt = None                 # one batched verify forward per cycle for all streams
     if graph_target:
-        from .target_graph import GraphedVerifyTarget
-        cap = max(1024, 1 << (int(cache_len) - 1).bit_length())
-        for r in range(R):
-            gts[r] = GraphedVerifyTarget(target, bs, cap, layer_ids, eng.buf["start"][r:r + 1], eng.block_ids[r:r + 1])
+        from .target_graph import BatchedVerifyTarget
+        try:
+            bt = _batched_target(draft, target, eng, int(cache_len), layer_ids)
+        except NotImplementedError:
+            if graph_target != "auto":
+                raise
+    graph_target = bt is not None
+    since_sync = 0
+    fwd0 = bt.n_forwards if bt is not None else 0
 
     def admit(r: int, i: int):
         ids = prompts[i].to(dev)
         P = ids.shape[1]
         cache = None
         if graph_target:
-            logits0, hidden0 = gts[r].prefill(ids)
+            logits0, hidden0 = bt.prefill(r, ids)
         else:
             cache = DynamicCache()
             with tap:
@@ -141,11 +163,10 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
         if not live:
             break
         eng.draft_step_graphed()
-        for r in live if graph_target else ():  # static graphs: positions / cache length come from start[r] on the device
-            logits, hidden = gts[r].verify_forward()
-            tl[r * bs: (r + 1) * bs] = logits
-            for s in range(nsel):
-                hs[s][r * bs: (r + 1) * bs] = hidden[s]
+        tl_c, hs_c = tl, hs
+        if graph_target:  # positions, mask and cache lengths come from start[r] on the device; the host only bounds them
+            since_sync += 1
+            tl_c, hs_c = bt.verify_forward(max(slot_start[r] for r in live) + bs * since_sync)
         for r in () if graph_target else live:  # the caller's target, per request, exactly as the reference calls it
             start = slot_start[r]
             eff = min(bs, slot_P[r] + max_new_tokens - start) if clamp_tail else bs
@@ -157,11 +178,12 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
             for s in range(nsel):
                 hs[s][r * bs: r * bs + eff] = tap.states[s][0]
         noise = noise_fn(cycle) if (noise_fn is not None and temperature >= 1e-5) else None
-        eng.verify_step(tl, hs, temperature=temperature, noise=noise, seed=seed, stop_ids=stop_t, forced_k=forced_t,
+        eng.verify_step(tl_c, hs_c, temperature=temperature, noise=noise, seed=seed, stop_ids=stop_t, forced_k=forced_t,
                         clamp_tail=clamp_tail)
         cycle += 1
         if graph_target and cycle % sync_every != 0:
             continue  # nothing on the host depends on this cycle's outcome
+        since_sync = 0
         # the one host sync of the cycle: the HF target caches need every stream's new length
         state_dev[0].copy_(eng.buf["start"])
         state_dev[1].copy_(eng.buf["done"])
@@ -174,4 +196,19 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
             if int(state[1, r]):
                 harvest(r)
     draft.last_batch_acceptance_lengths = taus
+    draft.last_batch_target_forwards = bt.n_forwards - fwd0 if bt is not None else None
+    draft.last_batch_cycles = cycle
     return results
+
+
+def _batched_target(draft, target, eng: DraftEngine, cache_len: int, layer_ids):
+    """The batched verify target lives with the cached engine (its graphs hold the engine's buffers)."""
+    from .target_graph import BatchedVerifyTarget
+    cached = getattr(draft, "_batch_engine_cache", None)
+    store = cached[2] if cached is not None and cached[1] is eng else {}
+    bt = store.get("bt")
+    if bt is None or bt.target is not target or bt.max_cache_len < cache_len or bt.R != eng.R:
+        bt = BatchedVerifyTarget(target, eng.block_size, eng.R, max(cache_len, eng.max_seq), layer_ids, eng.buf["start"],
+                                 eng.block_ids)
+        store["bt"] = bt
+    return bt

@@ -46,27 +46,40 @@ __device__ __forceinline__ void posterior_body(const PosteriorArgs& a, int row, 
     if (key > bv) { bv = key; bi = col; }
   };
   if (vec_ok) {
-    for (int c = c0 + threadIdx.x * 8; c < c1; c += 256 * 8) {
-      uint32_t rnd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (!greedy && a.noise == nullptr) {
-        philox4x32(static_cast<uint32_t>(c), static_cast<uint32_t>(row), static_cast<uint32_t>(step),
-                   static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(a.seed),
-                   static_cast<uint32_t>(a.seed >> 32), rnd);
-        philox4x32(static_cast<uint32_t>(c + 4), static_cast<uint32_t>(row), static_cast<uint32_t>(step),
-                   static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(a.seed),
-                   static_cast<uint32_t>(a.seed >> 32), rnd + 4);
-      }
-      if (c + 8 <= c1) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(lp + c);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    // kU 128-bit loads in flight per thread: at 64 streams this pass reads 311 MB of logits (one load per iteration
+    // left it at 2.3 TB/s). Columns are still visited in ascending order per thread (ties keep the lowest index).
+    constexpr int kU = 4;
+    for (int cb = c0 + threadIdx.x * 8; cb < c1; cb += 256 * 8 * kU) {
+      uint4 raw[kU];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          consider(f.x, c + 2 * j, rnd[2 * j]);
-          consider(f.y, c + 2 * j + 1, rnd[2 * j + 1]);
+      for (int u = 0; u < kU; ++u) {
+        const int c = cb + u * 256 * 8;
+        if (c + 8 <= c1) raw[u] = *reinterpret_cast<const uint4*>(lp + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int c = cb + u * 256 * 8;
+        if (c >= c1) break;
+        uint32_t rnd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (!greedy && a.noise == nullptr) {
+          philox4x32(static_cast<uint32_t>(c), static_cast<uint32_t>(row), static_cast<uint32_t>(step),
+                     static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(a.seed),
+                     static_cast<uint32_t>(a.seed >> 32), rnd);
+          philox4x32(static_cast<uint32_t>(c + 4), static_cast<uint32_t>(row), static_cast<uint32_t>(step),
+                     static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(a.seed),
+                     static_cast<uint32_t>(a.seed >> 32), rnd + 4);
         }
-      } else {
-        for (int j = 0; c + j < c1; ++j) consider(__bfloat162float(lp[c + j]), c + j, rnd[j]);
+        if (c + 8 <= c1) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            consider(f.x, c + 2 * j, rnd[2 * j]);
+            consider(f.y, c + 2 * j + 1, rnd[2 * j + 1]);
+          }
+        } else {
+          for (int j = 0; c + j < c1; ++j) consider(__bfloat162float(lp[c + j]), c + j, rnd[j]);
+        }
       }
     }
   } else {

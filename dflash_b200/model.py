@@ -129,9 +129,15 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
         return self._engine
 
     def release_engine(self):
+        """Drop the cached engines (single-stream and batched), their CUDA graphs and the graphed targets."""
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+        cached = getattr(self, "_batch_engine_cache", None)
+        if cached is not None:
+            cached[1].close()
+            self._batch_engine_cache = None
+        self._graphed_target = None
 
     # ------------------------------------------------------------------------------------------
     def forward(self, position_ids: torch.LongTensor, attention_mask: Optional[torch.Tensor] = None,

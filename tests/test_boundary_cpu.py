@@ -252,3 +252,53 @@ def test_shipped_library_has_no_result_changing_switches():
     src = "".join(open(os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", f)).read()
                   for f in os.listdir(os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc")))
     assert "getenv" not in src
+
+
+def test_batched_ragged_target_forward_equals_per_request_forwards():
+    """`BatchedVerifyTarget` (one verify forward for all streams: per-row positions, 4-D mask and a ragged static KV cache
+    from start[r]) against the reference's per-request calls with a DynamicCache + crop (model/dflash.py:249-255,262),
+    over three cycles with ragged acceptance lengths. Eager on CPU here; the GPU tests replay the same forward from a
+    CUDA graph."""
+    import torch
+    from transformers import DynamicCache
+    from dflash_b200 import DFlashDraftModel
+    from dflash_b200.target_graph import BatchedVerifyTarget
+    from dflash_b200.utils import ContextTap
+    from tests.tiny_models import TINY, build_pair
+    bs, R = 8, 3
+    target, draft = build_pair(DFlashDraftModel, seed=1234, block_size=bs)
+    layer_ids = draft.target_layer_ids
+    g = torch.Generator().manual_seed(5)
+    lens = [5, 21, 12]
+    prompts = [torch.randint(0, TINY["vocab"] - 1, (1, n), generator=g) for n in lens]
+    start = torch.tensor(lens, dtype=torch.int32)
+    block_ids = torch.randint(0, TINY["vocab"] - 1, (R, bs), generator=g)
+    bt = BatchedVerifyTarget(target, bs, R, 96, layer_ids, start, block_ids, bucket=32, use_graph=False)
+    caches = []
+    with torch.inference_mode():
+        for r in range(R):
+            logits0, hidden0 = bt.prefill(r, prompts[r])
+            c = DynamicCache()
+            with ContextTap(target, layer_ids) as tap:
+                ref0 = target(prompts[r], position_ids=torch.arange(lens[r]).unsqueeze(0), past_key_values=c,
+                              use_cache=True, logits_to_keep=1)
+            torch.testing.assert_close(logits0, ref0.logits)
+            for a, b in zip(hidden0, tap.states):
+                torch.testing.assert_close(a, b)
+            caches.append(c)
+        for cyc, acc in enumerate([(3, 8, 1), (8, 1, 5), (2, 2, 2)]):
+            max_end = int(start.max()) + bs
+            logits, hidden = bt.verify_forward(max_end)
+            assert bt.cache.kv_len == -(-max_end // 32) * 32 and logits.shape == (R * bs, TINY["vocab"])
+            for r in range(R):
+                s0 = int(start[r])
+                with ContextTap(target, layer_ids) as tap:
+                    ref = target(block_ids[r:r + 1], position_ids=torch.arange(s0, s0 + bs).unsqueeze(0),
+                                 past_key_values=caches[r], use_cache=True)
+                torch.testing.assert_close(logits[r * bs:(r + 1) * bs], ref.logits[0], rtol=1e-4, atol=1e-4)
+                for a, b in zip(hidden, tap.states):
+                    torch.testing.assert_close(a[r * bs:(r + 1) * bs], b[0], rtol=1e-4, atol=1e-4)
+                caches[r].crop(s0 + acc[r])           # the reference's rollback ...
+            start += torch.tensor(acc, dtype=torch.int32)  # ... is only the length here
+            block_ids.copy_(torch.randint(0, TINY["vocab"] - 1, (R, bs), generator=g))
+    assert bt.n_forwards == 3

@@ -106,7 +106,8 @@ inline size_t layout_workspace(const dflash_config_t& c, Region* reg, int sm_cou
   // gate/up GEMM (SwiGLU epilogue): one [128 x mb] fp32 partial tile per CTA (groups * ranges <= grid CTAs) and one
   // arrival counter per (column group, tile) per layer
   const long long part_elems = static_cast<long long>(grid) * kTileN * round_mb(RS);
-  const long long n_flags = static_cast<long long>(c.n_layers) * (I / (kTileN / 2)) * groups_of(RS);
+  // (+ the context-injection kernel's two CTA counters)
+  const long long n_flags = static_cast<long long>(c.n_layers) * (I / (kTileN / 2)) * groups_of(RS) + 2;
   size_t sz[DFLASH_BUF_COUNT] = {0};
   sz[DFLASH_BUF_X] = static_cast<size_t>(RSp) * H * 2;
   sz[DFLASH_BUF_A_IN] = static_cast<size_t>(RS2p) * H * 2;
@@ -267,9 +268,34 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   } while (0)
   // activation TMA tensors are declared with the buffers' padded row counts (a multiple of the UMMA width), so a box
   // never leaves the allocation; rows past the live ones are zero and their outputs are never used.
+  // context injection (dflash.py:177) + block embedding + layer 0's input_layernorm: ONE kernel (kModeCtxNorm)
+  // (its CTAs wait for each other: never more of them than SMs)
   DFL_PLAN(make_gemm_plan(&e->fc, w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_CTX_FEAT), RSp, 0, mb_blk, RS,
-                          kModePartials, e->grid));
+                          kModeCtxNorm, e->grid < sm_count ? e->grid : sm_count));
   finish(e->fc);
+  {
+    CtxNormEpi& cn = e->fc.args.cn;
+    cn.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
+    cn.ld = H;
+    cn.norm_w = static_cast<const __nv_bfloat16*>(w.hidden_norm);
+    if ((e->flags_used + 2) * 4 > e->reg[DFLASH_BUF_FLAGS].bytes) {
+      set_error("internal: flag region too small");
+      delete e;
+      return DFLASH_ERR_ARG;
+    }
+    cn.sync = e->buf<unsigned int>(DFLASH_BUF_FLAGS) + e->flags_used;
+    e->flags_used += 2;
+    cn.ctx_len = e->buf<int>(DFLASH_BUF_CTX_LEN);
+    cn.SL = e->SL;
+    cn.eps = c.rms_eps;
+    cn.ids_ld = e->bs;
+    cn.bs = e->bs;
+    cn.n_blk_rows = RS;
+    cn.pad_token = c.mask_token_id;
+    cn.resid = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
+    cn.ln_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
+    cn.blk_out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN) + static_cast<size_t>(RS) * H;
+  }
   e->qkv.resize(e->L); e->kv_pf.resize(e->L * 5); e->o.resize(e->L); e->gu.resize(e->L); e->d.resize(e->L);
   for (int i = 0; i < 5; ++i) {
     DFL_PLAN(make_gemm_plan(&e->fc_pf[i], w.fc, H, 0, H, e->nsel * H, e->buf<void>(DFLASH_BUF_PF_FEAT), kPrefillRows, 0,
@@ -334,14 +360,11 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "attn smem attribute"); }
   ce = cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize smem attribute"); }
-  ce = cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 6);
-  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "finalize2 smem attribute"); }
   // One shared-memory carveout for every kernel of the step: consecutive kernels with different L1/smem splits
   // cannot share an SM, which would serialise exactly the PDL overlaps the schedule relies on.
   {
     const int mx = cudaSharedmemCarveoutMaxShared;
     cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(finalize_rows2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(finalize_rows_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
@@ -400,17 +423,6 @@ inline cudaError_t launch_finalize(Engine* e, const RowsArgs& a, int rows, cudaS
   return launch_pdl(finalize_rows_kernel, dim3(rows), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a);
 }
 
-// fc GEMM + hidden_norm over the pending context rows -> a_in rows [0, RS)   (dflash.py:177)
-inline RowsArgs ctx_finalize_args(Engine* e) {
-  RowsArgs a = rows_args_base(e);
-  a.ws = e->fc.args.ws;
-  a.sm = slot_map_of(e->fc);
-  a.valid_mode = kRowsCtx;
-  a.norm_w = static_cast<const __nv_bfloat16*>(e->w.hidden_norm);
-  a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  return a;
-}
-
 inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_only) {
   QkvPostArgs a;
   memset(&a, 0, sizeof(a));
@@ -441,8 +453,8 @@ inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_on
 }
 
 // One draft step: ctx injection -> block embedding -> L layers -> final norm -> lm_head + argmax.
-// Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247). 2 + 9 L + 1 launches:
-//   fc GEMM           row kernel [hidden_norm of the ctx rows | embed + ln1 of the block]
+// Writes the drafted tokens into block_ids[:, 1:bs]  (dflash.py:235-247). 1 + 9 L + 1 launches:
+//   fc GEMM [epilogue: hidden_norm of the ctx rows | embed + ln1 of the block]
 //   per layer: qkv GEMM - qkv_post [q/k norm, RoPE, cache write] - attention split - merge - o GEMM -
 //              row kernel [+ residual, ln2] - gate/up GEMM [SwiGLU epilogue] - down GEMM - row kernel [+ residual, norm]
 //   lm_head GEMM [argmax; its last CTA reduces the candidates to the drafted tokens]
@@ -453,27 +465,19 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
   const int RS = e->RS;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
-  // ctx injection GEMM first (it only reads the features gathered by the previous verify step), then ONE row kernel
-  // for both the context finalize (fc -> hidden_norm -> a_in ctx rows) and the block rows
-  // (embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows)
-  DFL_CUDA(launch_gemm(e->fc, st, e->pdl), "fc gemm");
+  // Context injection as ONE kernel: the fc GEMM over the features gathered by the previous verify step finishes its
+  // tiles in its own epilogue (bf16 + hidden_norm -> a_in ctx rows), and its epilogue warps also do the block rows
+  // (embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows) before their first tile
   {
-    RowsArgs a = rows_args_base(e);
+    GemmPlan fc = e->fc;
     if (noise_embedding != nullptr) {
-      a.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
-      a.ids = nullptr;
+      fc.args.cn.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
+      fc.args.cn.ids = nullptr;
     } else {
-      a.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
-      a.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+      fc.args.cn.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
+      fc.args.cn.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
     }
-    a.ids_ld = e->bs;
-    a.pad_token = e->cfg.mask_token_id;
-    a.resid = x;
-    a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
-    a.out = a_in + static_cast<size_t>(RS) * e->H;
-    const RowsArgs c = ctx_finalize_args(e);
-    DFL_CUDA(launch_pdl(finalize_rows2_kernel, dim3(2 * RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st,
-                        e->pdl, c, a, RS), "ctx finalize + embed + ln1");
+    DFL_CUDA(launch_gemm(fc, st, e->pdl), "context injection (fc gemm + hidden_norm + embed + ln1)");
   }
   AttnArgs aa;
   memset(&aa, 0, sizeof(aa));

@@ -1,9 +1,14 @@
-// The row-wise epilogue that runs INSIDE the streaming GEMM (gemm_skinny.cuh, kModeSwiglu) on a finished output tile
-// staged in shared memory as tile[m][n] (m = activation row, n = column inside the tile), one warp per activation
-// row: SwiGLU with the reference's bf16 rounding points, written as the down projection's bf16 operand, so the
-// widest fp32 plane of the step (gate/up: 2 x intermediate columns) never reaches HBM.
-// (The same treatment of fc / qkv / o / down was built and measured slower than consumer kernels at every batch
-// width -- DESIGN.md section 7 -- because only a tile's finishing CTA does the row work.)
+// The row-wise epilogues that run INSIDE the streaming GEMM (gemm_skinny.cuh) on a finished output tile staged in
+// shared memory as tile[m][n] (m = activation row, n = column inside the tile), one warp per activation row:
+//   kModeSwiglu   SwiGLU with the reference's bf16 rounding points, written as the down projection's bf16 operand, so
+//                 the widest fp32 plane of the step (gate/up: 2 x intermediate columns) never reaches HBM;
+//   kModeCtxNorm  the target-context injection (model/dflash.py:177, hidden_norm(fc(target_hidden))) as ONE kernel: the
+//                 block rows' embedding gather + first input_layernorm (model/dflash.py:237, layer 0) on the epilogue
+//                 warps while they are idle, and after the main loop a device-wide arrival count over the CTAs'
+//                 split-K partials followed by the row pass (sum -> bf16 -> hidden_norm) on the CTAs themselves.
+// (The same treatment of qkv / o / down was built and measured slower than consumer kernels at every batch width --
+// DESIGN.md section 7 -- because only a tile's finishing CTA does the row work and the last tile's epilogue is exposed
+// at the end of every GEMM.)
 #pragma once
 #include "ptx.cuh"
 
@@ -44,6 +49,136 @@ __device__ __forceinline__ void swiglu_epi_apply(const SwigluEpi& e, const float
   const float2 u = *reinterpret_cast<const float2*>(tile_row + 64 + 2 * lane);
   const __nv_bfloat162 o = __floats2bfloat162_rn(silu_mul_bf16(g.x, u.x), silu_mul_bf16(g.y, u.y));
   *reinterpret_cast<__nv_bfloat162*>(e.out + static_cast<long long>(row) * e.ld + tile * 64 + 2 * lane) = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Context injection: hidden_norm(fc(target_hidden)) -> a_in context rows; embed_tokens(block) -> x, ln1 -> a_in block rows
+struct CtxNormEpi {
+  __nv_bfloat16* out;            // [rows][ld] a_in context rows
+  long long ld;                  // hidden size
+  const __nv_bfloat16* norm_w;   // hidden_norm.weight [H]
+  unsigned int* sync;            // [2]: CTAs whose partials are stored; CTAs that are past the wait (self-resetting)
+  const int* ctx_len;            // [R]: context row (r, j) is live iff j < ctx_len[r]
+  int SL;
+  float eps;
+  // block rows (n_blk_rows = R * SL; row i of request r is token ids[r * ids_ld + i], pad_token past bs)
+  const __nv_bfloat16* embed;    // embedding matrix [V][H], or (ids == null) already-embedded rows [n_blk_rows][H]
+  const long long* ids;
+  int ids_ld, bs, n_blk_rows;
+  long long pad_token;
+  __nv_bfloat16* resid;          // [n_blk_rows][H] residual stream (written)
+  const __nv_bfloat16* ln_w;     // layers[0].input_layernorm.weight
+  __nv_bfloat16* blk_out;        // [n_blk_rows][H]
+};
+
+// Context row `row` on all NT threads of the CTA, after every CTA's split-K partials are in `ws`:
+//   v = bf16(sum of the partial slots, in slot order)      (nn.Linear output dtype)
+//   out = w * bf16(v * rsqrt(mean(v^2) + eps))              (Qwen3RMSNorm, fp32 inside)
+// ns_tab[t] = partial slots of column tile t; rowbuf: H floats of shared memory (the idle TMA pipeline); red: NT / 32
+// floats of shared memory.
+template <int NT>
+__device__ __forceinline__ void ctxnorm_row_pass(const CtxNormEpi& e, const float* __restrict__ ws, long long slot_stride,
+                                                 long long ws_ld, int row, int tid, const int* ns_tab, float* rowbuf,
+                                                 float* red) {
+  const int H = static_cast<int>(e.ld);
+  constexpr int kBatch = 3;  // column groups whose slot loads are in flight together (these are L2 round trips)
+  constexpr int kSlots = 6;  // slots loaded up front (fc at Qwen3-8B dims: a tile spans <= 6 CTAs); more are added after
+  float ss = 0.f;
+  for (int n0 = tid * 4; n0 < H; n0 += NT * 4 * kBatch) {
+    float4 p[kBatch][kSlots];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int n = n0 + b * NT * 4;
+      if (n < H) {
+        const int ns = ns_tab[n >> 7];
+        const float* src = ws + static_cast<long long>(row) * ws_ld + n;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s)
+          if (s < ns) p[b][s] = __ldcg(reinterpret_cast<const float4*>(src + s * slot_stride));
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int n = n0 + b * NT * 4;
+      if (n < H) {
+        const int ns = ns_tab[n >> 7];
+        const float* src = ws + static_cast<long long>(row) * ws_ld + n;
+        float4 acc = p[b][0];
+#pragma unroll
+        for (int s = 1; s < kSlots; ++s)
+          if (s < ns) { acc.x += p[b][s].x; acc.y += p[b][s].y; acc.z += p[b][s].z; acc.w += p[b][s].w; }
+        for (int s = kSlots; s < ns; ++s) {
+          const float4 q = __ldcg(reinterpret_cast<const float4*>(src + s * slot_stride));
+          acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        acc.x = bf16_round(acc.x); acc.y = bf16_round(acc.y); acc.z = bf16_round(acc.z); acc.w = bf16_round(acc.w);
+        *reinterpret_cast<float4*>(rowbuf + n) = acc;
+        ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  __syncthreads();  // red[] of the previous row has been consumed
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) tot += red[w];
+  const float rstd = 1.0f / sqrtf(tot / static_cast<float>(H) + e.eps);
+  for (int n = tid * 4; n < H; n += NT * 4) {  // (each thread re-reads exactly what it wrote)
+    const float4 x = *reinterpret_cast<const float4*>(rowbuf + n);
+    const float4 w = unpack4_bf16(*reinterpret_cast<const uint2*>(e.norm_w + n));
+    *reinterpret_cast<uint2*>(e.out + static_cast<long long>(row) * e.ld + n) =
+        pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
+                   w.w * bf16_round(x.w * rstd));
+  }
+}
+
+// Block row `row` on the 128 epilogue threads: embedding gather -> residual stream; input_layernorm -> blk_out.
+// red: 4 floats of shared memory; named barrier 1 (the epilogue warps' barrier).
+constexpr int kEmbedMaxIt = 16;  // hidden <= 8192
+__device__ __forceinline__ void ctxnorm_embed_row(const CtxNormEpi& e, int row, int tid, float* red) {
+  const int H = static_cast<int>(e.ld);
+  long long tok = row;  // ids == null: `embed` already holds this row
+  if (e.ids != nullptr) {
+    const int r = row / e.SL, i = row % e.SL;
+    tok = (i < e.bs) ? e.ids[static_cast<long long>(r) * e.ids_ld + i] : e.pad_token;
+  }
+  const __nv_bfloat16* src = e.embed + tok * H;
+  const long long roff = static_cast<long long>(row) * H;
+  uint2 v[kEmbedMaxIt];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < kEmbedMaxIt; ++k) {
+    const int n = tid * 4 + k * 512;
+    if (n < H) v[k] = *reinterpret_cast<const uint2*>(src + n);
+  }
+#pragma unroll
+  for (int k = 0; k < kEmbedMaxIt; ++k) {
+    const int n = tid * 4 + k * 512;
+    if (n < H) {
+      *reinterpret_cast<uint2*>(e.resid + roff + n) = v[k];
+      const float4 x = unpack4_bf16(v[k]);
+      ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+  }
+  ss = warp_sum(ss);
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");  // red[] of the previous row has been consumed
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
+  const float tot = red[0] + red[1] + red[2] + red[3];
+  const float rstd = 1.0f / sqrtf(tot / static_cast<float>(H) + e.eps);
+#pragma unroll
+  for (int k = 0; k < kEmbedMaxIt; ++k) {
+    const int n = tid * 4 + k * 512;
+    if (n < H) {
+      const float4 x = unpack4_bf16(v[k]);
+      const float4 w = unpack4_bf16(*reinterpret_cast<const uint2*>(e.ln_w + n));
+      *reinterpret_cast<uint2*>(e.blk_out + roff + n) =
+          pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
+                     w.w * bf16_round(x.w * rstd));
+    }
+  }
 }
 
 }  // namespace dfl

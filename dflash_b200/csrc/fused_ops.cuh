@@ -358,25 +358,6 @@ __global__ void __launch_bounds__(kRowClThreads) finalize_rows_cluster_kernel(co
   DFL_TRACE(2);
 }
 
-// Two independent row passes in one launch (CTAs [0, rows0) run a0, the rest run a1): the step's first small
-// kernel does both the context finalize (fc -> hidden_norm) and the block embedding + first input_layernorm.
-__global__ void __launch_bounds__(kRowsThreads) finalize_rows2_kernel(const RowsArgs a0, const RowsArgs a1,
-                                                                     const int rows0) {
-  extern __shared__ __align__(16) float rowbuf[];
-  __shared__ float red[kRowsThreads / 32];
-  __shared__ int ns_tab[kRowsMaxTiles];
-  const bool first = static_cast<int>(blockIdx.x) < rows0;
-  const RowsArgs& a = first ? a0 : a1;
-  if (a.embed == nullptr) {
-    const int nt = (a.H + kTileN - 1) / kTileN;
-    for (int t = threadIdx.x; t < nt; t += kRowsThreads) ns_tab[t] = tile_slots32(t, a.sm);
-  }
-  __syncthreads();
-  DFL_WAIT_THEN_TRIGGER();
-  finalize_row_body<kRowsThreads, true>(a, first ? blockIdx.x : blockIdx.x - rows0, threadIdx.x, rowbuf, red, ns_tab, 0);
-  DFL_TRACE(2);
-}
-
 // ---------------------------------------------------------------------------------------------
 // QKV post-processing: per (row, head) warp. q/k: per-head RMSNorm over D=128 then RoPE
 // (half-split rotate, cos/sin rounded to bf16, products and sum rounded to bf16:

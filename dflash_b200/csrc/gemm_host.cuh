@@ -111,6 +111,7 @@ inline cudaError_t launch_gemm_any_mb(const GemmPlan& p, cudaStream_t stream, bo
 
 inline cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t stream, bool pdl) {
   if (p.mode == kModeSwiglu) return launch_gemm_any_mb<kModeSwiglu>(p, stream, pdl);
+  if (p.mode == kModeCtxNorm) return launch_gemm_any_mb<kModeCtxNorm>(p, stream, pdl);
   if (p.mode == kModeSample) {
     switch (p.mb) {
       case 16: return launch_gemm_t<16, kModeSample>(p, stream, pdl);
@@ -205,7 +206,7 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   p->args.m_valid = m_valid;
   const long long T = static_cast<long long>(p->args.n_tiles) * p->args.k_blocks;
   if (mode == kModeSwiglu) p->args.sw.I = N / 2;
-  if (mode == kModePartials && (T + 1) * grid >= (1ll << 31)) {
+  if ((mode == kModePartials || mode == kModeCtxNorm) && (T + 1) * grid >= (1ll << 31)) {
     set_error("gemm: %lld work units x %d CTAs overflows the consumers' 32-bit slot arithmetic", T, grid);
     return -1;
   }

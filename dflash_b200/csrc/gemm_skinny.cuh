@@ -42,6 +42,11 @@ enum GemmMode : int {
   // the other CTAs of the tile left in `part`, in slot order, and runs the epilogue on the finished tile. Tiles that
   // one CTA owns entirely never leave TMEM/registers. No fp32 partial plane, no consumer kernel.
   kModeSwiglu = 5,    // tile = 64 gate rows + 64 up rows of the same columns -> bf16 silu(gate) * up
+  // The target-context injection in ONE kernel (model/dflash.py:177 + :237): stream-K partial planes as kModePartials,
+  // then -- after a device-wide arrival count over the CTAs of the launch, which are all co-resident -- the CTAs
+  // themselves run the row pass over the context rows (sum of the slots -> bf16 -> hidden_norm -> a_in). Before their
+  // first tile the epilogue warps gather the block rows' embeddings and apply layer 0's input_layernorm.
+  kModeCtxNorm = 6,
 };
 constexpr int kTopK = 4;
 
@@ -65,6 +70,7 @@ struct GemmArgs {
   float* part;            // [groups * ranges][MB/4][128][4] fp32: the partial of CTA (group, range)'s FIRST segment
   unsigned int* flags;    // [groups][n_tiles] arrivals of a tile's non-finishing CTAs (reset by the finisher)
   SwigluEpi sw;           // kModeSwiglu
+  CtxNormEpi cn;          // kModeCtxNorm
   // kModeArgmax / kModeSample inside the engine: the LAST CTA to finish also reduces the per-CTA candidates to the
   // drafted tokens (block_ids[:, 1:bs], model/dflash.py:247) -- no separate reduce launch. Off when tok_counter is null.
   unsigned int* tok_counter;
@@ -239,8 +245,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (tr && threadIdx.x == 0) tr[1] = global_ns();
-  // Let the next kernel in the stream start its own prologue / weight prefetch right away.
-  pdl_trigger();
+  // Let the next kernel in the stream start its own prologue / weight prefetch right away. (kModeCtxNorm: the next
+  // kernel is a GEMM that would sit on the SMs, pipeline filled, for this kernel's whole duration -- measured 1 us
+  // slower than releasing it when the last MMA has been issued.)
+  if (MODE != kModeCtxNorm) pdl_trigger();
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -322,6 +330,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
         umma_commit(&tfull[acc]);  // accumulator complete
         if (tr && u >= u1) tr[4] = global_ns();
+        if (MODE == kModeCtxNorm && u >= u1) pdl_trigger();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -449,6 +458,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     //   (order key of the bf16-rounded logit) << 16 | (0xFFFF - tile)
     // so that keeping the best is ONE integer max per logit, and a tie keeps the lower tile = the lower vocab
     // index (this thread's weight row inside the tile is fixed). Decoded and reduced over threads at the end.
+    constexpr bool kPlanes = MODE == kModePartials || MODE == kModeCtxNorm;  // fp32 partial planes in `ws`
+    if constexpr (MODE == kModeCtxNorm) {
+      // block rows: embedding gather + first input_layernorm, while the first accumulator is still being built
+      __shared__ float s_red[4];
+      const int n_cta = static_cast<int>(gridDim.x * gridDim.y);
+      for (int row = static_cast<int>(blockIdx.y * gridDim.x + blockIdx.x); row < a.cn.n_blk_rows; row += n_cta)
+        ctxnorm_embed_row(a.cn, row, epi_tid, s_red);
+    }
     constexpr int kKeep = MODE == kModeTopK ? kTopK : 1;  // running bests per activation row (sorted, descending)
     constexpr bool kSample = MODE == kModeSample;
     uint32_t best[kArgmax ? kCols * kKeep : 1];
@@ -474,14 +491,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       if (tr && seg_end >= u1 && threadIdx.x == 0) tr[5] = global_ns();
       tc_fence_after();
       float* dst = nullptr;
-      if (MODE == kModePartials) {
+      if (kPlanes) {
         const int slot = cta - tile_first_cta(tile, a.k_blocks, T, G);
         dst = a.ws + (static_cast<long long>(slot) * a.ws_rows + m0) * a.ws_ld + n;
       }
       const uint32_t tile_tag = 0xFFFFu - static_cast<uint32_t>(tile);
       // kChunk columns per TMEM round trip: the loads of a chunk are all issued before the one wait
-      constexpr bool kStageOut = (MODE == kModePartials) && (MB >= 64);
-      constexpr int kChunk = (MODE == kModePartials) ? (kStageOut ? 32 : kCols)
+      constexpr bool kStageOut = kPlanes && (MB >= 64);
+      constexpr int kChunk = kPlanes ? (kStageOut ? 32 : kCols)
                                                       : ((kCols >= 32 && kCols < 128) ? 32 : 16);  // (register budget)
       // Wide partial tiles go out through a 16 KB transpose buffer: a thread owns one weight row (column n of the
       // output) and would store its 128-256 values 4 bytes at a time, one 128-byte warp store per activation row
@@ -525,7 +542,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
           continue;
         }
-        if (MODE == kModePartials) {
+        if (kPlanes) {
           if (n < a.N) {
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) {
@@ -688,6 +705,49 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
   }
 
+  if constexpr (MODE == kModeCtxNorm) {
+    // ---------------------------------------------------------------- in-kernel row pass over the context rows
+    // Every thread of the CTA (the TMA / MMA warps are done too). This CTA's partial planes are stored; count it in,
+    // and if it owns live context rows wait until every CTA of the launch is in (they are all co-resident: at most
+    // one CTA per SM's worth of them exists), then finish those rows. The LAST CTA to leave resets both counters.
+    __shared__ int s_ns[64];       // partial slots per column tile (hidden <= 8192)
+    __shared__ float s_red6[Cfg::kThreads / 32];
+    __shared__ int s_live;
+    const int n_cta = static_cast<int>(gridDim.x * gridDim.y);
+    const int me = static_cast<int>(blockIdx.y * gridDim.x + blockIdx.x);
+    const int tid = static_cast<int>(threadIdx.x);
+    for (int t = tid; t < a.n_tiles; t += Cfg::kThreads) s_ns[t] = tile_num_slots(t, a.k_blocks, T, G);
+    if (tid == 0) {
+      int live = 0;
+      for (int row = me; row < a.m_valid; row += n_cta)
+        live |= (row % a.cn.SL < __ldg(a.cn.ctx_len + row / a.cn.SL)) ? 1 : 0;
+      s_live = live;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      red_release_add_u32(&a.cn.sync[0], 1u);
+      if (s_live)
+        while (ld_acquire_u32(&a.cn.sync[0]) < static_cast<unsigned int>(n_cta)) { }
+    }
+    __syncthreads();
+    DFL_TRACE(5);
+    if (s_live) {
+      const long long slot_stride = static_cast<long long>(a.ws_rows) * a.ws_ld;
+      for (int row = me; row < a.m_valid; row += n_cta)
+        if (row % a.cn.SL < __ldg(a.cn.ctx_len + row / a.cn.SL))
+          ctxnorm_row_pass<Cfg::kThreads>(a.cn, a.ws, slot_stride, a.ws_ld, row, tid, s_ns,
+                                          reinterpret_cast<float*>(smem), s_red6);
+    }
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(&a.cn.sync[1], 1u);
+      if (prev == static_cast<unsigned int>(n_cta) - 1u) {
+        a.cn.sync[0] = 0u;
+        a.cn.sync[1] = 0u;
+      }
+    }
+    DFL_TRACE(2);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc<Cfg::kTmemCols>(tmem_base);

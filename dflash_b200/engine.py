@@ -240,11 +240,11 @@ class DraftEngine:
         self.cand_scores = self.buf["cand_scores"].view(R, 4)
         self.SL = 16 if bs <= 16 else 32
         self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
-        # launches per draft step of the schedule actually enqueued (engine.cuh): fc GEMM, one row kernel (context
-        # finalize + block embedding + first layernorm), per layer {qkv GEMM, qkv_post, attention, merge, o GEMM, row
+        # launches per draft step of the schedule actually enqueued (engine.cuh): the context-injection kernel (fc GEMM
+        # + hidden_norm + block embedding + first layernorm), per layer {qkv GEMM, qkv_post, attention, merge, o GEMM, row
         # kernel, gate/up GEMM (SwiGLU epilogue), down GEMM, row kernel}, lm_head GEMM (argmax + drafted tokens); the
         # verify step is one kernel
-        self.kernels_per_draft_step = 2 + 9 * cfg.num_hidden_layers + 1
+        self.kernels_per_draft_step = 1 + 9 * cfg.num_hidden_layers + 1
         self.kernels_per_verify_step = 1
         self._graph = None
 

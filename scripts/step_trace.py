@@ -63,14 +63,9 @@ for tag, t in rec.tolist():
     phase, bd, gx, gy = tag & 15, (tag >> 4) & 0xFFF, (tag >> 16) & 0xFFFFFF, (tag >> 40) & 0xFFFFFF
     ev.append((t, names.get((bd, gx, gy), f"?{bd},{gx},{gy}"), phase))
 ev.sort()
-# one step = from a finalize2 entry to the next
-starts = [i for i, e in enumerate(ev) if e[1] == "finalize2" and e[2] == 0]
+# one step = from a verify-kernel entry to the next
+starts = [i for i, e in enumerate(ev) if e[1] == "verify" and e[2] == 0]
 a, b = starts[-3], starts[-2]
-# the fc GEMM of the step starts before finalize2: back up to its entry
-while a > 0 and not (ev[a][1] == "verify" and ev[a][2] == 0):
-    a -= 1
-while b > 0 and not (ev[b][1] == "verify" and ev[b][2] == 0):
-    b -= 1
 t0 = ev[a][0]
 ph_name = {0: "entry", 1: "past wait", 2: "end", 3: "first stage landed", 4: "last accumulator complete",
            5: "other CTAs' partials arrived"}

@@ -278,6 +278,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     cn.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
     cn.ld = H;
     cn.norm_w = static_cast<const __nv_bfloat16*>(w.hidden_norm);
+    cn.max_slots = e->fc.max_slots;
     if ((e->flags_used + 2) * 4 > e->reg[DFLASH_BUF_FLAGS].bytes) {
       set_error("internal: flag region too small");
       delete e;

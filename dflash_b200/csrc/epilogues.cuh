@@ -58,6 +58,7 @@ struct CtxNormEpi {
   long long ld;                  // hidden size
   const __nv_bfloat16* norm_w;   // hidden_norm.weight [H]
   unsigned int* sync;            // [2]: CTAs whose partials are stored; CTAs that are past the wait (self-resetting)
+  int max_slots;                 // most partial slots any column tile has
   const int* ctx_len;            // [R]: context row (r, j) is live iff j < ctx_len[r]
   int SL;
   float eps;
@@ -76,6 +77,7 @@ struct CtxNormEpi {
 //   out = w * bf16(v * rsqrt(mean(v^2) + eps))              (Qwen3RMSNorm, fp32 inside)
 // ns_tab[t] = partial slots of column tile t; rowbuf: H floats of shared memory (the idle TMA pipeline); red: NT / 32
 // floats of shared memory.
+constexpr int kCtxMaxGroups = 11;  // float4 groups per thread: hidden <= 8192 over 192 threads
 template <int NT>
 __device__ __forceinline__ void ctxnorm_row_pass(const CtxNormEpi& e, const float* __restrict__ ws, long long slot_stride,
                                                  long long ws_ld, int row, int tid, const int* ns_tab, float* rowbuf,
@@ -131,6 +133,62 @@ __device__ __forceinline__ void ctxnorm_row_pass(const CtxNormEpi& e, const floa
     *reinterpret_cast<uint2*>(e.out + static_cast<long long>(row) * e.ld + n) =
         pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
                    w.w * bf16_round(x.w * rstd));
+  }
+}
+
+// The same row pass with the row's partial slots pulled into shared memory by the TMA engine (max_slots bulk copies of
+// H floats each into stage[slot][H], one mbarrier): ONE memory round trip however few threads the CTA has, instead of
+// max_slots * H / (4 * NT) dependent-latency loads per thread. Needs max_slots * H * 4 bytes of (idle pipeline) smem.
+template <int NT>
+__device__ __forceinline__ void ctxnorm_row_pass_bulk(const CtxNormEpi& e, const float* __restrict__ ws, long long slot_stride,
+                                                      long long ws_ld, int row, int tid, const int* ns_tab, float* stage,
+                                                      uint64_t* bar, uint32_t parity, float* red) {
+  const int H = static_cast<int>(e.ld);
+  __syncthreads();  // the previous row's readers are done with stage[] and red[]
+  if (tid == 0) {
+    fence_proxy_async();  // (acquired partials of other CTAs; this CTA's earlier generic reads of stage[])
+    mbar_expect_tx(bar, static_cast<uint32_t>(e.max_slots) * static_cast<uint32_t>(H) * 4u);
+    for (int s = 0; s < e.max_slots; ++s)
+      bulk_load_1d(stage + static_cast<long long>(s) * H, ws + s * slot_stride + static_cast<long long>(row) * ws_ld,
+                   static_cast<uint32_t>(H) * 4u, bar);
+  }
+  constexpr int kWG = 6;  // norm weights requested before the wait (hidden <= 4608 over 192 threads: all of them)
+  uint2 wv[kWG];
+#pragma unroll
+  for (int g = 0; g < kWG; ++g) {
+    const int n = (tid + g * NT) * 4;
+    if (n < H) wv[g] = *reinterpret_cast<const uint2*>(e.norm_w + n);
+  }
+  mbar_wait(bar, parity);
+  float ss = 0.f;
+  for (int n = tid * 4; n < H; n += NT * 4) {
+    const int ns = ns_tab[n >> 7];
+    float4 acc = *reinterpret_cast<const float4*>(stage + n);
+    for (int s = 1; s < ns; ++s) {  // slot order: the summation order is fixed
+      const float4 q = *reinterpret_cast<const float4*>(stage + static_cast<long long>(s) * H + n);
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    acc.x = bf16_round(acc.x); acc.y = bf16_round(acc.y); acc.z = bf16_round(acc.z); acc.w = bf16_round(acc.w);
+    *reinterpret_cast<float4*>(stage + n) = acc;  // (slot 0's place; this thread is its only reader)
+    ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) tot += red[w];
+  const float rstd = 1.0f / sqrtf(tot / static_cast<float>(H) + e.eps);
+#pragma unroll
+  for (int g = 0; g < kCtxMaxGroups; ++g) {
+    const int n = (tid + g * NT) * 4;
+    if (n < H) {
+      const float4 x = *reinterpret_cast<const float4*>(stage + n);
+      const float4 w = unpack4_bf16(g < kWG ? wv[g < kWG ? g : 0] : *reinterpret_cast<const uint2*>(e.norm_w + n));
+      *reinterpret_cast<uint2*>(e.out + static_cast<long long>(row) * e.ld + n) =
+          pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
+                     w.w * bf16_round(x.w * rstd));
+    }
   }
 }
 

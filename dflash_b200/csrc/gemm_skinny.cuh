@@ -713,10 +713,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     __shared__ int s_ns[64];       // partial slots per column tile (hidden <= 8192)
     __shared__ float s_red6[Cfg::kThreads / 32];
     __shared__ int s_live;
+    __shared__ __align__(8) uint64_t s_rowbar;
     const int n_cta = static_cast<int>(gridDim.x * gridDim.y);
     const int me = static_cast<int>(blockIdx.y * gridDim.x + blockIdx.x);
     const int tid = static_cast<int>(threadIdx.x);
-    for (int t = tid; t < a.n_tiles; t += Cfg::kThreads) s_ns[t] = tile_num_slots(t, a.k_blocks, T, G);
+    // the idle lanes of the TMA / MMA warps get here at once: they fill the slot table while the main loop runs
+    if (warp >= Cfg::kEpiWarps && lane != 0) {
+      const int helper = (warp - Cfg::kEpiWarps) * 31 + lane - 1;
+      for (int t = helper; t < a.n_tiles; t += 62) s_ns[t] = tile_num_slots(t, a.k_blocks, T, G);
+      if (helper == 0) {
+        mbar_init(&s_rowbar, 1);
+        mbar_fence_init();
+      }
+    }
     if (tid == 0) {
       int live = 0;
       for (int row = me; row < a.m_valid; row += n_cta)
@@ -725,26 +734,36 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
     __threadfence();
     __syncthreads();
+    unsigned int left = 0;
     if (tid == 0) {
       red_release_add_u32(&a.cn.sync[0], 1u);
       if (s_live)
         while (ld_acquire_u32(&a.cn.sync[0]) < static_cast<unsigned int>(n_cta)) { }
+      // past the wait (or never waiting): count out now, so that the round trip overlaps the row pass
+      left = atomicAdd(&a.cn.sync[1], 1u);
     }
     __syncthreads();
     DFL_TRACE(5);
     if (s_live) {
       const long long slot_stride = static_cast<long long>(a.ws_rows) * a.ws_ld;
+      float* stage = reinterpret_cast<float*>(smem);
+      const bool bulk = static_cast<long long>(a.cn.max_slots) * a.cn.ld * 4 <= static_cast<long long>(S) * Cfg::kStageBytes;
+      uint32_t parity = 0;
       for (int row = me; row < a.m_valid; row += n_cta)
-        if (row % a.cn.SL < __ldg(a.cn.ctx_len + row / a.cn.SL))
-          ctxnorm_row_pass<Cfg::kThreads>(a.cn, a.ws, slot_stride, a.ws_ld, row, tid, s_ns,
-                                          reinterpret_cast<float*>(smem), s_red6);
+        if (row % a.cn.SL < __ldg(a.cn.ctx_len + row / a.cn.SL)) {
+          if (bulk) {
+            ctxnorm_row_pass_bulk<Cfg::kThreads>(a.cn, a.ws, slot_stride, a.ws_ld, row, tid, s_ns, stage, &s_rowbar,
+                                                 parity, s_red6);
+            parity ^= 1u;
+          } else {
+            ctxnorm_row_pass<Cfg::kThreads>(a.cn, a.ws, slot_stride, a.ws_ld, row, tid, s_ns, stage, s_red6);
+          }
+        }
     }
-    if (tid == 0) {
-      const unsigned int prev = atomicAdd(&a.cn.sync[1], 1u);
-      if (prev == static_cast<unsigned int>(n_cta) - 1u) {
-        a.cn.sync[0] = 0u;
-        a.cn.sync[1] = 0u;
-      }
+    // the LAST CTA past the wait resets both counters for the next launch (nobody can still be polling them)
+    if (tid == 0 && left == static_cast<unsigned int>(n_cta) - 1u) {
+      a.cn.sync[0] = 0u;
+      a.cn.sync[1] = 0u;
     }
     DFL_TRACE(2);
   }

@@ -428,11 +428,11 @@ TAU_HIST_COLS = 512  # acceptance lengths per request carried by the result gath
 
 class StepRunner:
     """R request streams of the BASELINE workload in one engine: synthetic target outputs resident in HBM, the whole
-    draft+verify step (2 + 8 L + 1 + 1 kernels, device-resident state, PDL edges) captured in ONE CUDA graph."""
+    draft+verify step (device-resident state, PDL edges) captured in ONE CUDA graph."""
 
-    def __init__(self, eng, dims, device, R, seed, ks):
+    def __init__(self, eng, dims, device, R, seed, ks, inject=True):
         import torch
-        self.eng, self.R, self.ks, self.device = eng, R, ks, device
+        self.eng, self.R, self.ks, self.device, self.inject = eng, R, ks, device, inject
         bs, H, V, nsel = dims["block_size"], dims["hidden"], dims["vocab"], dims["draft_layers"]
         g = torch.Generator(device=device).manual_seed(seed)
         self.tlogits = torch.randn(R * bs, V, device=device, generator=g).to(torch.bfloat16)
@@ -462,13 +462,24 @@ class StepRunner:
         self.reset()
 
     def enqueue_step(self):
-        self.eng.draft_step()
-        self.eng.verify_step(self.tlogits, self.hsel, temperature=0.0, forced_k=self.forced)
+        """One step = draft (layers + lm_head) -> verify + the NEXT cycle's context injection (overlapped with the verify
+        kernel, reading the hidden states in place). --no-inject: the injection kernel at the head of the draft step,
+        fed from the features the verify kernel gathers."""
+        if self.inject:
+            self.eng._injected = "fresh"  # the graph is a fixed kernel list: reset() re-embeds the block rows itself
+            self.eng.draft_step_injected()
+            self.eng.verify_step(self.tlogits, self.hsel, temperature=0.0, forced_k=self.forced, inject=True)
+        else:
+            self.eng._injected = "no"
+            self.eng.draft_step()
+            self.eng.verify_step(self.tlogits, self.hsel, temperature=0.0, forced_k=self.forced)
 
     def reset(self):
         for r in range(self.R):
             self.eng.reset_request(r, self.prompt, 1, MAX_NEW)
             self.eng.prefill_context(r, self.prompt_hidden)
+        if self.inject:
+            self.eng.embed_block()
         self.since_reset = 0
 
     def run(self, n, events=None):
@@ -562,10 +573,11 @@ def run_cuda_arm(args):
     draft, eng, embed, lm_head = build_engine(dims, device, seed=rank, R=R)
     ks = forced_schedule(seed=0)
     mean_tau = sum(k + 1 for k in ks) / len(ks)
-    runner = StepRunner(eng, dims, device, R, 100 + rank, ks)
+    runner = StepRunner(eng, dims, device, R, 100 + rank, ks, inject=not args.no_inject)
     tlogits, hsel, forced, side = runner.tlogits, runner.hsel, runner.forced, runner.side
     steps_per_gen = runner.steps_per_gen
-    launches_per_step = eng.kernels_per_draft_step + eng.kernels_per_verify_step
+    launches_per_step = (eng.kernels_per_draft_step_injected + eng.kernels_per_verify_inject_step if runner.inject
+                         else eng.kernels_per_draft_step + eng.kernels_per_verify_step)
 
     res = timed_steps(runner, args.steps, args.warmup, device, local)
     value, total_ms_max, step_us, clock_info = res["value"], res["total_ms"], res["step_us"], res["clocks"]
@@ -597,7 +609,7 @@ def run_cuda_arm(args):
     copy_stream = torch.cuda.Stream(device=device)
 
     def verify_enqueue():
-        eng.verify_step(tl_dev, hs_dev, temperature=0.0, forced_k=forced)
+        eng.verify_step(tl_dev, hs_dev, temperature=0.0, forced_k=forced, inject=runner.inject)
         res_dev[0] = eng.buf["start"][0]
         res_dev[1] = eng.buf["ctx_len"][0]
         res_dev[2:] = eng.posterior[0]
@@ -607,7 +619,8 @@ def run_cuda_arm(args):
         copy_stream.wait_stream(cur)
         with torch.cuda.stream(copy_stream):
             stage_dev.copy_(stage_host, non_blocking=True)
-        eng.draft_step()
+        eng._injected = "fresh" if runner.inject else "no"
+        eng.draft_step()  # (injected state: the step without its injection kernel)
         cur.wait_stream(copy_stream)
         verify_enqueue()
         res_host.copy_(res_dev, non_blocking=True)
@@ -700,7 +713,7 @@ def run_cuda_arm(args):
         span = PROMPT_LEN + MAX_NEW + 64
         eng_s = DraftEngine(draft, embed, lm_head, max_seq=span, out_len=span, max_requests=Rs, block_size=bs,
                             device=device)
-        runner_s = StepRunner(eng_s, dims, device, Rs, 200 + rank, ks)
+        runner_s = StepRunner(eng_s, dims, device, Rs, 200 + rank, ks, inject=not args.no_inject)
         rs = timed_steps(runner_s, max(10, min(args.steps, 40)), 5, device, local, sample_clocks=False)
         su = rs["step_us"]
         sharded = dict(workload=f"global batch {SHARDED_BATCH} requests, {Rs} request streams per GPU (BASELINE.json "
@@ -798,6 +811,9 @@ def main():
     ap.add_argument("--requests", type=int, default=1, choices=[1, 2, 4, 8, 16, 32, 64],
                     help="request streams per GPU sharing one weight stream (headline metric is quoted at 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inject", action="store_true",
+                    help="A/B switch: context injection at the head of the draft step (fed from gathered features) "
+                         "instead of behind the verify kernel it overlaps")
     ap.add_argument("--no-sharded", action="store_true", help="skip the global-batch-64 sharded section")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip the torch op sequence of the same step on the GPU (north-star comparison)")

@@ -179,7 +179,7 @@ def _run(draft, target, eng: DraftEngine, prompts, max_new_tokens, stop_token_id
                 hs[s][r * bs: r * bs + eff] = tap.states[s][0]
         noise = noise_fn(cycle) if (noise_fn is not None and temperature >= 1e-5) else None
         eng.verify_step(tl_c, hs_c, temperature=temperature, noise=noise, seed=seed, stop_ids=stop_t, forced_k=forced_t,
-                        clamp_tail=clamp_tail)
+                        clamp_tail=clamp_tail, inject=True)
         cycle += 1
         if graph_target and cycle % sync_every != 0:
             continue  # nothing on the host depends on this cycle's outcome

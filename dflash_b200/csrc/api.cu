@@ -147,6 +147,63 @@ int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long 
   return enqueue_verify_step(e->impl, v, static_cast<cudaStream_t>(stream));
 }
 
+int dflash_verify_inject_step(dflash_engine_t* e, const void* target_logits, long long logits_ld,
+                              const long long* posterior_in, const void* const* hidden, float temperature,
+                              const float* noise, unsigned long long seed, const long long* stop_ids, int n_stop,
+                              const int* forced_k, int forced_ld, int clamp_tail, void* stream) {
+  if (!e || !hidden || (!target_logits && !posterior_in)) {
+    set_error("verify_inject_step: null argument");
+    return DFLASH_ERR_ARG;
+  }
+  VerifyInputs v;
+  memset(&v, 0, sizeof(v));
+  v.target_logits = target_logits;
+  v.logits_ld = logits_ld;
+  v.posterior_in = posterior_in;
+  for (int s = 0; s < e->impl->nsel; ++s) {
+    if (!hidden[s]) { set_error("verify_inject_step: hidden[%d] is null", s); return DFLASH_ERR_ARG; }
+    v.hidden[s] = hidden[s];
+  }
+  v.temperature = temperature;
+  v.noise = noise;
+  v.seed = seed;
+  v.stop_ids = stop_ids;
+  v.n_stop = stop_ids ? n_stop : 0;
+  v.forced_k = forced_k;
+  v.forced_ld = forced_ld;
+  v.clamp_tail = clamp_tail;
+  return enqueue_verify_step(e->impl, v, static_cast<cudaStream_t>(stream), true);
+}
+
+int dflash_draft_step_injected(dflash_engine_t* e, int run_lm_head, float temperature, unsigned long long seed,
+                               void* stream) {
+  if (!e) { set_error("draft_step_injected: null engine"); return DFLASH_ERR_ARG; }
+  if (temperature >= 1e-5f && !e->impl->has_sample) {
+    set_error("draft_step_injected: the sampling epilogue needs max_requests * row slots <= 32");
+    return DFLASH_ERR_ARG;
+  }
+  return enqueue_draft_step(e->impl, nullptr, run_lm_head != 0, static_cast<cudaStream_t>(stream), 1, 0, temperature,
+                            seed, false);
+}
+
+int dflash_embed_block(dflash_engine_t* e, void* stream) {
+  if (!e) { set_error("embed_block: null engine"); return DFLASH_ERR_ARG; }
+  return enqueue_embed_block(e->impl, static_cast<cudaStream_t>(stream));
+}
+
+int dflash_engine_launches(const dflash_engine_t* e, int which) {
+  if (!e) { set_error("engine_launches: null engine"); return DFLASH_ERR_ARG; }
+  const Engine* en = e->impl;
+  const int per_layer = en->nsplit_attn > 1 ? 9 : 8;  // (a single KV split needs no merge kernel)
+  switch (which) {
+    case 0: return 1 + per_layer * en->L + 1;  // dflash_draft_step
+    case 1: return per_layer * en->L + 1;      // dflash_draft_step_injected
+    case 2: return 1;                          // dflash_verify_step
+    case 3: return 2;                          // dflash_verify_inject_step
+    default: set_error("engine_launches: which must be 0..3"); return DFLASH_ERR_ARG;
+  }
+}
+
 int dflash_draft_step_sampled(dflash_engine_t* e, float temperature, unsigned long long seed, void* stream) {
   if (!e) { set_error("draft_step_sampled: null engine"); return DFLASH_ERR_ARG; }
   if (temperature >= 1e-5f && !e->impl->has_sample) {

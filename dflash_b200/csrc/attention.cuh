@@ -260,6 +260,20 @@ __device__ __forceinline__ void attn_split_body(const AttnArgs& a, int r, int qt
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  if (!LOCAL && a.nsplit == 1) {
+    // one split per (request, kv head): nothing to merge -- normalise and write the bf16 attention output here (the
+    // merge kernel is not launched). Same arithmetic as attn_combine_item with a single live split (weight exp2(0) = 1).
+    const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+    __nv_bfloat16* d_lo = a.out + (static_cast<long long>(row_lo) * a.Hq + hq) * kAttnD;
+    __nv_bfloat16* d_hi = a.out + (static_cast<long long>(row_lo + 8) * a.Hq + hq) * kAttnD;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const int d = nt * 8 + tq * 2;
+      *reinterpret_cast<uint32_t*>(d_lo + d) = pack_bf16(o[nt][0] * inv_lo, o[nt][1] * inv_lo);
+      *reinterpret_cast<uint32_t*>(d_hi + d) = pack_bf16(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
+    }
+    return;
+  }
   const long long p_lo = part_index(row_lo), p_hi = part_index(row_lo + 8);
   if (tq == 0) {
     a.part_ml[p_lo * 2 + 0] = m_lo; a.part_ml[p_lo * 2 + 1] = l_lo;

@@ -25,10 +25,14 @@ struct Engine {
   uint8_t* base = nullptr;
   size_t total = 0;
   Region reg[DFLASH_BUF_COUNT];
-  int R, SL, RS, H, I, L, Hq, Hkv, V, nsel, bs, grid, nsplit_attn, nsplit_post;
+  int R, SL, RS, H, I, L, Hq, Hkv, V, nsel, bs, grid, nsplit_attn, nsplit_post, sm_count;
   bool pdl;
   // plans
   GemmPlan fc;                  // ctx_feat -> partials
+  // the same kernel reading the selected target hidden states in place (3-D maps, rebuilt when the pointers change),
+  // launched right behind the verify kernel it overlaps (enqueue_verify_step with inject)
+  GemmPlan fc_direct;
+  const void* direct_hidden[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<GemmPlan> qkv;    // a_in (ctx + block rows)
   // prompt pass (c = P rows at once): fc and the K/V rows of wqkv over the dedicated prompt buffers,
   // one plan per UMMA width so that short prompts do not pay for 256 columns
@@ -67,17 +71,29 @@ inline int default_attn_splits(const dflash_config_t& c, int sm_count) {
   if (c.attn_splits > 0) return c.attn_splits;
   const int SL = c.block_size <= 16 ? 16 : 32;
   const int ctas = c.max_requests * c.n_kv_heads * (SL / 16);
+  // from about one CTA per SM up, ONE split: the attention kernel then writes the normalised output itself and the
+  // merge kernel (one more full-grid dependency per layer) is not launched
+  if (ctas * 8 >= sm_count * 7) return 1;
   int n = (2 * sm_count + ctas - 1) / ctas;
   return n < 1 ? 1 : (n > 16 ? 16 : n);
 }
 
-// Vocab splits of the posterior sampler: about four waves of (row, split) CTAs, 2..32 (each CTA then has enough
-// columns to keep several 128-bit loads in flight per thread).
+// Vocab splits of the posterior sampler, 1..32.
 inline int default_post_splits(const dflash_config_t& c, int sm_count) {
   if (c.post_splits > 0) return c.post_splits;
   const int rows = c.max_requests * c.block_size;
-  int n = (4 * sm_count + rows - 1) / rows;
-  return n < 2 ? 2 : (n > 32 ? 32 : n);
+  // about TWO CTAs per SM in all (the verify kernel walks the rows when there are more of them): the context-injection
+  // kernel that overlaps it needs its own CTA on every SM, and the register file of an SM sub-partition (16 K
+  // registers) holds four warps of this kernel (4 x 32 x 64) next to two of that one (2 x 32 x 112), not more
+  // (measured: -10..13 us per step at one stream). Wide batches (more block rows than SMs) gain nothing from the overlap
+  // -- the injection GEMM is tensor-bound there and from 32 streams up the board is power-capped -- and want the
+  // memory parallelism of about four waves of CTAs instead (R = 16 / 64: 1459 / 4242 us per step against 1484 / 4312).
+  if (rows > sm_count) {
+    const int n = (4 * sm_count + rows - 1) / rows;
+    return n < 2 ? 2 : n;
+  }
+  int n = (2 * sm_count) / rows;
+  return n < 1 ? 1 : (n > 32 ? 32 : n);
 }
 
 // Fills reg[] (offsets/sizes) for cfg; returns total bytes or 0 on a bad config.
@@ -221,6 +237,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
   e->H = c.hidden; e->I = c.intermediate; e->L = c.n_layers; e->Hq = c.n_q_heads; e->Hkv = c.n_kv_heads;
   e->V = c.vocab; e->nsel = c.n_sel; e->bs = c.block_size;
   e->grid = c.gemm_grid > 0 ? c.gemm_grid : sm_count;
+  e->sm_count = sm_count;
   e->nsplit_attn = default_attn_splits(c, sm_count);
   e->nsplit_post = default_post_splits(c, sm_count);
   e->pdl = c.use_pdl != 0;
@@ -296,6 +313,12 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     cn.resid = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
     cn.ln_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
     cn.blk_out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN) + static_cast<size_t>(RS) * H;
+    cn.direct = 0;
+    cn.kb_per_sel = H / kTileK;
+    cn.embed = static_cast<const __nv_bfloat16*>(w.embed);
+    cn.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+    e->fc_direct = e->fc;
+    e->fc_direct.args.cn.direct = 1;
   }
   e->qkv.resize(e->L); e->kv_pf.resize(e->L * 5); e->o.resize(e->L); e->gu.resize(e->L); e->d.resize(e->L);
   for (int i = 0; i < 5; ++i) {
@@ -462,14 +485,15 @@ inline QkvPostArgs qkv_post_args(Engine* e, int l, const GemmPlan& p, bool kv_on
 // n_candidates > 1: top-4 lm_head epilogue + candidate blocks (fixed_prefix_rank) instead of the plain argmax tail
 inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_lm_head, cudaStream_t st,
                               int n_candidates = 1, int fixed_prefix_len = 0, float draft_temperature = 0.f,
-                              unsigned long long draft_seed = 0) {
+                              unsigned long long draft_seed = 0, bool inject = true) {
   const int RS = e->RS;
   __nv_bfloat16* x = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
   __nv_bfloat16* a_in = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN);
   // Context injection as ONE kernel: the fc GEMM over the features gathered by the previous verify step finishes its
   // tiles in its own epilogue (bf16 + hidden_norm -> a_in ctx rows), and its epilogue warps also do the block rows
-  // (embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows) before their first tile
-  {
+  // (embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows) before their first tile.
+  // inject == false: the previous verify step (or the prompt pass) already did it (enqueue_verify_step with inject).
+  if (inject) {
     GemmPlan fc = e->fc;
     if (noise_embedding != nullptr) {
       fc.args.cn.embed = static_cast<const __nv_bfloat16*>(noise_embedding);  // [R*SL, H] rows, already embedded
@@ -503,8 +527,9 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
                         e->pdl, qa), "qkv post");
     DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),
                         kAttnSmem, st, e->pdl, aa), "attention");
-    DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0,
-                        st, e->pdl, aa), "attention combine");
+    if (e->nsplit_attn > 1)  // (a single split writes the normalised output itself)
+      DFL_CUDA(launch_pdl(attn_combine_kernel, dim3((RS * e->Hq + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0,
+                          st, e->pdl, aa), "attention combine");
     DFL_CUDA(launch_gemm(e->o[l], st, e->pdl), "o gemm");
     {
       RowsArgs a = rows_args_base(e);
@@ -584,7 +609,40 @@ struct VerifyInputs {
 // Posterior sampling -> acceptance/commit/state -> next-cycle context gather  (dflash.py:257-268).
 // The plain path is ONE kernel (verify_fused_kernel); multi-candidate verify and the given-posterior harness hook
 // keep the three-kernel form (the winner's rows are only known after the acceptance).
-inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st) {
+// Block rows only: embed_tokens(block_ids) -> residual stream, input_layernorm of layer 0 -> a_in block rows
+// (model/dflash.py:237 + the first norm). What the context-injection kernel does for the block rows, as its own launch:
+// after a request reset (or any other rewrite of block_ids), when the next draft step runs without injection.
+inline int enqueue_embed_block(Engine* e, cudaStream_t st) {
+  RowsArgs a = rows_args_base(e);
+  a.embed = static_cast<const __nv_bfloat16*>(e->w.embed);
+  a.ids = e->buf<long long>(DFLASH_BUF_BLOCK_IDS);
+  a.ids_ld = e->bs;
+  a.pad_token = e->cfg.mask_token_id;
+  a.resid = e->buf<__nv_bfloat16>(DFLASH_BUF_X);
+  a.norm_w = static_cast<const __nv_bfloat16*>(e->layers[0].ln1);
+  a.out = e->buf<__nv_bfloat16>(DFLASH_BUF_A_IN) + static_cast<size_t>(e->RS) * e->H;
+  DFL_CUDA(launch_pdl(finalize_rows_kernel, dim3(e->RS), dim3(kRowsThreads), static_cast<size_t>(e->H) * 6, st, e->pdl, a),
+           "block embedding");
+  return DFLASH_OK;
+}
+
+// The next cycle's context injection reading the selected hidden states in place (dflash.py:263 + :177 + :237 as one
+// kernel), launched behind the verify kernel: its fc main loop overlaps that kernel, its row pass waits for it.
+inline int enqueue_inject_direct(Engine* e, const void* const* hidden, cudaStream_t st) {
+  bool same = true;
+  for (int s = 0; s < e->nsel; ++s) same = same && hidden[s] == e->direct_hidden[s];
+  if (!same) {
+    GemmPlan& p = e->fc_direct;
+    for (int s = 0; s < e->nsel; ++s) {
+      if (make_tmap_hidden3d(&p.xm.m[s], hidden[s], e->R, e->bs, e->H, e->SL, p.mb / e->SL)) return DFLASH_ERR_ARG;
+      e->direct_hidden[s] = hidden[s];
+    }
+  }
+  DFL_CUDA(launch_gemm(e->fc_direct, st, e->pdl), "context injection (direct: concat + fc + hidden_norm + embed + ln1)");
+  return DFLASH_OK;
+}
+
+inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st, bool inject = false) {
   const int K = v.n_candidates > 1 ? v.n_candidates : 1;
   const int rows = e->R * K * e->bs;
   PosteriorArgs pa;
@@ -647,13 +705,22 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
     fa.acc = aa;
     fa.gather = ga;
     fa.counters = e->buf<unsigned int>(DFLASH_BUF_COUNTERS);
-    DFL_CUDA(launch_pdl(verify_fused_kernel, dim3(e->nsplit_post, rows), dim3(256), 0, st, e->pdl, fa), "verify");
+    if (inject) fa.gather.n_sel = 0;  // the injection kernel reads the hidden states in place: nothing to gather
+    int gy = rows;  // one CTA per (split, row); a narrower grid walks the rows
+    if (rows <= e->sm_count && e->nsplit_post * rows > 2 * e->sm_count) gy = (2 * e->sm_count) / e->nsplit_post;
+    gy = gy < 1 ? 1 : (gy > rows ? rows : gy);
+    DFL_CUDA(launch_pdl(verify_fused_kernel, dim3(e->nsplit_post, gy), dim3(256), 0, st, e->pdl, fa), "verify");
+    if (inject) return enqueue_inject_direct(e, v.hidden, st);
     return DFLASH_OK;
   }
   if (v.posterior_in == nullptr)
     DFL_CUDA(launch_pdl(posterior_kernel, dim3(e->nsplit_post, rows), dim3(256), 0, st, e->pdl, pa), "posterior");
   DFL_CUDA(launch_pdl(accept_kernel, dim3(e->R), dim3(32), 0, st, e->pdl, aa), "accept");
   DFL_CUDA(launch_pdl(ctx_gather_kernel, dim3(e->RS, e->nsel), dim3(256), 0, st, e->pdl, ga), "ctx gather");
+  if (inject) {  // (the gathered form of the injection kernel: these paths only know the rows after the acceptance)
+    GemmPlan fc = e->fc;
+    DFL_CUDA(launch_gemm(fc, st, e->pdl), "context injection (fc gemm + hidden_norm + embed + ln1)");
+  }
   return DFLASH_OK;
 }
 

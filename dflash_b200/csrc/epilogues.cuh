@@ -59,6 +59,11 @@ struct CtxNormEpi {
   const __nv_bfloat16* norm_w;   // hidden_norm.weight [H]
   unsigned int* sync;            // [2]: CTAs whose partials are stored; CTAs that are past the wait (self-resetting)
   int max_slots;                 // most partial slots any column tile has
+  // direct mode: the activation tiles are read IN PLACE from the selected target hidden states (XMaps, one 3-D map
+  // per selected layer) and the launch overlaps the verify kernel in front of it: the main loop does not wait for that
+  // kernel, everything that reads its results (ctx_len, the next block's first token) happens after the main loop
+  int direct;
+  int kb_per_sel;                // hidden / 64: k-blocks per selected layer
   const int* ctx_len;            // [R]: context row (r, j) is live iff j < ctx_len[r]
   int SL;
   float eps;
@@ -83,8 +88,10 @@ __device__ __forceinline__ void ctxnorm_row_pass(const CtxNormEpi& e, const floa
                                                  long long ws_ld, int row, int tid, const int* ns_tab, float* rowbuf,
                                                  float* red) {
   const int H = static_cast<int>(e.ld);
-  constexpr int kBatch = 3;  // column groups whose slot loads are in flight together (these are L2 round trips)
-  constexpr int kSlots = 6;  // slots loaded up front (fc at Qwen3-8B dims: a tile spans <= 6 CTAs); more are added after
+  // (fallback of ctxnorm_row_pass_bulk for rows that do not fit the pipeline's shared memory: kept small in registers,
+  // the kernel shares its SMs with the verify kernel it overlaps)
+  constexpr int kBatch = 1;  // column groups whose slot loads are in flight together (these are L2 round trips)
+  constexpr int kSlots = 4;  // slots loaded up front; more are added after
   float ss = 0.f;
   for (int n0 = tid * 4; n0 < H; n0 += NT * 4 * kBatch) {
     float4 p[kBatch][kSlots];
@@ -192,10 +199,16 @@ __device__ __forceinline__ void ctxnorm_row_pass_bulk(const CtxNormEpi& e, const
   }
 }
 
-// Block row `row` on the 128 epilogue threads: embedding gather -> residual stream; input_layernorm -> blk_out.
-// red: 4 floats of shared memory; named barrier 1 (the epilogue warps' barrier).
-constexpr int kEmbedMaxIt = 16;  // hidden <= 8192
+// Block row `row` on NT threads: embedding gather -> residual stream; input_layernorm -> blk_out.
+// red: NT / 32 floats of shared memory. NAMED: the NT = 128 epilogue threads meet at named barrier 1; otherwise the
+// whole CTA (NT threads) at barrier 0.
+template <int NT, bool NAMED>
 __device__ __forceinline__ void ctxnorm_embed_row(const CtxNormEpi& e, int row, int tid, float* red) {
+  constexpr int kEmbedMaxIt = (8192 + NT * 4 - 1) / (NT * 4);  // hidden <= 8192
+  auto sync = [&]() {
+    if (NAMED) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    else __syncthreads();
+  };
   const int H = static_cast<int>(e.ld);
   long long tok = row;  // ids == null: `embed` already holds this row
   if (e.ids != nullptr) {
@@ -208,12 +221,12 @@ __device__ __forceinline__ void ctxnorm_embed_row(const CtxNormEpi& e, int row, 
   float ss = 0.f;
 #pragma unroll
   for (int k = 0; k < kEmbedMaxIt; ++k) {
-    const int n = tid * 4 + k * 512;
+    const int n = tid * 4 + k * NT * 4;
     if (n < H) v[k] = *reinterpret_cast<const uint2*>(src + n);
   }
 #pragma unroll
   for (int k = 0; k < kEmbedMaxIt; ++k) {
-    const int n = tid * 4 + k * 512;
+    const int n = tid * 4 + k * NT * 4;
     if (n < H) {
       *reinterpret_cast<uint2*>(e.resid + roff + n) = v[k];
       const float4 x = unpack4_bf16(v[k]);
@@ -221,14 +234,16 @@ __device__ __forceinline__ void ctxnorm_embed_row(const CtxNormEpi& e, int row, 
     }
   }
   ss = warp_sum(ss);
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");  // red[] of the previous row has been consumed
+  sync();  // red[] of the previous row has been consumed
   if ((tid & 31) == 0) red[tid >> 5] = ss;
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");
-  const float tot = red[0] + red[1] + red[2] + red[3];
+  sync();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) tot += red[w];
   const float rstd = 1.0f / sqrtf(tot / static_cast<float>(H) + e.eps);
 #pragma unroll
   for (int k = 0; k < kEmbedMaxIt; ++k) {
-    const int n = tid * 4 + k * 512;
+    const int n = tid * 4 + k * NT * 4;
     if (n < H) {
       const float4 x = unpack4_bf16(v[k]);
       const float4 w = unpack4_bf16(*reinterpret_cast<const uint2*>(e.ln_w + n));

@@ -51,9 +51,37 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, long long rows, lo
   return 0;
 }
 
+// One selected target hidden state [n_req * rows_per_req, hidden] bf16 seen as [n_req][rows_per_req][hidden], tiled as
+// [box_req x SL x 64] boxes (128-byte swizzle): box row (r, j) is activation row r * SL + j of the a_in layout; slots
+// j >= rows_per_req and requests past n_req are out of bounds and therefore zero-filled.
+inline int make_tmap_hidden3d(CUtensorMap* out, const void* base, int n_req, int rows_per_req, long long hidden,
+                              int SL, int box_req) {
+  PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
+  if (!fn) return -2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (hidden * 2) % 16 != 0) {
+    set_error("tensor map: hidden-state base/pitch must be 16-byte aligned");
+    return -1;
+  }
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(hidden), static_cast<cuuint64_t>(rows_per_req),
+                        static_cast<cuuint64_t>(n_req)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(hidden) * 2, static_cast<cuuint64_t>(hidden) * 2 * rows_per_req};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kTileK), static_cast<cuuint32_t>(SL), static_cast<cuuint32_t>(box_req)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (hidden state, 3-D) failed: %d (req=%d rows=%d hidden=%lld SL=%d box_req=%d)",
+              static_cast<int>(r), n_req, rows_per_req, hidden, SL, box_req);
+    return -3;
+  }
+  return 0;
+}
+
 struct GemmPlan {
   CUtensorMap tmW;
   CUtensorMap tmX;
+  XMaps xm;   // kModeCtxNorm direct mode only
   GemmArgs args;
   int mb;     // UMMA N (padded activation rows): 16, 32, 64, 128, 256
   int mode;   // GemmMode
@@ -78,8 +106,12 @@ inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pd
   using Cfg = GemmCfg<MB, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<MB, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e;
+    if constexpr (MODE == kModeCtxNorm)
+      e = cudaFuncSetAttribute(gemm_ctx_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    else
+      e = cudaFuncSetAttribute(gemm_skinny_kernel<MB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -94,7 +126,8 @@ inline cudaError_t launch_gemm_t(const GemmPlan& p, cudaStream_t stream, bool pd
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<MB, MODE>, p.tmW, p.tmX, p.args);
+  if constexpr (MODE == kModeCtxNorm) return cudaLaunchKernelEx(&cfg, gemm_ctx_kernel<MB>, p.tmW, p.tmX, p.xm, p.args);
+  else return cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<MB, MODE>, p.tmW, p.tmX, p.args);
 }
 
 template <int MODE>

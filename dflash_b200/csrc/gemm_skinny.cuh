@@ -180,10 +180,18 @@ __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned in
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
+// Activation tensor maps of the context-injection kernel when it reads the selected target hidden states IN PLACE
+// (CtxNormEpi::direct): one 3-D map [R][block_size][hidden] per selected layer, box [MB / SL][SL][64] -- the box rows
+// come out in the a_in row order (request r, slot j), slots past block_size are zero-filled by the TMA unit. The
+// concatenation of extract_context_feature (model/utils.py:16-25) is then just "k-block kb belongs to tensor
+// kb / (hidden / 64)": no feature matrix is ever materialised.
+struct alignas(64) XMaps {
+  CUtensorMap m[8];
+};
+
 template <int MB, int MODE>
-__global__ void __launch_bounds__(GemmCfg<MB, MODE>::kThreads, 1)
-gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                   const __grid_constant__ GemmArgs a) {
+__device__ __forceinline__ void gemm_skinny_body(const CUtensorMap& tmW, const CUtensorMap& tmX, const CUtensorMap* xsel,
+                                                 const GemmArgs& a) {
   using Cfg = GemmCfg<MB, MODE>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -234,6 +242,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmX);
+    if (MODE == kModeCtxNorm && a.cn.direct)
+      for (int s = 0; s * a.cn.kb_per_sel < a.k_blocks; ++s) tma_prefetch_desc(xsel + s);
   }
   if (warp == kMmaWarp) {
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -276,13 +286,23 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_expect_tx(&full[i], Cfg::kStageBytes);
         load_w(i, static_cast<int>(u / a.k_blocks), static_cast<int>(u % a.k_blocks));
       }
-      pdl_wait();
+      // the activation tile of k-block kb into stage s
+      const bool direct = MODE == kModeCtxNorm && a.cn.direct != 0;
+      auto load_x = [&](int s, int kb) {
+        if (MODE == kModeCtxNorm && direct) {
+          const int sel = kb / a.cn.kb_per_sel;
+          tma_load_3d(sX + s * Cfg::kXBytes, xsel + sel, &full[s], (kb - sel * a.cn.kb_per_sel) * kTileK, 0,
+                      m0 / a.cn.SL, polX);
+        } else {
+          tma_load_2d(sX + s * Cfg::kXBytes, &tmX, &full[s], kb * kTileK, a.x_row0 + m0, polX);
+        }
+      };
+      // (direct context injection: the hidden states were complete before the verify kernel in front of this one
+      // released it -- that kernel waits before it triggers -- so the main loop does not wait for the verify kernel)
+      if (!direct) pdl_wait();
       if (tr) tr[2] = global_ns();
       DFL_TRACE_ANY(1);
-      for (int i = 0; i < npre; ++i) {
-        const int kb = static_cast<int>((u0 + i) % a.k_blocks);
-        tma_load_2d(sX + i * Cfg::kXBytes, &tmX, &full[i], kb * kTileK, a.x_row0 + m0, polX);
-      }
+      for (int i = 0; i < npre; ++i) load_x(i, static_cast<int>((u0 + i) % a.k_blocks));
       int stage = npre % S;
       uint32_t phase = (npre == S) ? 1u : 0u;
       for (long long u = u0 + npre; u < u1; ++u) {
@@ -291,7 +311,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_wait(&empty[stage], phase ^ 1u);
         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
         load_w(stage, tile, kb);
-        tma_load_2d(sX + stage * Cfg::kXBytes, &tmX, &full[stage], kb * kTileK, a.x_row0 + m0, polX);
+        load_x(stage, kb);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
@@ -337,7 +357,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..kEpiWarps-1)
-    pdl_wait();
+    if (!(MODE == kModeCtxNorm && a.cn.direct != 0)) pdl_wait();
     int acc = 0;
     uint32_t acc_phase = 0;
     const int quarter = warp & 3;                       // TMEM lanes [32 * quarter, +32)
@@ -461,10 +481,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     constexpr bool kPlanes = MODE == kModePartials || MODE == kModeCtxNorm;  // fp32 partial planes in `ws`
     if constexpr (MODE == kModeCtxNorm) {
       // block rows: embedding gather + first input_layernorm, while the first accumulator is still being built
+      // (direct mode: the block's first token is written by the verify kernel this launch overlaps -- done at the end)
       __shared__ float s_red[4];
       const int n_cta = static_cast<int>(gridDim.x * gridDim.y);
-      for (int row = static_cast<int>(blockIdx.y * gridDim.x + blockIdx.x); row < a.cn.n_blk_rows; row += n_cta)
-        ctxnorm_embed_row(a.cn, row, epi_tid, s_red);
+      if (!a.cn.direct)
+        for (int row = static_cast<int>(blockIdx.y * gridDim.x + blockIdx.x); row < a.cn.n_blk_rows; row += n_cta)
+          ctxnorm_embed_row<128, true>(a.cn, row, epi_tid, s_red);
     }
     constexpr int kKeep = MODE == kModeTopK ? kTopK : 1;  // running bests per activation row (sorted, descending)
     constexpr bool kSample = MODE == kModeSample;
@@ -726,6 +748,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_fence_init();
       }
     }
+    // direct mode: everything from here on reads what the verify kernel wrote (accepted lengths, the next block).
+    // The idle lanes must not sit in griddepcontrol.wait while lane 0 of their warp is still issuing loads / MMAs (a
+    // blocked divergent path starves the other one -- measured: not one stage landed before the verify kernel had
+    // finished), so the warp reconverges first.
+    __syncwarp();
+    if (a.cn.direct) pdl_wait();
     if (tid == 0) {
       int live = 0;
       for (int row = me; row < a.m_valid; row += n_cta)
@@ -765,11 +793,35 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       a.cn.sync[0] = 0u;
       a.cn.sync[1] = 0u;
     }
+    if (a.cn.direct) {
+      // block rows (embedding gather + first input_layernorm), dealt from the LAST CTA downwards: the context rows
+      // above were dealt from the first CTA upwards, so at small batches no CTA gets both
+      __syncthreads();  // (s_red6 of the row pass has been consumed)
+      for (int row = n_cta - 1 - me; row < a.cn.n_blk_rows; row += n_cta)
+        ctxnorm_embed_row<Cfg::kThreads, false>(a.cn, row, tid, s_red6);
+    }
     DFL_TRACE(2);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int MB, int MODE>
+__global__ void __launch_bounds__(GemmCfg<MB, MODE>::kThreads, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                   const __grid_constant__ GemmArgs a) {
+  gemm_skinny_body<MB, MODE>(tmW, tmX, nullptr, a);
+}
+
+// The context-injection kernel (kModeCtxNorm) with the per-layer activation maps of its direct mode
+// (register cap: this kernel shares its SMs with the verify kernel it overlaps -- per SM sub-partition, four warps of
+// that kernel at 64 registers plus two of this one at 112 fit the 16 K registers)
+template <int MB>
+__global__ void __maxnreg__(112)
+gemm_ctx_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ XMaps xm, const __grid_constant__ GemmArgs a) {
+  gemm_skinny_body<MB, kModeCtxNorm>(tmW, tmX, xm.m, a);
 }
 
 }  // namespace dfl

@@ -314,10 +314,16 @@ struct VerifyFusedArgs {
   unsigned int* counters;  // [R + 1] arrivals per request, then of the whole grid (self-resetting)
 };
 
-__global__ void __launch_bounds__(256) verify_fused_kernel(const VerifyFusedArgs v) {
-  DFL_VERIFY_SYNC();
-  const int row = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+__global__ void __launch_bounds__(256, 4) verify_fused_kernel(const VerifyFusedArgs v) {
+  // wait first, release second: the context-injection kernel behind this one starts its fc main loop without waiting
+  // for this kernel, on the strength of "everything in front of the verify kernel (the target's forward, the draft
+  // step) is complete once the verify kernel has released its dependent"
+  DFL_WAIT_THEN_TRIGGER();
+  const int split = blockIdx.x, nsplit = gridDim.x;
   const int bs = v.acc.bs;
+  // gridDim.y may be smaller than the number of block rows (wide batches): the grid is kept to about two CTAs per SM
+  // so that the context-injection kernel behind this one finds room on every SM while this kernel is still running
+  for (int row = blockIdx.y; row < v.post.rows; row += gridDim.y) {
   const int r = row / bs, i = row % bs;
   {
     const GatherArgs& g = v.gather;
@@ -345,6 +351,7 @@ __global__ void __launch_bounds__(256) verify_fused_kernel(const VerifyFusedArgs
   if (s_last) {
     __threadfence();
     if (threadIdx.x < 32) accept_request(v.acc, r, threadIdx.x);
+  }
   }
   if (threadIdx.x == 0) {
     __threadfence();

@@ -72,6 +72,14 @@ def _declare(lib):
     lib.dflash_verify_step.restype = c_int
     lib.dflash_verify_step.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, POINTER(c_void_p), c_float,
                                        c_void_p, c_ulonglong, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
+    lib.dflash_verify_inject_step.restype = c_int
+    lib.dflash_verify_inject_step.argtypes = lib.dflash_verify_step.argtypes
+    lib.dflash_draft_step_injected.restype = c_int
+    lib.dflash_draft_step_injected.argtypes = [c_void_p, c_int, c_float, c_ulonglong, c_void_p]
+    lib.dflash_embed_block.restype = c_int
+    lib.dflash_embed_block.argtypes = [c_void_p, c_void_p]
+    lib.dflash_engine_launches.restype = c_int
+    lib.dflash_engine_launches.argtypes = [c_void_p, c_int]
     lib.dflash_draft_step_sampled.restype = c_int
     lib.dflash_draft_step_sampled.argtypes = [c_void_p, c_float, c_ulonglong, c_void_p]
     lib.dflash_gemm_sample.restype = c_int
@@ -240,13 +248,20 @@ class DraftEngine:
         self.cand_scores = self.buf["cand_scores"].view(R, 4)
         self.SL = 16 if bs <= 16 else 32
         self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
-        # launches per draft step of the schedule actually enqueued (engine.cuh): the context-injection kernel (fc GEMM
-        # + hidden_norm + block embedding + first layernorm), per layer {qkv GEMM, qkv_post, attention, merge, o GEMM, row
-        # kernel, gate/up GEMM (SwiGLU epilogue), down GEMM, row kernel}, lm_head GEMM (argmax + drafted tokens); the
-        # verify step is one kernel
-        self.kernels_per_draft_step = 1 + 9 * cfg.num_hidden_layers + 1
-        self.kernels_per_verify_step = 1
+        # launches of the schedule actually enqueued (engine.cuh), as the library counts them. Per layer {qkv GEMM,
+        # qkv_post, attention, merge (only with several KV splits), o GEMM, row kernel, gate/up GEMM (SwiGLU epilogue),
+        # down GEMM, row kernel}, lm_head GEMM (argmax + drafted tokens); the context-injection kernel (concat + fc +
+        # hidden_norm + block embedding + first layernorm) is the first kernel of draft_step() or, with
+        # verify_step(inject=True), the second kernel of the verify step (where it overlaps the verify kernel)
+        n = [self.lib.dflash_engine_launches(self.handle, w) for w in range(4)]
+        self.kernels_per_draft_step, self.kernels_per_draft_step_injected = n[0], n[1]
+        self.kernels_per_verify_step, self.kernels_per_verify_inject_step = n[2], n[3]
         self._graph = None
+        self._graph_injected = None
+        # where the next draft step finds its activation rows: "no" = nothing injected (draft_step runs the injection
+        # kernel itself, from the gathered features); "fresh" = injected by verify_step(inject=True);
+        # "stale" = a draft step has already consumed them (the block rows are re-embedded before another one)
+        self._injected = "no"
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -285,6 +300,8 @@ class DraftEngine:
             raise ValueError("hist_len too small: one acceptance-length entry per cycle is kept")
         if self.R == 1:  # a fresh request restarts the Philox step: same seed -> same draws (engines are cached)
             self.buf["rng_step"].zero_()
+        if self._injected == "fresh":
+            self._injected = "stale"  # the block rows of this request are embedded again before the next draft step
 
     def _call(self, name: str, *args):
         """Every library call runs with the engine's device current (the C side launches on the current device)."""
@@ -301,25 +318,46 @@ class DraftEngine:
         self._call("dflash_prefill_context_at", self.handle, r, arr, P, int(pos0), _stream(self.device))
         self._keep = hs
 
+    def embed_block(self):
+        """embed_tokens(block_ids) -> residual stream + layer 0's input_layernorm (model/dflash.py:237) for every stream."""
+        self._call("dflash_embed_block", self.handle, _stream(self.device))
+
     def draft_step(self, noise_embedding: Optional[torch.Tensor] = None, lm_head: bool = True):
+        if noise_embedding is None and self._injected != "no":
+            return self.draft_step_injected(lm_head=lm_head)
         self._call("dflash_draft_step", self.handle, _p(noise_embedding), int(lm_head), _stream(self.device))
+        self._injected = "no"
+
+    def draft_step_injected(self, lm_head: bool = True, temperature: float = 0.0, seed: int = 0):
+        """The draft step without its injection kernel (the previous verify_step(inject=True) ran it)."""
+        if self._injected == "stale":
+            self.embed_block()
+        self._call("dflash_draft_step_injected", self.handle, int(lm_head), float(temperature), int(seed) & (2**64 - 1),
+                   _stream(self.device))
+        self._injected = "stale"
 
     def verify_step(self, target_logits: Optional[torch.Tensor], hidden: Sequence[torch.Tensor], *,
                     temperature: float = 0.0, posterior_in: Optional[torch.Tensor] = None,
                     noise: Optional[torch.Tensor] = None, seed: int = 0, stop_ids: Optional[torch.Tensor] = None,
-                    forced_k: Optional[torch.Tensor] = None, clamp_tail: bool = False):
-        """target_logits: [R*bs, V] bf16 (last dim contiguous); hidden[s]: [R*bs, H] bf16 contiguous."""
+                    forced_k: Optional[torch.Tensor] = None, clamp_tail: bool = False, inject: bool = False):
+        """target_logits: [R*bs, V] bf16 (last dim contiguous); hidden[s]: [R*bs, H] bf16 contiguous.
+        inject: also run the NEXT cycle's context injection, overlapped with the verify kernel and reading `hidden` in
+        place (dflash_verify_inject_step); the next draft step then skips its injection kernel."""
         arr = (c_void_p * self.n_sel)(*[h.data_ptr() for h in hidden])
         ld = 0 if target_logits is None else target_logits.stride(-2)
         n_stop = 0 if stop_ids is None else int(stop_ids.numel())
         fld = 0 if forced_k is None else int(forced_k.shape[-1])
-        self._call("dflash_verify_step", self.handle, _p(target_logits), ld, _p(posterior_in), arr,
-                                               float(temperature), _p(noise), int(seed) & (2**64 - 1), _p(stop_ids),
-                                               n_stop, _p(forced_k), fld, int(clamp_tail), _stream(self.device))
+        self._call("dflash_verify_inject_step" if inject else "dflash_verify_step", self.handle, _p(target_logits), ld,
+                   _p(posterior_in), arr, float(temperature), _p(noise), int(seed) & (2**64 - 1), _p(stop_ids),
+                   n_stop, _p(forced_k), fld, int(clamp_tail), _stream(self.device))
+        self._injected = "fresh" if inject else "no"
+        self._keep_hidden = list(hidden) if inject else None  # re-read in place by the injection kernel
 
     def draft_step_sampled(self, temperature: float, seed: int = 0):
         """Draft step whose tokens are drawn from softmax(draft_logits / temperature) in the lm_head epilogue
         (benchmark_dynamic_schedule.py:342); temperature 0 = the greedy step."""
+        if self._injected != "no":
+            return self.draft_step_injected(temperature=temperature, seed=seed)
         self._call("dflash_draft_step_sampled", self.handle, float(temperature), int(seed) & (2**64 - 1),
                                                       _stream(self.device))
 
@@ -327,6 +365,7 @@ class DraftEngine:
         """Draft step with the top-4 lm_head epilogue; fills cand_ids[:, :n_candidates] / cand_scores
         (fixed_prefix_rank candidates, benchmark_candidate_solutions.py:181-249)."""
         self._call("dflash_draft_step_candidates", self.handle, int(n_candidates), int(fixed_prefix_len), _stream(self.device))
+        self._injected = "no"
 
     def verify_step_candidates(self, n_candidates: int, target_logits: torch.Tensor, hidden: Sequence[torch.Tensor], *,
                                temperature: float = 0.0, noise: Optional[torch.Tensor] = None, seed: int = 0,
@@ -338,6 +377,7 @@ class DraftEngine:
                                                           target_logits.stride(-2), arr, float(temperature), _p(noise),
                                                           int(seed) & (2**64 - 1), _p(stop_ids), n_stop, int(clamp_tail),
                                                           _stream(self.device))
+        self._injected = "no"
 
     def sample(self, logits: torch.Tensor, temperature: float, seed: int = 0, noise: Optional[torch.Tensor] = None):
         """sample() of model/utils.py:27-34 on [rows, V] bf16 logits -> int64 [rows]."""
@@ -351,27 +391,52 @@ class DraftEngine:
         return out
 
     # ------------------------------------------------------------------------------------------
-    def capture_draft_graph(self):
-        """Capture one draft step (static pointers, device-resident state) into a CUDA graph."""
+    def capture_draft_graph(self, injected: bool = False):
+        """Capture one draft step (static pointers, device-resident state) into a CUDA graph: the full step, or
+        (injected) the step without its injection kernel."""
         torch.cuda.synchronize(self.device)
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         # the warm-up step runs on live request state: keep the block (slots 1.. are mask tokens until the first real
         # draft step fills them, model/dflash.py:233-235) and the draft tokens it would overwrite
         keep_blk, keep_tok = self.buf["block_ids"].clone(), self.buf["draft_tokens"].clone()
+        state = self._injected
         with torch.cuda.stream(s):
-            self.draft_step()  # warm up (module load, func attributes) outside capture
+            # warm up (module load, func attributes) outside capture
+            if injected:
+                self._call("dflash_draft_step_injected", self.handle, 1, 0.0, 0, _stream(self.device))
+            else:
+                self._call("dflash_draft_step", self.handle, None, 1, _stream(self.device))
             self.buf["block_ids"].copy_(keep_blk)
             self.buf["draft_tokens"].copy_(keep_tok)
+            if injected:  # the warm-up consumed the block rows: put them back
+                self.embed_block()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
-            self.draft_step()
-        self._graph = g
+            if injected:
+                self._call("dflash_draft_step_injected", self.handle, 1, 0.0, 0, _stream(self.device))
+            else:
+                self._call("dflash_draft_step", self.handle, None, 1, _stream(self.device))
+        self._injected = state
+        if injected:
+            self._graph_injected = g
+        else:
+            self._graph = g
         return g
 
     def draft_step_graphed(self):
+        """One draft step replayed from a CUDA graph: without the injection kernel when the previous
+        verify_step(inject=True) (or the prompt pass) has already prepared the activation rows."""
+        if self._injected != "no":
+            if self._graph_injected is None:
+                self.capture_draft_graph(injected=True)
+            if self._injected == "stale":
+                self.embed_block()
+            self._graph_injected.replay()
+            self._injected = "stale"
+            return
         if self._graph is None:
             self.capture_draft_graph()
         self._graph.replay()

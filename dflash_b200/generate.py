@@ -130,7 +130,7 @@ def dflash_generate(model, target, input_ids: torch.Tensor, mask_token_id: int, 
                 if eff < bs:
                     logits = torch.nn.functional.pad(logits, (0, 0, 0, bs - eff))
                     hidden = [torch.nn.functional.pad(h, (0, 0, 0, bs - eff)) for h in hidden]
-                eng.verify_step(logits, hidden, temperature=temperature, seed=seed, stop_ids=stop_t, clamp_tail=True)
+                eng.verify_step(logits, hidden, temperature=temperature, seed=seed, stop_ids=stop_t, clamp_tail=True, inject=True)
                 state[0:1].copy_(eng.buf["start"][0:1], non_blocking=True)
                 state[1:2].copy_(eng.buf["done"][0:1], non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()

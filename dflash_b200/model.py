@@ -295,7 +295,7 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
             if logits.dtype != torch.bfloat16:
                 logits = logits.to(torch.bfloat16)
             e.verify_step(logits, hidden, temperature=temperature, seed=seed, stop_ids=stop_t, forced_k=forced_t,
-                          clamp_tail=clamp_tail)
+                          clamp_tail=clamp_tail, inject=True)
             cyc += 1
             if cyc % max(1, sync_every) == 0:  # blind cycles past the end are frozen on the device (`done`)
                 state[0:1].copy_(e.buf["start"][0:1], non_blocking=True)
@@ -320,7 +320,7 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
                 logits = torch.nn.functional.pad(logits, (0, 0, 0, bs - eff))
                 hidden = [torch.nn.functional.pad(h, (0, 0, 0, bs - eff)) for h in hidden]
             e.verify_step(logits, hidden, temperature=temperature, seed=seed, stop_ids=stop_t, forced_k=forced_t,
-                          clamp_tail=clamp_tail)
+                          clamp_tail=clamp_tail, inject=True)
             # the one host sync of the cycle: the HF target needs `start` to slice positions / crop its cache
             state[0:1].copy_(e.buf["start"][0:1], non_blocking=True)
             state[1:2].copy_(e.buf["done"][0:1], non_blocking=True)

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DFLASH_ABI_VERSION 2
+#define DFLASH_ABI_VERSION 3
 
 #define DFLASH_OK 0
 #define DFLASH_ERR_ARG (-1)   /* bad argument / unsupported shape */
@@ -57,7 +57,7 @@ typedef struct dflash_config {
   float rope_scale;     /* rotary attention_scaling (1.0 for default rope) */
   long long mask_token_id;
   int attn_splits;      /* KV splits of the draft attention (0 = about two waves of CTAs, 1..16) */
-  int post_splits;      /* vocab splits of the posterior sampler (0 = about four waves of CTAs, 2..32) */
+  int post_splits;      /* vocab splits of the posterior sampler (0 = about two CTAs per SM in all, 1..32) */
   int gemm_grid;        /* CTAs per streaming GEMM (0 = SM count) */
   int use_pdl;          /* programmatic dependent launch between the step's kernels */
   int keep_draft_logits;/* also store the draft's bf16 logits (parity tests) */
@@ -189,6 +189,35 @@ int dflash_verify_step(dflash_engine_t* e, const void* target_logits, long long 
                        const long long* posterior_in, const void* const* hidden_host, float temperature,
                        const float* noise, unsigned long long seed, const long long* stop_ids, int n_stop,
                        const int* forced_k, int forced_ld, int clamp_tail, void* stream);
+
+/* The verify step AND the next cycle's target-context injection (north-star subsystems (d) + (a)) as two kernels
+ * that overlap: dflash_verify_step's kernel, and behind it the context-injection kernel reading the first tau rows of
+ * the selected hidden states IN PLACE through one tensor map per selected layer -- the concatenation of
+ * extract_context_feature (model/utils.py:16-25), the fc projection, hidden_norm (model/dflash.py:177), the next
+ * block's embedding and layer 0's input_layernorm (:237) in ONE kernel whose fc main loop runs while the verify kernel
+ * is still sampling and accepting; only its row pass waits for the accepted lengths. Same arguments as
+ * dflash_verify_step; hidden_host[s] must stay valid until the work enqueued here has run (they are re-read, not
+ * copied). The next draft step is then dflash_draft_step_injected.
+ * Replaces model/dflash.py:257-268 plus, for the next cycle, :263 (extract_context_feature), :177 and :237. */
+int dflash_verify_inject_step(dflash_engine_t* e, const void* target_logits, long long logits_ld,
+                              const long long* posterior_in, const void* const* hidden_host, float temperature,
+                              const float* noise, unsigned long long seed, const long long* stop_ids, int n_stop,
+                              const int* forced_k, int forced_ld, int clamp_tail, void* stream);
+
+/* dflash_draft_step without its first kernel: the context rows and the block rows were already injected by
+ * dflash_verify_inject_step (a caller that rewrites block_ids in between -- a request reset -- runs
+ * dflash_embed_block first). temperature >= 1e-5 samples the drafted tokens as dflash_draft_step_sampled does.
+ * Replaces model/dflash.py:238-247. */
+int dflash_draft_step_injected(dflash_engine_t* e, int run_lm_head, float temperature, unsigned long long seed,
+                               void* stream);
+
+/* Block rows only: embed_tokens(block_ids) -> residual stream, layer 0's input_layernorm -> activation rows
+ * (model/dflash.py:237). For callers that rewrite block_ids before a dflash_draft_step_injected. */
+int dflash_embed_block(dflash_engine_t* e, void* stream);
+
+/* Kernel launches one call enqueues: which = 0 dflash_draft_step, 1 dflash_draft_step_injected, 2 dflash_verify_step,
+ * 3 dflash_verify_inject_step (plain verify path). */
+int dflash_engine_launches(const dflash_engine_t* e, int which);
 
 /* dflash_draft_step with the drafted tokens SAMPLED from softmax(draft_logits / temperature) instead of argmax-ed
  * (the reference's policy loop does that: benchmark_dynamic_schedule.py:342; spec_generate itself always drafts

@@ -26,13 +26,22 @@ ph = [(torch.randn(128, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) fo
 prompt = torch.randint(0, V - 1, (128,), device=dev, generator=g)
 ks = bench.forced_schedule(seed=0)
 forced = torch.tensor([ks], dtype=torch.int32, device=dev)
+INJECT = os.environ.get("DFLASH_TRACE_NO_INJECT") is None
 eng.reset_request(0, prompt, 1, 2048)
 eng.prefill_context(0, ph)
+if INJECT:
+    eng.embed_block()
 
 
 def step():
-    eng.draft_step()
-    eng.verify_step(tl, hsel, temperature=0.0, forced_k=forced)
+    if INJECT:
+        eng._injected = "fresh"
+        eng.draft_step_injected()
+        eng.verify_step(tl, hsel, temperature=0.0, forced_k=forced, inject=True)
+    else:
+        eng._injected = "no"
+        eng.draft_step()
+        eng.verify_step(tl, hsel, temperature=0.0, forced_k=forced)
 
 
 step()
@@ -57,7 +66,7 @@ torch.cuda.synchronize()
 rec = buf.view(cap, 2).cpu()
 rec = rec[rec[:, 1] != 0]
 names = {(512, 32, 1): "finalize2", (256, 4, 16): "finalize_cl", (256, 192, 1): "qkv_post", (128, 16, 8): "attn_split",
-         (256, 64, 1): "attn_combine", (256, 32, 16): "verify", (192, 1, 148): "gemm", (192, 1, 132): "gemm_lm"}
+         (256, 64, 1): "attn_combine", (256, 32, 16): "verify", (256, 18, 16): "verify", (192, 1, 148): "gemm", (192, 1, 132): "gemm_lm"}
 ev = []
 for tag, t in rec.tolist():
     phase, bd, gx, gy = tag & 15, (tag >> 4) & 0xFFF, (tag >> 16) & 0xFFFFFF, (tag >> 40) & 0xFFFFFF

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
             "dflash_sample", "dflash_gemm_skinny", "dflash_gemm_argmax", "dflash_workspace_bytes"} <= set(names)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dflash_b200.h but not exported"
-    assert lib.dflash_abi_version() == 2
+    assert lib.dflash_abi_version() == 3
 
 
 def test_no_torch_types_in_abi():

@@ -350,7 +350,9 @@ __device__ __forceinline__ void gemm_skinny_body(const CUtensorMap& tmW, const C
         }
         umma_commit(&tfull[acc]);  // accumulator complete
         if (tr && u >= u1) tr[4] = global_ns();
-        if (MODE == kModeCtxNorm && u >= u1) pdl_trigger();
+        // (direct mode releases its dependents only after its own wait for the verify kernel, in the tail: kernels
+        // further down the chain read request state before THEIR waits, on the strength of "the verify kernel is complete")
+        if (MODE == kModeCtxNorm && !a.cn.direct && u >= u1) pdl_trigger();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -753,7 +755,10 @@ __device__ __forceinline__ void gemm_skinny_body(const CUtensorMap& tmW, const C
     // blocked divergent path starves the other one -- measured: not one stage landed before the verify kernel had
     // finished), so the warp reconverges first.
     __syncwarp();
-    if (a.cn.direct) pdl_wait();
+    if (a.cn.direct) {
+      pdl_wait();
+      pdl_trigger();
+    }
     if (tid == 0) {
       int live = 0;
       for (int row = me; row < a.m_valid; row += n_cta)

@@ -8,6 +8,6 @@ python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; e
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-sharded --no-gpu-reference --no-full-cycle > gpurun_out/${tag}_ncu_l.log 2>&1; echo "ncu list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm_skinny_kernel -s 60 -c 24 -o gpurun_out/${tag}_gemm -f \
+ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 60 -c 24 -o gpurun_out/${tag}_gemm -f \
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-sharded --no-gpu-reference --no-full-cycle > gpurun_out/${tag}_ncu_g.log 2>&1; echo "ncu full rc=$?"
 tail -3 gpurun_out/${tag}_tests.log

@@ -8,6 +8,8 @@ def short(n):
     n = re.sub(r'dfl::', '', n); n = re.sub(r'void ', '', n); return re.sub(r'\(.*', '', n)
 lm = [i for i, d in enumerate(data) if re.search(r'gemm_skinny_kernel<\d+, 1>', d[0])]  # lm_head GEMM (argmax mode)
 pairs = [(x + 1, y + 1) for x, y in zip(lm, lm[1:]) if y - x >= 20]  # (back-to-back lm_head launches = the roofline timing loop)
+if not pairs:
+    sys.exit(f"no complete step between two lm_head GEMMs among the {len(data)} captured launches (raise ncu's -c / -s)")
 a, b = min(pairs, key=lambda p: p[1] - p[0])   # kernels after one lm_head GEMM up to and including the next = one step (no request reset inside)
 step = data[a:b]
 agg = collections.OrderedDict()

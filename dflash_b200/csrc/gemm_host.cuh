@@ -218,6 +218,14 @@ inline int make_gemm_plan(GemmPlan* p, const void* W, long long w_rows_total, in
   const int groups = m_valid > mb ? (m_valid + mb - 1) / mb : 1;
   if (x_row0 + groups * mb > x_rows_total) { set_error("gemm: activation buffer too small"); return -1; }
   grid = ranges_for(grid, groups);
+  if (groups > 1 && (mode == kModePartials || mode == kModeCtxNorm)) {
+    // Wide batches are tensor-bound and their consumers pay for every fp32 partial plane (64 streams: 150 MB per QKV
+    // launch): when a range count that divides the tile count exists within 20 % of the full one, cut on tile
+    // boundaries -- every tile then has ONE slot (4 x 32 instead of 4 x 37 ranges for the 32 tiles of o / down).
+    const int nt = (N + kTileN - 1) / kTileN;
+    for (int g = grid; g * 5 >= grid * 4 && g >= 1; --g)
+      if (nt % g == 0) { grid = g; break; }
+  }
   if (mode_is_fused(mode) && N % kTileN != 0) {
     set_error("gemm: fused epilogues need N (%d) to be a multiple of %d", N, kTileN);
     return -1;

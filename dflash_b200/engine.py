@@ -247,7 +247,7 @@ class DraftEngine:
         self.cand_ids = self.buf["cand_ids"].view(R, 4, bs)        # candidate blocks (multi-candidate drafting)
         self.cand_scores = self.buf["cand_scores"].view(R, 4)
         self.SL = 16 if bs <= 16 else 32
-        self.hn = self.buf["hn"].view(R * self.SL, self.hidden)
+        self.hn = self.buf["hn"].view(-1, self.hidden)[:R * self.SL]  # (the buffer is padded to the UMMA width)
         # launches of the schedule actually enqueued (engine.cuh), as the library counts them. Per layer {qkv GEMM,
         # qkv_post, attention, merge (only with several KV splits), o GEMM, row kernel, gate/up GEMM (SwiGLU epilogue),
         # down GEMM, row kernel}, lm_head GEMM (argmax + drafted tokens); the context-injection kernel (concat + fc +

@@ -995,6 +995,61 @@ def test_verify_with_given_posterior_and_stop_and_clamp():
 
 
 # ------------------------------------------------------------------------------------------------
+# the two forms of the context injection give the same draft: at the head of the draft step from gathered features, or
+# behind the verify kernel reading the hidden states in place (dflash_verify_inject_step / dflash_draft_step_injected)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bs,R", [(16, 1), (8, 3), (32, 2)])
+def test_injection_forms_agree(bs, R):
+    dev = _cuda()
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY
+    target, draft = _tiny(bs)
+    H, V, nsel = TINY["hidden"], TINY["vocab"], len(draft.target_layer_ids)
+    g = torch.Generator(device=dev).manual_seed(11)
+    P = 29
+    hs0 = [(torch.randn(P, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+    prompt = torch.randint(0, V - 1, (P,), device=dev, generator=g)
+    engs = [DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=P + 8 * bs,
+                        out_len=P + 7 * bs, max_requests=R, block_size=bs, keep_draft_logits=True) for _ in range(2)]
+    for e in engs:
+        for r in range(R):
+            e.reset_request(r, prompt, 7 + r, 5 * bs)
+            e.prefill_context(r, hs0)
+    forced = torch.tensor([[2, bs - 1, 0, 5][r % 4:] + [1] * (r % 4) for r in range(R)], dtype=torch.int32, device=dev)
+    for cyc in range(4):
+        for e in engs:
+            e.draft_step()
+        torch.cuda.synchronize()
+        # same inputs -> same draft, whichever kernel injected the context (the block rows' layernorm sums its squares
+        # over a different thread layout in the two forms: allow the last bf16 bit of the hidden state)
+        a = engs[0].hn.view(R, engs[0].SL, H)[:, :bs].float()
+        b = engs[1].hn.view(R, engs[1].SL, H)[:, :bs].float()
+        assert _rel_err(b, a) < 4e-3, (cyc, _rel_err(b, a))
+        same = (engs[0].block_ids == engs[1].block_ids).float().mean().item()
+        assert same >= 0.9, (cyc, same)  # (argmax flips only at near-ties of the tiny random head)
+        engs[1].block_ids.copy_(engs[0].block_ids)  # keep the integer state of the two engines comparable
+        tl = torch.randn(R * bs, V, device=dev, generator=g).to(torch.bfloat16)
+        hsel = [(torch.randn(R * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        if cyc == 2:  # the three-kernel verify (given posterior) with injection: the gathered form of the same kernel
+            post = tl.float().argmax(-1).view(R, bs).contiguous()
+            engs[0].verify_step(None, hsel, posterior_in=post, inject=False)
+            engs[1].verify_step(None, hsel, posterior_in=post, inject=True)
+        else:
+            engs[0].verify_step(tl, hsel, temperature=0.0, forced_k=forced, inject=False)
+            engs[1].verify_step(tl, hsel, temperature=0.0, forced_k=forced, inject=True)
+        torch.cuda.synchronize()
+        for name in ("start", "ctx_len", "done", "n_cycles"):
+            assert torch.equal(engs[0].buf[name], engs[1].buf[name]), (cyc, name)
+        assert torch.equal(engs[0].output_ids, engs[1].output_ids)
+        if cyc == 1 and R > 1:  # a slot is refilled between an injecting verify step and the next draft step
+            for e in engs:
+                e.reset_request(R - 1, prompt, 3, 5 * bs)
+                e.prefill_context(R - 1, hs0)
+    for e in engs:
+        e.close()
+
+
+# ------------------------------------------------------------------------------------------------
 # target verify forward from a CUDA graph over a static cache
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("sync_every", [1, 4])

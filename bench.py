@@ -361,6 +361,8 @@ def full_cycle_bench(dims, draft, eng, embed, lm_head, device, ks, new_tokens=51
     rows = (("default", None), ("eager_target", False), ("graphed_target", True))
     for name, graph in rows:
         draft.spec_generate(target, prompt, 64, None, 0.0, forced_k=ks, graph_target=graph)  # warm-up / capture
+        if graph is not False:  # (and one generation of the timed length: the first one after a capture runs ~1 ms
+            draft.spec_generate(target, prompt, new_tokens, None, 0.0, forced_k=ks, graph_target=graph)  # per cycle slower)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ids = draft.spec_generate(target, prompt, new_tokens, None, 0.0, forced_k=ks, graph_target=graph)

@@ -246,8 +246,10 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
             key = (id(target), bs, e.buf["start"].data_ptr())
             try:
                 gt = getattr(self, "_graphed_target", None)
-                if gt is None or getattr(self, "_graphed_target_key", None) != key or gt.max_cache_len < max_length + bs:
-                    cap = max(1024, 1 << (max_length + bs - 1).bit_length())
+                # (+ one more block: a blind cycle behind the end of the request -- sync_every > 1 -- still runs the target
+                # over the frozen block at positions [start, start + bs), start < max_length + bs)
+                if gt is None or getattr(self, "_graphed_target_key", None) != key or gt.max_cache_len < max_length + 2 * bs:
+                    cap = max(1024, 1 << (max_length + 2 * bs - 1).bit_length())
                     gt = GraphedVerifyTarget(target, bs, cap, self.target_layer_ids, e.buf["start"], e.block_ids)
                     self._graphed_target, self._graphed_target_key = gt, key
                 logits0, hidden0 = gt.prefill(input_ids)
@@ -297,6 +299,8 @@ class DFlashDraftModel(Qwen3PreTrainedModel):
             e.verify_step(logits, hidden, temperature=temperature, seed=seed, stop_ids=stop_t, forced_k=forced_t,
                           clamp_tail=clamp_tail, inject=True)
             cyc += 1
+            # (polling one cycle late, so that the GPU never waits for the host, was measured: the blind cycle at the
+            # end of the request costs more than the per-cycle sync it saves -- 11.49 vs 11.21 ms per cycle)
             if cyc % max(1, sync_every) == 0:  # blind cycles past the end are frozen on the device (`done`)
                 state[0:1].copy_(e.buf["start"][0:1], non_blocking=True)
                 state[1:2].copy_(e.buf["done"][0:1], non_blocking=True)

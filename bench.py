@@ -555,7 +555,10 @@ def timed_steps(runner, steps, warmup, device, local, sample_clocks=True):
     n_expect = int(runner.eng.buf["start"][0]) - PROMPT_LEN
     assert gathered.shape[0] == world and bool((gathered[:, :, 0] == n_expect).all()), "gathered lengths differ"
     return dict(value=tokens_all / (total_ms_max / 1e3), total_ms=total_ms_max, step_us=step_us,
-                gather_us=ddist.max_over_ranks(t_g0.elapsed_time(t_end) * 1e3, device), clocks=clock_info,
+                # the collective itself = what the LAST rank to arrive sees (min over ranks); the max also contains the
+                # wait for the slowest rank's steps, which `value` already counts (max over ranks of the whole region)
+                gather_us=-ddist.max_over_ranks(-t_g0.elapsed_time(t_end) * 1e3, device),
+                gather_wait_us_max=ddist.max_over_ranks(t_g0.elapsed_time(t_end) * 1e3, device), clocks=clock_info,
                 gather_bytes_per_rank=packed.numel() * 4)
 
 
@@ -722,6 +725,7 @@ def run_cuda_arm(args):
                                 "configs[4] shape at bs 16), forced-tau schedule, one packed all-gather per generation",
                        scaling="strong", global_batch=SHARDED_BATCH, streams_per_gpu=Rs, tokens_per_s=rs["value"],
                        step_us_median=su[len(su) // 2], steps=len(su), gather_us=rs["gather_us"],
+                       gather_wait_us_max=rs["gather_wait_us_max"],
                        gather_bytes_per_rank=rs["gather_bytes_per_rank"])
         eng_s.close()
         del runner_s, eng_s
@@ -770,7 +774,10 @@ def run_cuda_arm(args):
             clocks=clock_info,
             gather_us=res["gather_us"],
             gather=dict(collective="all_gather_into_tensor (NCCL), one packed int32 buffer per generation, inside the "
-                                   "timed region", bytes_per_rank=res["gather_bytes_per_rank"], us=res["gather_us"]),
+                                   "timed region", bytes_per_rank=res["gather_bytes_per_rank"], us=res["gather_us"],
+                        wait_us_max=res["gather_wait_us_max"],
+                        note="us = the collective as the last-arriving rank sees it; wait_us_max also holds the wait for "
+                             "the slowest rank's steps"),
             sharded_batch=sharded,
             gpu_reference=gpu_ref,
             step_speedup_vs_torch=(None if not gpu_ref or "error" in gpu_ref else

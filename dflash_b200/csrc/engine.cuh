@@ -26,6 +26,7 @@ struct Engine {
   size_t total = 0;
   Region reg[DFLASH_BUF_COUNT];
   int R, SL, RS, H, I, L, Hq, Hkv, V, nsel, bs, grid, nsplit_attn, nsplit_post, sm_count;
+  int row_block_max_rows = DFLASH_ROW_BLOCK_MAX_ROWS;
   bool pdl;
   // plans
   GemmPlan fc;                  // ctx_feat -> partials
@@ -390,6 +391,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     const int mx = cudaSharedmemCarveoutMaxShared;
     cudaFuncSetAttribute(finalize_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(finalize_rows_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(finalize_rows_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(qkv_post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
@@ -441,6 +443,10 @@ inline RowsArgs rows_args_base(const Engine* e) {
 inline cudaError_t launch_finalize(Engine* e, const RowsArgs& a, int rows, cudaStream_t st) {
   const bool ok = a.ws != nullptr && a.embed == nullptr && a.norm_w != nullptr &&
                   e->H % (4 * kRowCtas) == 0 && e->H / kRowCtas <= kRowClThreads * 4 * kRowClGroups;
+  // few rows (one or two streams): one 1024-thread CTA per row -- no cluster exchange; more rows want the four-fold
+  // spread of each row's loads over SMs
+  if (DFLASH_ROW_BLOCK && ok && e->H <= 4 * kRowBlkThreads && rows <= e->row_block_max_rows)
+    return launch_pdl(finalize_rows_block_kernel, dim3(rows), dim3(kRowBlkThreads), 0, st, e->pdl, a);
   if (ok)
     return launch_cluster_pdl(finalize_rows_cluster_kernel, dim3(kRowCtas, rows), dim3(kRowClThreads),
                               dim3(kRowCtas, 1, 1), 0, st, e->pdl, a);

@@ -358,6 +358,74 @@ __global__ void __launch_bounds__(kRowClThreads) finalize_rows_cluster_kernel(co
   DFL_TRACE(2);
 }
 
+// The same row pass on ONE CTA of 1024 threads per row (hidden <= 4096: four columns per thread, everything in
+// registers, all of a thread's slot loads in flight together, the row's sum of squares through shared memory): no
+// cluster barrier and no distributed-shared-memory exchange, which were 1.6-3 us of the cluster form's 4.9 us.
+#ifndef DFLASH_ROW_BLOCK
+#define DFLASH_ROW_BLOCK 1
+#endif
+#ifndef DFLASH_ROW_BLOCK_MAX_ROWS   // rows up to which the one-CTA form is used (tuning switch)
+#define DFLASH_ROW_BLOCK_MAX_ROWS 32
+#endif
+constexpr int kRowBlkThreads = 1024;
+
+__global__ void __launch_bounds__(kRowBlkThreads, 1) finalize_rows_block_kernel(const RowsArgs a) {
+  __shared__ int ns_tab[kRowsMaxTiles];
+  __shared__ float red[kRowBlkThreads / 32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  {
+    const int nt = (a.H + kTileN - 1) / kTileN;
+    for (int t = tid; t < nt; t += kRowBlkThreads) ns_tab[t] = tile_slots32(t, a.sm);
+  }
+  __syncthreads();
+  DFL_WAIT_THEN_TRIGGER();
+  if (a.valid_mode == kRowsCtx) {
+    const int r = row / a.SL, j = row % a.SL;
+    if (j >= a.ctx_len[r]) return;
+  }
+  const long long roff = static_cast<long long>(row) * a.H;
+  const int n = tid * 4;
+  const bool live = n < a.H;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint2 rs = make_uint2(0u, 0u), wv = make_uint2(0u, 0u);
+  if (live) {
+    wv = *reinterpret_cast<const uint2*>(a.norm_w + n);
+    if (a.resid != nullptr) rs = __ldcg(reinterpret_cast<const uint2*>(a.resid + roff + n));
+    x = sum_slots_4(a.ws, a.sm, row, n, ns_tab[n / kTileN]);
+    if (a.bias != nullptr) {
+      const float4 b = unpack4_bf16(*reinterpret_cast<const uint2*>(a.bias + n));
+      x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+    }
+  }
+  float ss = 0.f;
+  if (live) {
+    x.x = bf16_round(x.x); x.y = bf16_round(x.y); x.z = bf16_round(x.z); x.w = bf16_round(x.w);
+    if (a.resid != nullptr) {
+      const float4 rsd = unpack4_bf16(rs);
+      x.x = bf16_round(rsd.x + x.x); x.y = bf16_round(rsd.y + x.y);
+      x.z = bf16_round(rsd.z + x.z); x.w = bf16_round(rsd.w + x.w);
+      *reinterpret_cast<uint2*>(a.resid + roff + n) = pack4_bf16(x.x, x.y, x.z, x.w);
+    }
+    ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+  }
+  DFL_TRACE(4);
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  DFL_TRACE(5);
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < kRowBlkThreads / 32; ++w) tot += red[w];
+  const float rstd = 1.0f / sqrtf(tot / static_cast<float>(a.H) + a.eps);
+  if (live) {
+    const float4 w = unpack4_bf16(wv);
+    *reinterpret_cast<uint2*>(a.out + roff + n) =
+        pack4_bf16(w.x * bf16_round(x.x * rstd), w.y * bf16_round(x.y * rstd), w.z * bf16_round(x.z * rstd),
+                   w.w * bf16_round(x.w * rstd));
+  }
+  DFL_TRACE(2);
+}
+
 // ---------------------------------------------------------------------------------------------
 // QKV post-processing: per (row, head) warp. q/k: per-head RMSNorm over D=128 then RoPE
 // (half-split rotate, cos/sin rounded to bf16, products and sum rounded to bf16:

@@ -65,7 +65,7 @@ for _ in range(6):
 torch.cuda.synchronize()
 rec = buf.view(cap, 2).cpu()
 rec = rec[rec[:, 1] != 0]
-names = {(512, 32, 1): "finalize2", (256, 4, 16): "finalize_cl", (256, 192, 1): "qkv_post", (128, 16, 8): "attn_split",
+names = {(512, 32, 1): "finalize2", (256, 4, 16): "finalize_cl", (1024, 16, 1): "finalize_blk", (256, 192, 1): "qkv_post", (128, 16, 8): "attn_split",
          (256, 64, 1): "attn_combine", (256, 32, 16): "verify", (256, 18, 16): "verify", (192, 1, 148): "gemm", (192, 1, 132): "gemm_lm"}
 ev = []
 for tag, t in rec.tolist():

@@ -443,8 +443,8 @@ inline RowsArgs rows_args_base(const Engine* e) {
 inline cudaError_t launch_finalize(Engine* e, const RowsArgs& a, int rows, cudaStream_t st) {
   const bool ok = a.ws != nullptr && a.embed == nullptr && a.norm_w != nullptr &&
                   e->H % (4 * kRowCtas) == 0 && e->H / kRowCtas <= kRowClThreads * 4 * kRowClGroups;
-  // few rows (one or two streams): one 1024-thread CTA per row -- no cluster exchange; more rows want the four-fold
-  // spread of each row's loads over SMs
+  // up to 128 rows (8 streams): one 1024-thread CTA per row -- no cluster exchange (R = 1 / 2 / 8: -10 / -7 / -14 us per
+  // step; flat at 4); more rows than SMs want the four-fold spread of each row's loads
   if (DFLASH_ROW_BLOCK && ok && e->H <= 4 * kRowBlkThreads && rows <= e->row_block_max_rows)
     return launch_pdl(finalize_rows_block_kernel, dim3(rows), dim3(kRowBlkThreads), 0, st, e->pdl, a);
   if (ok)

@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kRowClThreads) finalize_rows_cluster_kernel(co
 #define DFLASH_ROW_BLOCK 1
 #endif
 #ifndef DFLASH_ROW_BLOCK_MAX_ROWS   // rows up to which the one-CTA form is used (tuning switch)
-#define DFLASH_ROW_BLOCK_MAX_ROWS 32
+#define DFLASH_ROW_BLOCK_MAX_ROWS 128
 #endif
 constexpr int kRowBlkThreads = 1024;
 

@@ -11,3 +11,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 60 -c 24 -o gpurun_out/${tag}_gemm -f \
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-sharded --no-gpu-reference --no-full-cycle > gpurun_out/${tag}_ncu_g.log 2>&1; echo "ncu full rc=$?"
 tail -3 gpurun_out/${tag}_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"
+DFLASH_LIB=$PWD/build/lib_trace_new.so python scripts/step_trace.py > gpurun_out/${tag}_trace.txt 2>&1; echo "trace rc=$?"

@@ -565,9 +565,10 @@ __global__ void __launch_bounds__(32 * kItemWarps) qkv_post_kernel(const QkvPost
   QkvItem it;
   it.kind = -1;
   // positions, rope table and norm weights while the QKV GEMM in front of this kernel is still running. The request
-  // state read here was written by the previous cycle's verify kernel, which has completed: the row kernel at the top
-  // of the step waits (griddepcontrol.wait) for the fc GEMM, whose own wait covers the verify kernel, before it
-  // releases anything behind it.
+  // state read here was written by the previous cycle's verify kernel, which has completed: every kernel of the draft
+  // step sits behind the context-injection kernel, and that kernel releases its dependents only after its own
+  // griddepcontrol.wait for the verify kernel has returned (gathered form: at its last MMA, whose operands were loaded
+  // after the wait; direct form: explicitly after the wait in its tail).
   if (item < a.rows * heads_per_row) it = qkv_post_prepare(a, a.row0 + item / heads_per_row, item % heads_per_row, lane);
   DFL_WAIT_THEN_TRIGGER();
   qkv_post_apply(a, it, lane);

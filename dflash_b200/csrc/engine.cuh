@@ -443,8 +443,7 @@ inline RowsArgs rows_args_base(const Engine* e) {
 inline cudaError_t launch_finalize(Engine* e, const RowsArgs& a, int rows, cudaStream_t st) {
   const bool ok = a.ws != nullptr && a.embed == nullptr && a.norm_w != nullptr &&
                   e->H % (4 * kRowCtas) == 0 && e->H / kRowCtas <= kRowClThreads * 4 * kRowClGroups;
-  // up to 128 rows (8 streams): one 1024-thread CTA per row -- no cluster exchange (R = 1 / 2 / 8: -10 / -7 / -14 us per
-  // step; flat at 4); more rows than SMs want the four-fold spread of each row's loads
+  // one 1024-thread CTA per row -- no cluster exchange -- whenever the row fits (hidden <= 4096)
   if (DFLASH_ROW_BLOCK && ok && e->H <= 4 * kRowBlkThreads && rows <= e->row_block_max_rows)
     return launch_pdl(finalize_rows_block_kernel, dim3(rows), dim3(kRowBlkThreads), 0, st, e->pdl, a);
   if (ok)
@@ -529,6 +528,8 @@ inline int enqueue_draft_step(Engine* e, const void* noise_embedding, bool run_l
     const int items = qa.rows * (e->Hq + 2 * e->Hkv);
     aa.k_cache = qa.k_cache;
     aa.v_cache = qa.v_cache;
+    // (four items per warp with their loads in flight together, for the ten waves of one-item CTAs at 64 streams: 170
+    // registers, 1563 / 4384 us per step at 16 / 64 streams against 1440 / 4112 -- occupancy is what hides the latency)
     DFL_CUDA(launch_pdl(qkv_post_kernel, dim3((items + kItemWarps - 1) / kItemWarps), dim3(32 * kItemWarps), 0, st,
                         e->pdl, qa), "qkv post");
     DFL_CUDA(launch_pdl(attn_split_kernel, dim3(e->nsplit_attn, e->Hkv, e->R * (e->SL / 16)), dim3(32 * group),

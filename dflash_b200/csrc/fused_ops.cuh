@@ -364,8 +364,11 @@ __global__ void __launch_bounds__(kRowClThreads) finalize_rows_cluster_kernel(co
 #ifndef DFLASH_ROW_BLOCK
 #define DFLASH_ROW_BLOCK 1
 #endif
-#ifndef DFLASH_ROW_BLOCK_MAX_ROWS   // rows up to which the one-CTA form is used (tuning switch)
-#define DFLASH_ROW_BLOCK_MAX_ROWS 128
+// rows up to which the one-CTA form is used (tuning switch). Measured better at every batch width -- 1 / 2 / 8 / 16 /
+// 32 / 64 streams: -10 / -7 / -14 / -11 / -6 / -100 us per step (at wide batches the cluster form's 4096 CTAs each
+// live for a cluster barrier) -- so the cluster form only serves hidden sizes above 4096.
+#ifndef DFLASH_ROW_BLOCK_MAX_ROWS
+#define DFLASH_ROW_BLOCK_MAX_ROWS (1 << 30)
 #endif
 constexpr int kRowBlkThreads = 1024;
 
@@ -515,10 +518,16 @@ __device__ __forceinline__ QkvItem qkv_post_prepare(const QkvPostArgs& a, int ro
   return it;
 }
 
-__device__ __forceinline__ void qkv_post_apply(const QkvPostArgs& a, const QkvItem& it, int lane) {
-  if (it.kind < 0) return;
+// the item's four fp32 sums per lane (the slots are L2 round trips: a warp that owns several items requests all of them
+// before it finishes the first)
+__device__ __forceinline__ float4 qkv_post_load(const QkvPostArgs& a, const QkvItem& it, int lane) {
+  if (it.kind < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
   // head hh covers output columns [hh*128, hh*128+128) = exactly stream-K tile hh
-  float4 xv = sum_slots_4(a.ws, a.sm, it.ws_row, it.hh * 128 + lane * 4, tile_slots32(it.hh, a.sm));
+  return sum_slots_4(a.ws, a.sm, it.ws_row, it.hh * 128 + lane * 4, tile_slots32(it.hh, a.sm));
+}
+
+__device__ __forceinline__ void qkv_post_finish(const QkvPostArgs& a, const QkvItem& it, float4 xv, int lane) {
+  if (it.kind < 0) return;
   if (a.bias != nullptr) {
     const float4 b = unpack4_bf16(*reinterpret_cast<const uint2*>(a.bias + it.hh * 128 + lane * 4));
     xv.x += b.x; xv.y += b.y; xv.z += b.z; xv.w += b.w;
@@ -544,6 +553,10 @@ __device__ __forceinline__ void qkv_post_apply(const QkvPostArgs& a, const QkvIt
     o[t] = bf16_round(bf16_round(x[t] * it.cs[t]) + bf16_round(rot * it.sn[t]));
   }
   *reinterpret_cast<uint2*>(it.dst + lane * 4) = pack4_bf16(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ void qkv_post_apply(const QkvPostArgs& a, const QkvItem& it, int lane) {
+  qkv_post_finish(a, it, qkv_post_load(a, it, lane), lane);
 }
 
 __device__ __forceinline__ void qkv_post_rowhead(const QkvPostArgs& a, int row, int hh, int lane) {

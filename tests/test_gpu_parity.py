@@ -995,6 +995,64 @@ def test_verify_with_given_posterior_and_stop_and_clamp():
 
 
 # ------------------------------------------------------------------------------------------------
+# hidden sizes above 4096 (Qwen3-14B / 32B width): the row pass takes its four-CTA cluster form there, the context
+# injection's row pass and the embedding rows their widest loops
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hidden,R,inject", [(5120, 1, True), (5120, 2, False), (8192, 1, True)])
+def test_wide_hidden_draft_vs_oracle(hidden, R, inject):
+    dev = _cuda()
+    from oracle import dflash_oracle as O
+    from dflash_b200 import DFlashDraftModel
+    from dflash_b200.engine import DraftEngine
+    from tests.tiny_models import TINY, build_pair, draft_state_dict
+    bs = 16
+    dims = dict(TINY, hidden=hidden, intermediate=1024, heads=4, kv_heads=2, vocab=1200)
+    target, draft = build_pair(DFlashDraftModel, seed=77, block_size=bs, dims=dims, dtype=torch.bfloat16, device=dev)
+    cfg = O.DraftConfig.from_hf(draft)
+    sd = draft_state_dict(draft)
+    H, V, nsel = dims["hidden"], dims["vocab"], len(draft.target_layer_ids)
+    g = torch.Generator(device=dev).manual_seed(3)
+    P = [19, 33][:R]
+    n_new = 4 * bs
+    eng = DraftEngine(draft, target.model.embed_tokens.weight, target.lm_head.weight, max_seq=max(P) + n_new + 3 * bs,
+                      out_len=max(P) + n_new + 2 * bs, max_requests=R, block_size=bs, keep_draft_logits=True)
+    caches = [O.DraftCache() for _ in range(R)]
+    starts, pend, first = list(P), [], [5 + r for r in range(R)]
+    for r in range(R):
+        hs = [(torch.randn(P[r], H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        eng.reset_request(r, torch.randint(0, V - 1, (P[r],), device=dev, generator=g), first[r], n_new)
+        eng.prefill_context(r, hs)
+        pend.append(torch.cat(hs, dim=-1))
+    blocks = [torch.tensor([first[r]] + [cfg.mask_token_id] * (bs - 1), device=dev) for r in range(R)]
+    forced = torch.tensor([[4, 0, bs - 1][r:] + [2] * r for r in range(R)], dtype=torch.int32, device=dev)
+    for cyc in range(3):
+        eng.draft_step()
+        torch.cuda.synchronize()
+        tl = torch.randn(R * bs, V, device=dev, generator=g).to(torch.bfloat16)
+        hsel = [(torch.randn(R * bs, H, device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(nsel)]
+        for r in range(R):
+            pos = torch.arange(caches[r].get_seq_length(), starts[r] + bs, device=dev).unsqueeze(0)
+            noise = target.model.embed_tokens(blocks[r].unsqueeze(0))
+            hid = O.draft_forward(sd, cfg, pend[r].unsqueeze(0), noise, pos, caches[r])
+            caches[r].crop(starts[r])
+            got = eng.hn[r * eng.SL: r * eng.SL + bs]
+            assert _rel_err(got, hid[0]) < REL_TOL, (cyc, r, _rel_err(got, hid[0]))
+        blk = eng.block_ids.clone()
+        eng.verify_step(tl, hsel, temperature=0.0, forced_k=forced, inject=inject)
+        torch.cuda.synchronize()
+        for r in range(R):
+            post = tl[r * bs:(r + 1) * bs].float().cpu().argmax(-1)
+            k = int(forced[r, cyc])
+            post[:k] = blk[r].cpu()[1:k + 1]
+            a = O.acceptance_length(blk[r].cpu().tolist(), post.tolist())
+            starts[r] += a + 1
+            assert int(eng.buf["start"][r]) == starts[r] and int(eng.buf["ctx_len"][r]) == a + 1
+            pend[r] = torch.cat([h[r * bs: r * bs + a + 1] for h in hsel], dim=-1)
+            blocks[r] = torch.tensor([int(post[a])] + [cfg.mask_token_id] * (bs - 1), device=dev)
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
 # the two forms of the context injection give the same draft: at the head of the draft step from gathered features, or
 # behind the verify kernel reading the hidden states in place (dflash_verify_inject_step / dflash_draft_step_injected)
 # ------------------------------------------------------------------------------------------------

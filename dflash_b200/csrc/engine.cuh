@@ -396,6 +396,7 @@ inline int engine_create(const dflash_config_t& c, const dflash_weights_t& w, vo
     cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(attn_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(verify_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(verify_fused_wide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(accept_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(ctx_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
@@ -716,7 +717,10 @@ inline int enqueue_verify_step(Engine* e, const VerifyInputs& v, cudaStream_t st
     int gy = rows;  // one CTA per (split, row); a narrower grid walks the rows
     if (rows <= e->sm_count && e->nsplit_post * rows > 2 * e->sm_count) gy = (2 * e->sm_count) / e->nsplit_post;
     gy = gy < 1 ? 1 : (gy > rows ? rows : gy);
-    DFL_CUDA(launch_pdl(verify_fused_kernel, dim3(e->nsplit_post, gy), dim3(256), 0, st, e->pdl, fa), "verify");
+    if (rows > e->sm_count)
+      DFL_CUDA(launch_pdl(verify_fused_wide_kernel, dim3(e->nsplit_post, gy), dim3(256), 0, st, e->pdl, fa), "verify");
+    else
+      DFL_CUDA(launch_pdl(verify_fused_kernel, dim3(e->nsplit_post, gy), dim3(256), 0, st, e->pdl, fa), "verify");
     if (inject) return enqueue_inject_direct(e, v.hidden, st);
     return DFLASH_OK;
   }

@@ -77,8 +77,10 @@ __device__ __forceinline__ void posterior_body(const PosteriorArgs& a, int row, 
             consider(f.x, c + 2 * j, rnd[2 * j]);
             consider(f.y, c + 2 * j + 1, rnd[2 * j + 1]);
           }
-        } else {
-          for (int j = 0; c + j < c1; ++j) consider(__bfloat162float(lp[c + j]), c + j, rnd[j]);
+        } else {  // (unrolled with constant indices: a runtime index would put rnd[] in local memory for every path)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c + j < c1) consider(__bfloat162float(lp[c + j]), c + j, rnd[j]);
         }
       }
     }
@@ -314,7 +316,17 @@ struct VerifyFusedArgs {
   unsigned int* counters;  // [R + 1] arrivals per request, then of the whole grid (self-resetting)
 };
 
-__global__ void __launch_bounds__(256, 4) verify_fused_kernel(const VerifyFusedArgs v) {
+// MINB = 4: at most 64 registers, which is what lets two CTAs per SM sit next to the context-injection kernel's CTA
+// (small batches: the overlap pays, and the spills this costs in the vocab loop are hidden under that kernel's fc
+// stream). MINB = 3: 85 registers (no spills in the loop), for wide batches, where the kernel reads 78-311 MB of logits and is on the critical path.
+template <int MINB>
+__device__ __forceinline__ void verify_fused_body(const VerifyFusedArgs& v);
+
+__global__ void __launch_bounds__(256, 4) verify_fused_kernel(const VerifyFusedArgs v) { verify_fused_body<4>(v); }
+__global__ void __launch_bounds__(256, 3) verify_fused_wide_kernel(const VerifyFusedArgs v) { verify_fused_body<3>(v); }
+
+template <int MINB>
+__device__ __forceinline__ void verify_fused_body(const VerifyFusedArgs& v) {
   // wait first, release second: the context-injection kernel behind this one starts its fc main loop without waiting
   // for this kernel, on the strength of "everything in front of the verify kernel (the target's forward, the draft
   // step) is complete once the verify kernel has released its dependent"

@@ -706,7 +706,25 @@ __device__ __forceinline__ void gemm_skinny_body(const CUtensorMap& tmW, const C
           for (int row = warp; row < a.tok_rows; row += Cfg::kEpiWarps) {
             float bv = -INFINITY;
             int bi = 0x7fffffff;
-            for (int g = lane; g < n_cta; g += 32) {
+            // (all of a lane's candidates requested before the first compare: this runs after the last weight byte, on
+            // the critical path in front of the target's forward -- one L2 round trip per row, not one per 32 CTAs)
+            constexpr int kMaxPerLane = 8;  // up to 256 CTAs
+            float cv[kMaxPerLane];
+            int ci[kMaxPerLane];
+#pragma unroll
+            for (int k = 0; k < kMaxPerLane; ++k) {
+              const int g = lane + 32 * k;
+              cv[k] = -INFINITY;
+              ci[k] = 0x7fffffff;
+              if (g < n_cta) {
+                cv[k] = __ldcg(a.cand_val + static_cast<long long>(g) * a.cand_ld + row);
+                ci[k] = __ldcg(a.cand_idx + static_cast<long long>(g) * a.cand_ld + row);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxPerLane; ++k)
+              if (cv[k] > bv || (cv[k] == bv && ci[k] < bi)) { bv = cv[k]; bi = ci[k]; }
+            for (int g = lane + 32 * kMaxPerLane; g < n_cta; g += 32) {
               const float v = __ldcg(a.cand_val + static_cast<long long>(g) * a.cand_ld + row);
               const int i = __ldcg(a.cand_idx + static_cast<long long>(g) * a.cand_ld + row);
               if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }

@@ -94,7 +94,9 @@ typedef struct dflash_weights {
 enum dflash_buffer_id {
   DFLASH_BUF_X = 0,        /* bf16 [R*SL, hidden] residual stream of the block rows */
   DFLASH_BUF_A_IN,         /* bf16 [2*R*SL, hidden] context rows then normed block rows */
-  DFLASH_BUF_CTX_FEAT,     /* bf16 [R*SL, n_sel*hidden] pending target-context features */
+  DFLASH_BUF_CTX_FEAT,     /* bf16 [R*SL, n_sel*hidden] pending target-context features (filled by the gathering forms
+                              only: dflash_verify_step, the candidate verify, forward(target_hidden=...);
+                              dflash_verify_inject_step reads the hidden states in place) */
   DFLASH_BUF_Q,            /* bf16 [R*SL, Hq, 128] */
   DFLASH_BUF_ATTN_OUT,     /* bf16 [R*SL, Hq*128] */
   DFLASH_BUF_A2,           /* bf16 [R*SL, hidden] */

@@ -209,7 +209,7 @@ class DraftEngine:
             max_seq=int(max_seq), out_len=int(out_len), hist_len=int(hist_len), rms_eps=float(cfg.rms_norm_eps),
             rope_scale=self.weights.rope_scale, mask_token_id=self.mask_token_id,
             attn_splits=int(os.environ.get("DFLASH_ATTN_SPLITS", attn_splits)),
-            post_splits=0, gemm_grid=int(os.environ.get("DFLASH_GEMM_GRID", gemm_grid)), use_pdl=int(use_pdl),
+            post_splits=int(os.environ.get("DFLASH_POST_SPLITS", 0)), gemm_grid=int(os.environ.get("DFLASH_GEMM_GRID", gemm_grid)), use_pdl=int(use_pdl),
             keep_draft_logits=int(keep_draft_logits), max_candidates=int(max_candidates))
         self.max_candidates = int(max_candidates)
         self.max_seq, self.out_len = int(max_seq), int(out_len)
